@@ -1,0 +1,209 @@
+"""CPU tests: the oracle against the reference's golden vectors and against fp64 autograd."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from dmgs_b200 import synthetic as S
+from oracle import oracle as O
+from oracle import torch_oracle as TO
+from util import cam_params, cov6_from_scale_rot, golden, rel_err, small_scene
+
+
+def test_exp_contract_accuracy():
+    x = np.concatenate([np.linspace(-90, 5, 200001), [-1e30, 0.0, -0.0, 100.0]]).astype(np.float32)
+    y = O.exp_array(x)
+    ref = np.exp(np.clip(x.astype(np.float64), -80, 80))
+    assert np.max(np.abs(y - ref) / ref) < 3e-7
+    assert O.exp_array(np.array([0.0], np.float32))[0] == 1.0
+
+
+def test_barycentric_golden():
+    g = golden("barycentric.npz")
+    for k in (1, 3, 6):
+        bc, rad = S.barycentric_layout(k)
+        assert np.array_equal(bc.numpy(), g[f"bc{k}"])
+        assert rad == float(g[f"rad{k}"])
+    assert math.isclose(S.barycentric_layout(3)[1], 0.18301270189221933)
+    assert math.isclose(S.barycentric_layout(6)[1], 0.13397459621556135)
+
+
+def test_camera_golden():
+    g = golden("camera.npz")
+    Rt = np.zeros((4, 4))
+    Rt[:3, :3] = g["R"].T
+    Rt[:3, 3] = g["T"]
+    Rt[3, 3] = 1
+    c2w = np.linalg.inv(Rt)
+    c2w[:3, 1:3] *= -1  # camera_from_c2w takes the OpenGL convention
+    cam = S.camera_from_c2w(c2w, 100, 80, float(g["fovx"]), float(g["fovy"]))
+    assert np.allclose(cam.world_view_transform.numpy(), g["world_view"], atol=1e-6)
+    assert np.allclose(cam.full_proj_transform.numpy(), g["full_proj"], atol=1e-5)
+    assert np.allclose(cam.camera_center.numpy(), g["center"], atol=1e-5)
+
+
+@pytest.mark.parametrize("k", [1, 3, 6])
+@pytest.mark.parametrize("adaptive", [True, False])
+def test_binding_stage2_golden(k, adaptive):
+    g = golden("binding_stage2.npz")
+    tag = f"k{k}_{'adp' if adaptive else 'iso'}"
+    bc, rad = S.barycentric_layout(k)
+    sf = float(g[f"{tag}_scale_factor"][0])
+    gscale = math.tanh(sf) * 2
+    out = O.bind_forward(g[f"{tag}_verts"], g[f"{tag}_faces"], bc.numpy(), rad, 4.43 * 1e-6, gscale, adaptive)
+    assert np.allclose(out["xyz"], g[f"{tag}_xyz"], rtol=1e-5, atol=1e-6)
+    assert np.allclose(out["rot_t2w"], g[f"{tag}_rot_t2w"], atol=2e-6)
+    assert np.allclose(out["cov3D_L"], g[f"{tag}_cov3D_L"], rtol=2e-5, atol=1e-9)
+    assert rel_err(out["cov6"], g[f"{tag}_cov6"]) < 2e-6
+    bw = O.bind_backward(g[f"{tag}_verts"], g[f"{tag}_faces"], bc.numpy(), rad, 4.43 * 1e-6, gscale,
+                         g[f"{tag}_gxyz"], g[f"{tag}_gcov"], adaptive)
+    assert rel_err(bw["dverts"], g[f"{tag}_dverts"]) < 2e-5
+    dsf = bw["dg"] * 2 * (1 - math.tanh(sf) ** 2)
+    assert abs(dsf - float(g[f"{tag}_dscale_factor"][0])) <= 2e-5 * abs(float(g[f"{tag}_dscale_factor"][0]))
+
+
+def test_affine_known_answers():
+    # geo/affine_verify.ipynb cells 0-1 (example B), 4-dp values from the notebook
+    verts = np.array([[0, 0, 0], [0.0038, 0, 0], [0.0011, 0.0035, 0]], np.float32)
+    bc, rad = S.barycentric_layout(6)
+    out = O.bind_forward(verts, np.array([[0, 1, 2]]), bc.numpy(), rad, 4.43e-6, 1.0, True)
+    L = out["cov3D_L"][0]
+    assert np.allclose(np.round(L[:2, :2], 4), [[0.0005, -0.0001], [0.0, 0.0005]])
+    assert np.allclose(L, golden("binding_stage2.npz")["affineB_cov3D_L"][0], rtol=1e-5, atol=1e-10)
+    # geo/affine_proto.ipynb cells 0-1 (example A): M_2d for tri (0,0),(1,0),(0.9,0.6)
+    verts = np.array([[0, 0, 0], [1, 0, 0], [0.9, 0.6, 0]], np.float32)
+    out = O.bind_forward(verts, np.array([[0, 1, 2]]), bc.numpy(), rad, 0.0, 1.0, True)
+    M = out["cov3D_L"][0][:2, :2] / rad  # l = 1
+    h = math.sqrt(3) / 2
+    assert np.allclose(M, [[1, (0.9 - 0.5) / h], [0, 0.6 / h]], rtol=1e-5)
+
+
+def _sh_scene(P):
+    # camera far enough that every golden point is visible
+    g = golden("eval_sh.npz")
+    cam = S.look_at_camera([0.0, -9.0, 0.0], 64, 64, fovx=1.2)
+    return g, cam
+
+
+@pytest.mark.parametrize("deg", [0, 1, 2, 3])
+@pytest.mark.parametrize("act", [0, 1])
+def test_eval_sh_golden(deg, act):
+    g, cam = _sh_scene(64)
+    P = g["xyz"].shape[0]
+    pr = cam_params(cam, P, [0, 0, 0], sh_degree=deg, sh_layout=1, sh_act=act)
+    pr.campos[:] = [float(v) for v in g["campos"]]  # colour uses campos only
+    geom = O.preprocess(pr, g["xyz"], np.full((P, 1), 0.5, np.float32), scales=np.full((P, 3), 0.01, np.float32),
+                        rotations=np.tile(np.array([[1, 0, 0, 0]], np.float32), (P, 1)), shs=g["features"])
+    vis = geom["radii"] > 0
+    assert vis.sum() > P // 2
+    want = g[f"{'clamp' if act == 0 else 'sigmoid'}{deg}"]
+    assert np.allclose(geom["rgb"][vis], want[vis], atol=2e-6)
+    # same numbers through the [P,M,3] rasteriser layout
+    pr2 = cam_params(cam, P, [0, 0, 0], sh_degree=deg, sh_layout=0, sh_act=act)
+    pr2.campos[:] = [float(v) for v in g["campos"]]
+    geom2 = O.preprocess(pr2, g["xyz"], np.full((P, 1), 0.5, np.float32), scales=np.full((P, 3), 0.01, np.float32),
+                         rotations=np.tile(np.array([[1, 0, 0, 0]], np.float32), (P, 1)),
+                         shs=np.ascontiguousarray(g["features"].transpose(0, 2, 1)))
+    assert np.array_equal(geom["rgb"], geom2["rgb"])
+    # and the fp64 restatement
+    t = TO.eval_sh_colors(deg, torch.tensor(g["features"]).double().transpose(1, 2), torch.tensor(g["xyz"]).double(),
+                          torch.tensor(g["campos"]).double(), act)
+    assert np.allclose(t.numpy(), want, atol=1e-6)
+    assert np.all(g["zero"] == 0)
+
+
+def test_cov_layout_golden():
+    g = golden("cov_layout.npz")
+    q = g["q"] / np.linalg.norm(g["q"], axis=1, keepdims=True)  # callers normalise (gaussian_model.py:101)
+    P = q.shape[0]
+    cam = S.look_at_camera([0.0, -6.0, 0.0], 64, 64, fovx=1.2)
+    pr = cam_params(cam, P, [0, 0, 0])
+    xyz = np.zeros((P, 3), np.float32)
+    xyz[:, 0] = np.linspace(-1, 1, P)
+    geom = O.preprocess(pr, xyz, np.full((P, 1), 0.5, np.float32), scales=g["s"], rotations=q.astype(np.float32),
+                        colors_precomp=np.zeros((P, 3), np.float32))
+    assert (geom["radii"] > 0).all()
+    assert rel_err(geom["cov3D"], g["cov6"]) < 2e-6
+
+
+MODES = ["sh_scale_rot", "precomp", "sigmoid_features"]
+
+
+def _mode_inputs(mode, cl, P):
+    if mode == "sh_scale_rot":
+        return dict(scales=cl["scales"], rotations=cl["rotations"], shs=cl["shs"]), {}
+    if mode == "precomp":
+        col = torch.rand(P, 3, generator=torch.Generator().manual_seed(9))
+        return dict(cov3D_precomp=cov6_from_scale_rot(cl["scales"], cl["rotations"]), colors_precomp=col), {}
+    feats = cl["shs"].transpose(1, 2).contiguous()
+    return dict(scales=cl["scales"], rotations=cl["rotations"], shs=feats), dict(sh_layout=1, sh_act=1, sh_degree=2)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_c_oracle_matches_fp64_autograd(mode):
+    cam, cl = small_scene()
+    P, W, H = cl["means3D"].shape[0], cam.image_width, cam.image_height
+    inp, pk = _mode_inputs(mode, cl, P)
+    bg = np.array([0.2, 0.5, 0.7], np.float32)
+    pr = cam_params(cam, P, bg, **pk)
+    npin = {k: v.numpy() for k, v in inp.items()}
+    fwd = O.render_forward(pr, cl["means3D"].numpy(), cl["opacities"].numpy(), **npin)
+    assert fwd["bins"]["R"] > 500
+    m3 = cl["means3D"].double().requires_grad_()
+    op = cl["opacities"].double().requires_grad_()
+    tin = {k: v.double().requires_grad_() for k, v in inp.items()}
+    img, inter = TO.render(W, H, pr.tanfovx, pr.tanfovy, torch.tensor(bg), cam.world_view_transform,
+                           cam.full_proj_transform, cam.camera_center, m3, op, **tin, **pk)
+    assert np.array_equal(fwd["geom"]["radii"], inter["radii"].numpy())
+    assert np.abs(fwd["img"]["color"] - img.detach().numpy()).max() < 5e-6
+    assert np.abs(fwd["img"]["final_T"] - inter["final_T"].detach().numpy()).max() < 5e-6
+    dL = torch.randn(3, H, W, generator=torch.Generator().manual_seed(5))
+    (img * dL.double()).sum().backward()
+    bw = O.render_backward(pr, fwd, dL.numpy(), cl["means3D"].numpy(), scales=npin.get("scales"),
+                           rotations=npin.get("rotations"), shs=npin.get("shs"),
+                           precomp_color="colors_precomp" in npin)
+    assert rel_err(bw["dL_dmeans3D"], m3.grad) < 2e-5
+    assert rel_err(bw["dL_dopacity"], op.grad) < 2e-5
+    if "scales" in tin:
+        assert rel_err(bw["dL_dscales"], tin["scales"].grad) < 2e-5
+        assert rel_err(bw["dL_drotations"], tin["rotations"].grad) < 2e-5
+    if "shs" in tin:
+        assert rel_err(bw["dL_dshs"], tin["shs"].grad) < 2e-5
+    if "cov3D_precomp" in tin:
+        assert rel_err(bw["dL_dcov3D"], tin["cov3D_precomp"].grad) < 2e-5
+        assert rel_err(bw["dL_dcolors_precomp"], tin["colors_precomp"].grad) < 2e-5
+
+
+def test_binning_properties():
+    cam, cl = small_scene(P=2000, W=160, H=96, scale=0.05)
+    P = 2000
+    pr = cam_params(cam, P, [0, 0, 0])
+    geom = O.preprocess(pr, cl["means3D"].numpy(), cl["opacities"].numpy(), scales=cl["scales"].numpy(),
+                        rotations=cl["rotations"].numpy(), shs=cl["shs"].numpy())
+    b = O.binning(pr, geom)
+    assert b["R"] == int(geom["tiles_touched"].sum())
+    assert np.all(np.diff(b["keys"].astype(np.uint64)) >= 0)
+    tiles = (b["keys"] >> np.uint64(32)).astype(np.int64)
+    for t in np.unique(tiles):
+        s, e = b["ranges"][t]
+        assert np.all(tiles[s:e] == t) and (s == 0 or tiles[s - 1] != t) and (e == b["R"] or tiles[e] != t)
+    empty = np.setdiff1d(np.arange(b["ranges"].shape[0]), np.unique(tiles))
+    assert np.all(b["ranges"][empty] == 0)
+    # ties (same tile, same depth bits) come out in ascending Gaussian index
+    same = np.diff(b["keys"].astype(np.uint64)) == 0
+    assert np.all(np.diff(b["vals"].astype(np.int64))[same] > 0)
+    # depth bits of the key are the Gaussian's depth
+    assert np.array_equal((b["keys"] & np.uint64(0xFFFFFFFF)).astype(np.uint32),
+                          geom["depths"][b["vals"]].view(np.uint32))
+
+
+def test_empty_and_culled_inputs():
+    cam, cl = small_scene(P=50)
+    pr = cam_params(cam, 50, [0.1, 0.2, 0.3])
+    behind = cl["means3D"].numpy() * 0 + np.array([[10.0, 4.0, 4.8]], np.float32)  # behind the camera
+    fwd = O.render_forward(pr, behind, cl["opacities"].numpy(), scales=cl["scales"].numpy(),
+                           rotations=cl["rotations"].numpy(), shs=cl["shs"].numpy())
+    assert fwd["bins"]["R"] == 0 and (fwd["geom"]["radii"] == 0).all()
+    assert np.allclose(fwd["img"]["color"], np.array([0.1, 0.2, 0.3], np.float32)[:, None, None])
+    assert (fwd["img"]["n_contrib"] == 0).all() and (fwd["img"]["final_T"] == 1).all()

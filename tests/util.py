@@ -1,0 +1,52 @@
+"""Shared helpers for the tests: scene builders and oracle parameter packing."""
+import math
+import os
+
+import numpy as np
+import torch
+
+from dmgs_b200 import synthetic as S
+from oracle import oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def cam_params(cam, P, bg, **kw):
+    return O.make_params(P, cam.image_width, cam.image_height, math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5),
+                         bg, cam.world_view_transform.numpy(), cam.full_proj_transform.numpy(),
+                         cam.camera_center.numpy(), **kw)
+
+
+def small_scene(P=300, W=64, H=48, seed=3, scale=0.08, extent=1.0):
+    cam = S.look_at_camera([2.5, 1.0, 1.2], W, H, fovx=0.9)
+    cl = S.random_cloud(P, seed=seed, extent=extent, log_scale_mean=math.log(scale))
+    return cam, cl
+
+
+def cov6_from_scale_rot(scales, rotations):
+    """utils/general_utils.py:78-110 semantics without the internal normalisation (unit quats given)."""
+    from oracle import torch_oracle as TO
+    R = TO.quat_to_rot(rotations.double())
+    M = R @ torch.diag_embed(scales.double())
+    Sg = M @ M.transpose(1, 2)
+    return torch.stack([Sg[:, 0, 0], Sg[:, 0, 1], Sg[:, 0, 2], Sg[:, 1, 1], Sg[:, 1, 2], Sg[:, 2, 2]], 1).float()
+
+
+def rel_err(a, b):
+    a = np.asarray(a, np.float64).reshape(-1)
+    b = np.asarray(b, np.float64).reshape(-1)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+def grad_close(got, ref, rtol=1e-4, name=""):
+    """|got-ref| <= rtol * max(|ref|, floor) elementwise, floor = 1e-3 * RMS of the reference tensor
+    (sums of many fp32 terms of mixed sign cannot be relative-accurate near zero)."""
+    got = np.asarray(got, np.float64)
+    ref = np.asarray(ref, np.float64)
+    floor = 1e-3 * (np.sqrt(np.mean(ref ** 2)) + 1e-30)
+    bad = np.abs(got - ref) > rtol * np.maximum(np.abs(ref), floor)
+    assert not bad.any(), f"{name}: {bad.sum()} / {bad.size} elements off; worst abs {np.abs(got - ref).max():.3e}"
