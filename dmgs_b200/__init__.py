@@ -1,0 +1,4 @@
+"""dmgs_b200 -- B200-native rasteriser + mesh binding for DMGS."""
+from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer  # noqa: F401
+
+__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer"]

@@ -1,0 +1,248 @@
+// api.cu -- the extern "C" surface declared in include/dmgs_raster.h.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace dmgs {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_stage(const dmgs_params *prm, cudaStream_t s, const char *stage)
+{
+    if (!prm || !prm->debug) return 0;
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("stage '%s' failed: %s", stage, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+static int tile_bits(int T)
+{
+    int b = 0;
+    while ((1 << b) < T) ++b;
+    return b;
+}
+
+static int validate(const dmgs_params *p)
+{
+    if (!p) { set_error("params is NULL"); return -1; }
+    if (p->P < 0 || p->image_width <= 0 || p->image_height <= 0) { set_error("bad sizes P=%d W=%d H=%d", p->P, p->image_width, p->image_height); return -2; }
+    if (p->image_width > 65535 * DMGS_TILE || p->image_height > 65535 * DMGS_TILE) { set_error("image too large"); return -2; }
+    if (p->sh_degree < 0 || p->sh_degree > 3) { set_error("sh_degree %d not in 0..3", p->sh_degree); return -3; }
+    return 0;
+}
+
+}  // namespace dmgs
+
+using namespace dmgs;
+
+extern "C" {
+
+int dmgs_abi_version(void) { return 1; }
+const char *dmgs_last_error(void) { return g_err; }
+
+size_t dmgs_geom_bytes(int32_t P) { return geom_layout(P).total; }
+size_t dmgs_binning_bytes(int32_t P, int64_t R, int32_t W, int32_t H) { return bin_layout(P, R, W, H).total; }
+size_t dmgs_image_bytes(int32_t W, int32_t H) { return img_layout(W, H).total; }
+size_t dmgs_backward_scratch_bytes(int32_t P) { return align_up((size_t)(P > 0 ? P : 1) * 12 * sizeof(float)); }
+
+int dmgs_geom_layout(int32_t P, int64_t *o)
+{
+    const GeomLayout L = geom_layout(P);
+    o[0] = L.depths; o[1] = L.rec; o[2] = L.rgb; o[3] = L.clamped; o[4] = L.cov3D; o[5] = L.tiles; o[6] = L.rect;
+    o[7] = L.order; o[8] = L.offsets;
+    return 0;
+}
+int dmgs_binning_layout(int32_t P, int64_t R, int32_t W, int32_t H, int64_t *o)
+{
+    const BinLayout L = bin_layout(P, R, W, H);
+    o[0] = L.tiles; o[1] = L.gidx; o[2] = L.ranges;
+    return 0;
+}
+int dmgs_image_layout(int32_t W, int32_t H, int64_t *o)
+{
+    const ImgLayout L = img_layout(W, H);
+    o[0] = L.final_T; o[1] = L.n_contrib;
+    return 0;
+}
+
+int dmgs_preprocess_forward(const dmgs_params *prm, const float *means3D, const float *scales, const float *rotations,
+                            const float *cov3D_precomp, const float *opacities, const float *shs,
+                            const float *colors_precomp, int32_t *radii, void *geom, uint32_t *num_rendered,
+                            void *stream)
+{
+    int rc = validate(prm);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((shs == nullptr) == (colors_precomp == nullptr)) { set_error("provide exactly one of shs / colors_precomp"); return -4; }
+    if (((scales == nullptr) || (rotations == nullptr)) == (cov3D_precomp == nullptr)) {
+        set_error("provide exactly one of (scales, rotations) / cov3D_precomp");
+        return -5;
+    }
+    if (!num_rendered) { set_error("num_rendered is NULL"); return -6; }
+    const int P = prm->P;
+    if (P == 0) {
+        DMGS_CUDA(cudaMemsetAsync(num_rendered, 0, sizeof(uint32_t), s));
+        return 0;
+    }
+    if (!means3D || !opacities || !radii || !geom) { set_error("NULL required pointer"); return -6; }
+    const GeomLayout L = geom_layout(P);
+    rc = launch_preprocess_fwd(prm, means3D, scales, rotations, cov3D_precomp, opacities, shs, colors_precomp, radii,
+                               geom, L, s);
+    if (rc) return rc;
+    if ((rc = check_stage(prm, s, "preprocess"))) return rc;
+    // stable depth sort of the Gaussians: keys_a/order -> (4 passes) -> keys_a/order
+    uint32_t *ka = at<uint32_t>(geom, L.keys_a), *kb = at<uint32_t>(geom, L.keys_b);
+    uint32_t *va = at<uint32_t>(geom, L.order), *vb = at<uint32_t>(geom, L.vals_b);
+    uint32_t *hist = at<uint32_t>(geom, L.hist), *tmp = at<uint32_t>(geom, L.scan_tmp);
+    for (int pass = 0; pass < 4; ++pass) {
+        rc = (pass & 1) ? radix_pass(kb, vb, ka, va, P, 8 * pass, 8, hist, tmp, s)
+                        : radix_pass(ka, va, kb, vb, P, 8 * pass, 8, hist, tmp, s);
+        if (rc) return rc;
+    }
+    if ((rc = check_stage(prm, s, "depth sort"))) return rc;
+    rc = exclusive_scan_u32(at<uint32_t>(geom, L.tiles), va, at<uint32_t>(geom, L.offsets), P, num_rendered, tmp, s);
+    if (rc) return rc;
+    return check_stage(prm, s, "tile scan");
+}
+
+int dmgs_bin_forward(const dmgs_params *prm, const void *geom, int64_t R, void *binning, void *stream)
+{
+    int rc = validate(prm);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int P = prm->P, W = prm->image_width, H = prm->image_height;
+    const int gx = (W + DMGS_TILE - 1) / DMGS_TILE, gy = (H + DMGS_TILE - 1) / DMGS_TILE, T = gx * gy;
+    if (R < 0 || R >= ((int64_t)1 << 31)) { set_error("num_rendered %lld out of range", (long long)R); return -7; }
+    if (!binning) { set_error("binning buffer is NULL"); return -6; }
+    const GeomLayout GL = geom_layout(P);
+    const BinLayout BL = bin_layout(P, R, W, H);
+    uint32_t *ta = at<uint32_t>(binning, BL.tiles), *tb = at<uint32_t>(binning, BL.tiles_b);
+    uint32_t *ga = at<uint32_t>(binning, BL.gidx), *gb = at<uint32_t>(binning, BL.gidx_b);
+    uint32_t *hist = at<uint32_t>(binning, BL.hist), *tmp = at<uint32_t>(binning, BL.scan_tmp);
+    if (R > 0 && P > 0) {
+        const int tbits = tile_bits(T);
+        int nbits[2] = {0, 0}, npass = 0;
+        if (tbits > 8) { nbits[0] = (tbits + 1) / 2; nbits[1] = tbits - nbits[0]; npass = 2; }
+        else if (tbits > 0) { nbits[0] = tbits; npass = 1; }
+        // emit into the buffer that makes the last pass land in (tiles, gidx)
+        uint32_t *ek = (npass & 1) ? tb : ta, *ev = (npass & 1) ? gb : ga;
+        rc = launch_emit_instances(P, at<uint32_t>(geom, GL.order), at<uint32_t>(geom, GL.offsets),
+                                   at<uint32_t>(geom, GL.tiles), at<uint2>(geom, GL.rect), gx, ek, ev, s);
+        if (rc) return rc;
+        if ((rc = check_stage(prm, s, "emit instances"))) return rc;
+        uint32_t *ck = ek, *cv = ev;
+        int shift = 0;
+        for (int pass = 0; pass < npass; ++pass) {
+            uint32_t *ok = (ck == ta) ? tb : ta, *ov = (cv == ga) ? gb : ga;
+            rc = radix_pass(ck, cv, ok, ov, R, shift, nbits[pass], hist, tmp, s);
+            if (rc) return rc;
+            shift += nbits[pass];
+            ck = ok; cv = ov;
+        }
+        if ((rc = check_stage(prm, s, "tile partition"))) return rc;
+    }
+    rc = launch_tile_ranges(R, ta, at<uint2>(binning, BL.ranges), T, s);
+    if (rc) return rc;
+    return check_stage(prm, s, "tile ranges");
+}
+
+int dmgs_blend_forward(const dmgs_params *prm, const void *geom, const void *binning, int64_t R, float *out_color,
+                       void *image, void *stream)
+{
+    int rc = validate(prm);
+    if (rc) return rc;
+    if (!out_color || !image || !binning) { set_error("NULL required pointer"); return -6; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const GeomLayout GL = geom_layout(prm->P);
+    const BinLayout BL = bin_layout(prm->P, R, prm->image_width, prm->image_height);
+    const ImgLayout IL = img_layout(prm->image_width, prm->image_height);
+    rc = launch_blend_fwd(prm, geom, GL, binning, BL, out_color, image, IL, s);
+    if (rc) return rc;
+    return check_stage(prm, s, "blend forward");
+}
+
+int dmgs_backward(const dmgs_params *prm, const float *means3D, const float *scales, const float *rotations,
+                  const float *cov3D_precomp, const float *shs, const int32_t *radii, const void *geom,
+                  const void *binning, const void *image, int64_t R, const float *dL_dpix, float *dL_dmeans3D,
+                  float *dL_dmeans2D, float *dL_dopacity, float *dL_dcolors_precomp, float *dL_dshs, float *dL_dscales,
+                  float *dL_drotations, float *dL_dcov3D, void *scratch, void *stream)
+{
+    int rc = validate(prm);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int P = prm->P;
+    if (P == 0) return 0;
+    if (!means3D || !radii || !geom || !binning || !image || !dL_dpix || !dL_dmeans3D || !dL_dmeans2D || !dL_dopacity || !scratch) {
+        set_error("NULL required pointer");
+        return -6;
+    }
+    const GeomLayout GL = geom_layout(P);
+    const BinLayout BL = bin_layout(P, R, prm->image_width, prm->image_height);
+    const ImgLayout IL = img_layout(prm->image_width, prm->image_height);
+    float *grad_blend = (float *)scratch;
+    DMGS_CUDA(cudaMemsetAsync(grad_blend, 0, (size_t)P * 12 * sizeof(float), s));
+    if (R > 0) {
+        rc = launch_blend_bwd(prm, geom, GL, binning, BL, image, IL, dL_dpix, grad_blend, s);
+        if (rc) return rc;
+        if ((rc = check_stage(prm, s, "blend backward"))) return rc;
+    }
+    rc = launch_preprocess_bwd(prm, means3D, scales, rotations, cov3D_precomp, shs, radii, geom, GL, grad_blend,
+                               dL_dmeans3D, dL_dmeans2D, dL_dopacity, dL_dcolors_precomp, dL_dshs, dL_dscales,
+                               dL_drotations, dL_dcov3D, s);
+    if (rc) return rc;
+    return check_stage(prm, s, "preprocess backward");
+}
+
+int dmgs_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,
+                      uint8_t *visible, void *stream)
+{
+    (void)projmatrix;
+    if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !visible))) { set_error("bad arguments"); return -6; }
+    return launch_mark_visible(P, means3D, viewmatrix, visible, (cudaStream_t)stream);
+}
+
+int dmgs_bind_forward(int64_t F, int32_t k, const float *verts, const int64_t *faces, const float *bc, float rad_base,
+                      float thin_z, const float *g, int32_t adaptive, float *xyz, float *cov6, float *rot_t2w, void *stream)
+{
+    if (F < 0 || k <= 0 || (F > 0 && (!verts || !faces || !bc))) { set_error("bad arguments"); return -6; }
+    return launch_bind_fwd(F, k, verts, faces, bc, rad_base, thin_z, g, adaptive, xyz, cov6, rot_t2w, (cudaStream_t)stream);
+}
+
+int dmgs_bind_backward(int64_t F, int32_t k, const float *verts, const int64_t *faces, const float *bc, float rad_base,
+                       float thin_z, const float *g, int32_t adaptive, const float *dL_dxyz, const float *dL_dcov6,
+                       const float *dL_drot, float *dverts, float *dg, void *stream)
+{
+    if (F < 0 || k <= 0 || (F > 0 && (!verts || !faces || !bc || !dverts))) { set_error("bad arguments"); return -6; }
+    return launch_bind_bwd(F, k, verts, faces, bc, rad_base, thin_z, g, adaptive, dL_dxyz, dL_dcov6, dL_drot, dverts,
+                           dg, (cudaStream_t)stream);
+}
+
+int dmgs_sorted_keys(const void *geom, const void *binning, int32_t P, int64_t R, int32_t W, int32_t H,
+                     uint64_t *keys_out, void *stream)
+{
+    const GeomLayout GL = geom_layout(P);
+    const BinLayout BL = bin_layout(P, R, W, H);
+    return launch_sorted_keys(R, at<uint32_t>(binning, BL.tiles), at<uint32_t>(binning, BL.gidx),
+                              at<float>(geom, GL.depths), keys_out, (cudaStream_t)stream);
+}
+
+int dmgs_exp_array(const float *x, float *y, int64_t n, void *stream)
+{
+    return launch_exp_array(x, y, n, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,164 @@
+// common.cuh -- shared device helpers, state-buffer layouts and error plumbing.
+//
+// Arithmetic contract: the translation units are compiled with
+// -fmad=false, so `a*b+c` is never contracted; every fused multiply-add is an explicit
+// __fmaf_rn().  Division and sqrt are the IEEE-rounded defaults (no --use_fast_math), and
+// exp() is dmgs_exp() below, a fixed sequence of IEEE operations.  The CPU oracle
+// (oracle/splat_oracle.c) is written independently to the same contract; that is what
+// makes keys, tile ranges, radii and contributor counts comparable bit for bit.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/dmgs_raster.h"
+
+#define DMGS_TILE 16
+#define DMGS_NEAR 0.2f
+
+namespace dmgs {
+
+// ----------------------------------------------------------------------------- errors
+void set_error(const char *fmt, ...);
+int check_stage(const dmgs_params *prm, cudaStream_t s, const char *stage);
+
+#define DMGS_CUDA(call)                                                              \
+    do {                                                                             \
+        cudaError_t e__ = (call);                                                    \
+        if (e__ != cudaSuccess) {                                                    \
+            dmgs::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                            __FILE__, __LINE__);                                     \
+            return (int)e__;                                                         \
+        }                                                                            \
+    } while (0)
+
+// ----------------------------------------------------------------------------- layouts
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct GeomLayout {
+    size_t depths, rec, rgb, clamped, cov3D, tiles, rect, order, offsets;  // inspection arrays
+    size_t keys_a, keys_b, vals_b, hist, scan_tmp, total;
+    int sort_blocks;
+};
+struct BinLayout {
+    size_t tiles, gidx, ranges;  // inspection arrays (final sorted list)
+    size_t tiles_b, gidx_b, hist, scan_tmp, total;
+    int sort_blocks;
+};
+struct ImgLayout {
+    size_t final_T, n_contrib, total;
+};
+
+constexpr int SORT_ITEMS_PER_BLOCK = 8192;  // 256 threads x 32 rounds
+constexpr int SORT_MAX_BINS = 256;
+
+static inline size_t scan_tmp_bytes(size_t n) { return align_up((n / 2048 + 2) * sizeof(uint32_t) * 2); }
+
+static inline GeomLayout geom_layout(int32_t P)
+{
+    GeomLayout L;
+    size_t n = (size_t)(P > 0 ? P : 1), o = 0;
+    L.depths = o;  o += align_up(n * 4);
+    L.rec = o;     o += align_up(n * 32);
+    L.rgb = o;     o += align_up(n * 16);
+    L.clamped = o; o += align_up(n);
+    L.cov3D = o;   o += align_up(n * 24);
+    L.tiles = o;   o += align_up(n * 4);
+    L.rect = o;    o += align_up(n * 8);
+    L.order = o;   o += align_up(n * 4);
+    L.offsets = o; o += align_up(n * 4);
+    L.keys_a = o;  o += align_up(n * 4);
+    L.keys_b = o;  o += align_up(n * 4);
+    L.vals_b = o;  o += align_up(n * 4);
+    L.sort_blocks = (int)((n + SORT_ITEMS_PER_BLOCK - 1) / SORT_ITEMS_PER_BLOCK);
+    size_t hist_n = (size_t)L.sort_blocks * SORT_MAX_BINS + 1;
+    L.hist = o;    o += align_up(hist_n * 4);
+    size_t big = hist_n > n ? hist_n : n;
+    L.scan_tmp = o; o += scan_tmp_bytes(big);
+    L.total = o;
+    return L;
+}
+
+static inline BinLayout bin_layout(int32_t P, int64_t R, int32_t W, int32_t H)
+{
+    (void)P;
+    BinLayout L;
+    size_t n = (size_t)(R > 0 ? R : 1), o = 0;
+    size_t T = (size_t)((W + DMGS_TILE - 1) / DMGS_TILE) * ((H + DMGS_TILE - 1) / DMGS_TILE);
+    L.tiles = o;   o += align_up(n * 4);
+    L.gidx = o;    o += align_up(n * 4);
+    L.ranges = o;  o += align_up(T * 8);
+    L.tiles_b = o; o += align_up(n * 4);
+    L.gidx_b = o;  o += align_up(n * 4);
+    L.sort_blocks = (int)((n + SORT_ITEMS_PER_BLOCK - 1) / SORT_ITEMS_PER_BLOCK);
+    size_t hist_n = (size_t)L.sort_blocks * SORT_MAX_BINS + 1;
+    L.hist = o;    o += align_up(hist_n * 4);
+    L.scan_tmp = o; o += scan_tmp_bytes(hist_n);
+    L.total = o;
+    return L;
+}
+
+static inline ImgLayout img_layout(int32_t W, int32_t H)
+{
+    ImgLayout L;
+    size_t n = (size_t)W * H, o = 0;
+    L.final_T = o;   o += align_up(n * 4);
+    L.n_contrib = o; o += align_up(n * 4);
+    L.total = o;
+    return L;
+}
+
+template <typename T> static inline T *at(void *base, size_t off) { return reinterpret_cast<T *>((char *)base + off); }
+template <typename T> static inline const T *at(const void *base, size_t off)
+{
+    return reinterpret_cast<const T *>((const char *)base + off);
+}
+
+// ----------------------------------------------------------------------------- device math
+#ifdef __CUDACC__
+__device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ float dot3(float a0, float b0, float a1, float b1, float a2, float b2)
+{
+    return fma_(a2, b2, fma_(a1, b1, a0 * b0));
+}
+// row r of a column-major 4x4 applied to (x, y, z, 1)
+__device__ __forceinline__ float affine3(const float *m, int r, float x, float y, float z)
+{
+    return dot3(m[r], x, m[4 + r], y, m[8 + r], z) + m[12 + r];
+}
+
+// exp(x): clamp to [-80, 80], Cody-Waite reduction by ln2, degree-6 Horner, exponent insert.
+__device__ __forceinline__ float dmgs_exp(float x)
+{
+    x = fminf(fmaxf(x, -80.0f), 80.0f);
+    const float t = x * 1.44269502162933349609375f;
+    const float r = t + 12582912.0f;
+    const float jf = r - 12582912.0f;
+    const int j = __float_as_int(r) - 0x4B400000;
+    float f = fma_(jf, -0.693145751953125f, x);
+    f = fma_(jf, -1.42860682030941723212e-6f, f);
+    float p = 0x1.6d8360p-10f;
+    p = fma_(p, f, 0x1.127dd8p-7f);
+    p = fma_(p, f, 0x1.55549ep-5f);
+    p = fma_(p, f, 0x1.5553e8p-3f);
+    p = fma_(p, f, 0.5f);
+    p = fma_(p, f, 1.0f);
+    p = fma_(p, f, 1.0f);
+    return __int_as_float(__float_as_int(p) + (j << 23));
+}
+
+__device__ __forceinline__ int clampi_f(float v, int hi) { return (int)fminf(fmaxf(v, 0.0f), (float)hi); }
+
+// per-launch constants shared by the per-Gaussian kernels
+struct DevParams {
+    int P, sh_degree, M, W, H, sh_layout, sh_act;
+    int gx, gy;
+    float tanfovx, tanfovy, fx, fy, limx, limy, mod;
+    float bg[3];
+    float V[16];
+    float PV[16];
+    float cam[3];
+};
+#endif
+
+}  // namespace dmgs

@@ -1,0 +1,48 @@
+// kernels.cuh -- launcher declarations shared by the translation units of libdmgs_raster.so.
+#pragma once
+#include "common.cuh"
+
+namespace dmgs {
+
+DevParams make_dev_params(const dmgs_params *p);
+
+// preprocess.cu
+int launch_preprocess_fwd(const dmgs_params *prm, const float *means3D, const float *scales, const float *rotations,
+                          const float *cov3D_precomp, const float *opacities, const float *shs,
+                          const float *colors_precomp, int32_t *radii, void *geom, const GeomLayout &L, cudaStream_t s);
+int launch_preprocess_bwd(const dmgs_params *prm, const float *means3D, const float *scales, const float *rotations,
+                          const float *cov3D_precomp, const float *shs, const int32_t *radii, const void *geom,
+                          const GeomLayout &L, const float *grad_blend, float *dL_dmeans3D, float *dL_dmeans2D,
+                          float *dL_dopacity, float *dL_dcolprec, float *dL_dshs, float *dL_dscales, float *dL_drots,
+                          float *dL_dcov3D, cudaStream_t s);
+int launch_mark_visible(int P, const float *means3D, const float *view_dev, uint8_t *visible, cudaStream_t s);
+int launch_exp_array(const float *x, float *y, int64_t n, cudaStream_t s);
+
+// sort.cu
+// Stable LSD radix pass over (key,value) pairs on `bits` bits starting at `shift`.
+int radix_pass(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out, int64_t n,
+               int shift, int bits, uint32_t *hist, uint32_t *scan_tmp, cudaStream_t s);
+// out[i] = sum_{j<i} in[gather ? gather[j] : j]; *total = sum of all (may be NULL)
+int exclusive_scan_u32(const uint32_t *in, const uint32_t *gather, uint32_t *out, int64_t n, uint32_t *total,
+                       uint32_t *scan_tmp, cudaStream_t s);
+int launch_emit_instances(int P, const uint32_t *order, const uint32_t *offsets, const uint32_t *tiles,
+                          const uint2 *rect, int gx, uint32_t *inst_tile, uint32_t *inst_gidx, cudaStream_t s);
+int launch_tile_ranges(int64_t R, const uint32_t *sorted_tiles, uint2 *ranges, int T, cudaStream_t s);
+int launch_sorted_keys(int64_t R, const uint32_t *sorted_tiles, const uint32_t *sorted_gidx, const float *depths,
+                       uint64_t *keys_out, cudaStream_t s);
+
+// blend.cu
+int launch_blend_fwd(const dmgs_params *prm, const void *geom, const GeomLayout &GL, const void *binning,
+                     const BinLayout &BL, float *out_color, void *image, const ImgLayout &IL, cudaStream_t s);
+int launch_blend_bwd(const dmgs_params *prm, const void *geom, const GeomLayout &GL, const void *binning,
+                     const BinLayout &BL, const void *image, const ImgLayout &IL, const float *dL_dpix,
+                     float *grad_blend, cudaStream_t s);
+
+// binding.cu
+int launch_bind_fwd(int64_t F, int k, const float *verts, const int64_t *faces, const float *bc, float rad_base,
+                    float thin_z, const float *g, int adaptive, float *xyz, float *cov6, float *rot_t2w, cudaStream_t s);
+int launch_bind_bwd(int64_t F, int k, const float *verts, const int64_t *faces, const float *bc, float rad_base,
+                    float thin_z, const float *g, int adaptive, const float *dL_dxyz, const float *dL_dcov6,
+                    const float *dL_drot, float *dverts, float *dg, cudaStream_t s);
+
+}  // namespace dmgs

@@ -1,0 +1,484 @@
+// preprocess.cu -- per-Gaussian forward (EWA projection, SH colour, tile rectangle, depth key)
+// and the fused per-Gaussian backward (cov2D adjoint + projection + SH + scale/quaternion).
+// Replaces upstream preprocessCUDA fwd/bwd + computeCov2DCUDA; the SH
+// colour path also covers DMGS's python eval_sh + sigmoid (utils/sh_utils.py:41-99,
+// gaussian_renderer/__init__.py:74-78).  One thread per Gaussian; HBM-bound.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace dmgs {
+
+#define SH_C0 0.28209479177387814f
+#define SH_C1 0.4886025119029199f
+#define SH_C2_0 1.0925484305920792f
+#define SH_C2_1 -1.0925484305920792f
+#define SH_C2_2 0.31539156525252005f
+#define SH_C2_3 -1.0925484305920792f
+#define SH_C2_4 0.5462742152960396f
+#define SH_C3_0 -0.5900435899266435f
+#define SH_C3_1 2.890611442640554f
+#define SH_C3_2 -0.4570457994644658f
+#define SH_C3_3 0.3731763325901154f
+#define SH_C3_4 -0.4570457994644658f
+#define SH_C3_5 1.445305721320277f
+#define SH_C3_6 -0.5900435899266435f
+
+DevParams make_dev_params(const dmgs_params *p)
+{
+    DevParams d;
+    d.P = p->P; d.sh_degree = p->sh_degree; d.M = p->sh_coeffs; d.W = p->image_width; d.H = p->image_height;
+    d.sh_layout = p->sh_layout; d.sh_act = p->sh_activation;
+    d.gx = (d.W + DMGS_TILE - 1) / DMGS_TILE; d.gy = (d.H + DMGS_TILE - 1) / DMGS_TILE;
+    d.tanfovx = p->tanfovx; d.tanfovy = p->tanfovy;
+    d.fx = (float)d.W / (2.0f * p->tanfovx); d.fy = (float)d.H / (2.0f * p->tanfovy);
+    d.limx = 1.3f * p->tanfovx; d.limy = 1.3f * p->tanfovy;
+    d.mod = p->scale_modifier;
+    for (int i = 0; i < 3; ++i) { d.bg[i] = p->bg[i]; d.cam[i] = p->campos[i]; }
+    for (int i = 0; i < 16; ++i) { d.V[i] = p->viewmatrix[i]; d.PV[i] = p->projmatrix[i]; }
+    return d;
+}
+
+__device__ __forceinline__ int sh_basis(int deg, float x, float y, float z, float *b)
+{
+    b[0] = SH_C0;
+    if (deg < 1) return 1;
+    b[1] = -(SH_C1 * y);
+    b[2] = SH_C1 * z;
+    b[3] = -(SH_C1 * x);
+    if (deg < 2) return 4;
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    b[4] = SH_C2_0 * xy;
+    b[5] = SH_C2_1 * yz;
+    b[6] = SH_C2_2 * (fma_(2.0f, zz, -xx) - yy);
+    b[7] = SH_C2_3 * xz;
+    b[8] = SH_C2_4 * (xx - yy);
+    if (deg < 3) return 9;
+    const float t4 = fma_(4.0f, zz, -xx) - yy;
+    b[9] = (SH_C3_0 * y) * fma_(3.0f, xx, -yy);
+    b[10] = (SH_C3_1 * xy) * z;
+    b[11] = (SH_C3_2 * y) * t4;
+    b[12] = (SH_C3_3 * z) * fma_(-3.0f, yy, fma_(-3.0f, xx, 2.0f * zz));
+    b[13] = (SH_C3_4 * x) * t4;
+    b[14] = (SH_C3_5 * z) * (xx - yy);
+    b[15] = (SH_C3_6 * x) * fma_(-3.0f, yy, xx);
+    return 16;
+}
+
+__device__ __forceinline__ void quat_to_rot(const float *q, float R[3][3])
+{
+    const float r = q[0], x = q[1], y = q[2], z = q[3];
+    R[0][0] = fma_(-2.0f, fma_(z, z, y * y), 1.0f);
+    R[0][1] = 2.0f * fma_(-r, z, x * y);
+    R[0][2] = 2.0f * fma_(r, y, x * z);
+    R[1][0] = 2.0f * fma_(r, z, x * y);
+    R[1][1] = fma_(-2.0f, fma_(z, z, x * x), 1.0f);
+    R[1][2] = 2.0f * fma_(-r, x, y * z);
+    R[2][0] = 2.0f * fma_(-r, y, x * z);
+    R[2][1] = 2.0f * fma_(r, x, y * z);
+    R[2][2] = fma_(-2.0f, fma_(y, y, x * x), 1.0f);
+}
+
+// Shared between forward and backward: T = J * W (2x3), u = Sigma * T^T, cov2D (a,b,c incl. +0.3)
+struct Ewa {
+    float tx, ty, tz, cx, cy, txtz, tytz;
+    float T0[3], T1[3], u0[3], u1[3];
+    float a, b, c;
+};
+__device__ __forceinline__ void ewa_project(const DevParams &pr, float x, float y, float z, const float *c6, Ewa &e)
+{
+    e.tx = affine3(pr.V, 0, x, y, z);
+    e.ty = affine3(pr.V, 1, x, y, z);
+    e.tz = affine3(pr.V, 2, x, y, z);
+    e.txtz = e.tx / e.tz;
+    e.tytz = e.ty / e.tz;
+    e.cx = fminf(pr.limx, fmaxf(-pr.limx, e.txtz)) * e.tz;
+    e.cy = fminf(pr.limy, fmaxf(-pr.limy, e.tytz)) * e.tz;
+    const float J00 = pr.fx / e.tz, J02 = -(pr.fx * e.cx) / (e.tz * e.tz);
+    const float J11 = pr.fy / e.tz, J12 = -(pr.fy * e.cy) / (e.tz * e.tz);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        e.T0[j] = fma_(J02, pr.V[4 * j + 2], J00 * pr.V[4 * j + 0]);
+        e.T1[j] = fma_(J12, pr.V[4 * j + 2], J11 * pr.V[4 * j + 1]);
+    }
+    const float S[3][3] = {{c6[0], c6[1], c6[2]}, {c6[1], c6[3], c6[4]}, {c6[2], c6[4], c6[5]}};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        e.u0[j] = dot3(S[j][0], e.T0[0], S[j][1], e.T0[1], S[j][2], e.T0[2]);
+        e.u1[j] = dot3(S[j][0], e.T1[0], S[j][1], e.T1[1], S[j][2], e.T1[2]);
+    }
+    e.a = dot3(e.T0[0], e.u0[0], e.T0[1], e.u0[1], e.T0[2], e.u0[2]) + 0.3f;
+    e.b = dot3(e.T1[0], e.u0[0], e.T1[1], e.u0[1], e.T1[2], e.u0[2]);
+    e.c = dot3(e.T1[0], e.u1[0], e.T1[1], e.u1[1], e.T1[2], e.u1[2]) + 0.3f;
+}
+
+__device__ __forceinline__ float sh_load(const float *__restrict__ shs, const DevParams &pr, int i, int k, int ch)
+{
+    return pr.sh_layout == 0 ? __ldg(shs + ((size_t)i * pr.M + k) * 3 + ch) : __ldg(shs + ((size_t)i * 3 + ch) * pr.M + k);
+}
+
+__global__ void __launch_bounds__(256)
+preprocess_fwd_kernel(const __grid_constant__ DevParams pr, const float *__restrict__ means3D, const float *__restrict__ scales,
+                      const float *__restrict__ rotations, const float *__restrict__ cov3D_precomp,
+                      const float *__restrict__ opacities, const float *__restrict__ shs,
+                      const float *__restrict__ colors_precomp, int32_t *__restrict__ radii,
+                      float *__restrict__ depths, float4 *__restrict__ rec, float4 *__restrict__ rgb4,
+                      uint8_t *__restrict__ clamped, float *__restrict__ cov3D, uint32_t *__restrict__ tiles,
+                      uint2 *__restrict__ rect, uint32_t *__restrict__ sort_key, uint32_t *__restrict__ sort_val)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pr.P) return;
+    // invisible defaults
+    int rad = 0;
+    uint32_t ntiles = 0, key = 0xFFFFFFFFu;
+    float depth = 0.0f;
+    float4 ra = make_float4(0, 0, 0, 0), rb = make_float4(0, 0, 0, 0), col = make_float4(0, 0, 0, 0);
+    uint2 rc = make_uint2(0, 0);
+    uint8_t clampbits = 0;
+    float c6[6] = {0, 0, 0, 0, 0, 0};
+
+    const float x = means3D[3 * i], y = means3D[3 * i + 1], z = means3D[3 * i + 2];
+    const float tz = affine3(pr.V, 2, x, y, z);
+    if (tz > DMGS_NEAR) {
+        const float hx = affine3(pr.PV, 0, x, y, z), hy = affine3(pr.PV, 1, x, y, z), hw = affine3(pr.PV, 3, x, y, z);
+        const float pw = 1.0f / (hw + 1e-7f);
+        const float ppx = hx * pw, ppy = hy * pw;
+        if (cov3D_precomp) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) c6[k] = cov3D_precomp[6 * (size_t)i + k];
+        } else {
+            const float s[3] = {pr.mod * scales[3 * i], pr.mod * scales[3 * i + 1], pr.mod * scales[3 * i + 2]};
+            const float4 q4 = reinterpret_cast<const float4 *>(rotations)[i];
+            const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+            float R[3][3], Mm[3][3];
+            quat_to_rot(q, R);
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) Mm[k][j] = s[k] * R[j][k];
+            c6[0] = dot3(Mm[0][0], Mm[0][0], Mm[1][0], Mm[1][0], Mm[2][0], Mm[2][0]);
+            c6[1] = dot3(Mm[0][0], Mm[0][1], Mm[1][0], Mm[1][1], Mm[2][0], Mm[2][1]);
+            c6[2] = dot3(Mm[0][0], Mm[0][2], Mm[1][0], Mm[1][2], Mm[2][0], Mm[2][2]);
+            c6[3] = dot3(Mm[0][1], Mm[0][1], Mm[1][1], Mm[1][1], Mm[2][1], Mm[2][1]);
+            c6[4] = dot3(Mm[0][1], Mm[0][2], Mm[1][1], Mm[1][2], Mm[2][1], Mm[2][2]);
+            c6[5] = dot3(Mm[0][2], Mm[0][2], Mm[1][2], Mm[1][2], Mm[2][2], Mm[2][2]);
+        }
+        Ewa e;
+        ewa_project(pr, x, y, z, c6, e);
+        const float det = fma_(-e.b, e.b, e.a * e.c);
+        if (det != 0.0f) {
+            const float det_inv = 1.0f / det;
+            const float mid = 0.5f * (e.a + e.c);
+            const float sq = sqrtf(fmaxf(0.1f, fma_(mid, mid, -det)));
+            const float rf = fminf(ceilf(3.0f * sqrtf(fmaxf(mid + sq, mid - sq))), 1.0e9f);
+            const float px = fma_(ppx + 1.0f, (float)pr.W, -1.0f) * 0.5f;
+            const float py = fma_(ppy + 1.0f, (float)pr.H, -1.0f) * 0.5f;
+            const int x0 = clampi_f((px - rf) * 0.0625f, pr.gx), x1 = clampi_f((px + rf + 15.0f) * 0.0625f, pr.gx);
+            const int y0 = clampi_f((py - rf) * 0.0625f, pr.gy), y1 = clampi_f((py + rf + 15.0f) * 0.0625f, pr.gy);
+            const int nt = (x1 - x0) * (y1 - y0);
+            if (nt > 0) {
+                if (colors_precomp) {
+                    col = make_float4(colors_precomp[3 * i], colors_precomp[3 * i + 1], colors_precomp[3 * i + 2], 0.0f);
+                } else {
+                    const float dx = x - pr.cam[0], dy = y - pr.cam[1], dz = z - pr.cam[2];
+                    const float len = sqrtf(dot3(dx, dx, dy, dy, dz, dz));
+                    float bas[16];
+                    const int nb = sh_basis(pr.sh_degree, dx / len, dy / len, dz / len, bas);
+                    float v[3];
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        float acc = bas[0] * sh_load(shs, pr, i, 0, ch);
+                        for (int k = 1; k < nb; ++k) acc = fma_(bas[k], sh_load(shs, pr, i, k, ch), acc);
+                        if (pr.sh_act == 0) {
+                            acc = acc + 0.5f;
+                            if (acc < 0.0f) clampbits |= (uint8_t)(1u << ch);
+                            acc = fmaxf(acc, 0.0f);
+                        } else {
+                            acc = 1.0f / (1.0f + dmgs_exp(-acc));
+                        }
+                        v[ch] = acc;
+                    }
+                    col = make_float4(v[0], v[1], v[2], 0.0f);
+                }
+                const float op = opacities[i];
+                // conservative blend cut-off: power < -cut  =>  opacity*exp(power) < 1/255 for sure
+                const float cut = op > 0.0f ? logf(255.0f * op) + 1.0e-3f : -1.0f;
+                rad = (int)rf;
+                ntiles = (uint32_t)nt;
+                depth = e.tz;
+                key = __float_as_uint(depth);
+                ra = make_float4(px, py, e.c * det_inv, -e.b * det_inv);
+                rb = make_float4(e.a * det_inv, op, cut, 0.0f);
+                rc = make_uint2((uint32_t)x0 | ((uint32_t)x1 << 16), (uint32_t)y0 | ((uint32_t)y1 << 16));
+            }
+        }
+    }
+    radii[i] = rad;
+    depths[i] = depth;
+    rec[2 * (size_t)i] = ra;
+    rec[2 * (size_t)i + 1] = rb;
+    rgb4[i] = col;
+    clamped[i] = clampbits;
+    tiles[i] = ntiles;
+    rect[i] = rc;
+    sort_key[i] = key;
+    sort_val[i] = (uint32_t)i;
+    if (!cov3D_precomp) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) cov3D[6 * (size_t)i + k] = ntiles ? c6[k] : 0.0f;
+    }
+}
+
+int launch_preprocess_fwd(const dmgs_params *prm, const float *means3D, const float *scales, const float *rotations,
+                          const float *cov3D_precomp, const float *opacities, const float *shs,
+                          const float *colors_precomp, int32_t *radii, void *geom, const GeomLayout &L,
+                          cudaStream_t s)
+{
+    const int P = prm->P;
+    if (P <= 0) return 0;
+    preprocess_fwd_kernel<<<(P + 255) / 256, 256, 0, s>>>(
+        make_dev_params(prm), means3D, scales, rotations, cov3D_precomp, opacities, shs, colors_precomp, radii, at<float>(geom, L.depths),
+        at<float4>(geom, L.rec), at<float4>(geom, L.rgb), at<uint8_t>(geom, L.clamped), at<float>(geom, L.cov3D),
+        at<uint32_t>(geom, L.tiles), at<uint2>(geom, L.rect), at<uint32_t>(geom, L.keys_a), at<uint32_t>(geom, L.order));
+    DMGS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------ backward
+// grad_blend: per Gaussian 12 floats {dmean2D.x, dmean2D.y, dconic.a, dconic.b(half), dconic.c,
+// dopacity, dcolor.r, dcolor.g, dcolor.b, pad x3} accumulated by the blend backward.
+__global__ void __launch_bounds__(256)
+preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restrict__ means3D, const float *__restrict__ scales,
+                      const float *__restrict__ rotations, const float *__restrict__ cov3D_precomp,
+                      const float *__restrict__ shs, const int32_t *__restrict__ radii,
+                      const float *__restrict__ cov3D_state, const uint8_t *__restrict__ clamped,
+                      const float4 *__restrict__ rgb4, const float4 *__restrict__ grad_blend,
+                      float *__restrict__ dL_dmeans3D, float *__restrict__ dL_dmeans2D,
+                      float *__restrict__ dL_dopacity, float *__restrict__ dL_dcolprec, float *__restrict__ dL_dshs,
+                      float *__restrict__ dL_dscales, float *__restrict__ dL_drots, float *__restrict__ dL_dcov3D)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pr.P) return;
+    const bool vis = radii[i] > 0;
+    float gm[3] = {0, 0, 0}, g6[6] = {0, 0, 0, 0, 0, 0};
+    float gs[3] = {0, 0, 0}, gq[4] = {0, 0, 0, 0};
+    float d2x = 0, d2y = 0, dop = 0, dcol[3] = {0, 0, 0};
+    const int M = pr.M;
+
+    if (vis) {
+        const float4 ga = grad_blend[3 * (size_t)i], gb = grad_blend[3 * (size_t)i + 1], gc = grad_blend[3 * (size_t)i + 2];
+        d2x = ga.x; d2y = ga.y;
+        const float gcx = ga.z, gcy = ga.w, gcz = gb.x;
+        dop = gb.y;
+        dcol[0] = gb.z; dcol[1] = gb.w; dcol[2] = gc.x;
+
+        const float x = means3D[3 * i], y = means3D[3 * i + 1], z = means3D[3 * i + 2];
+        float c6[6];
+        const float *csrc = cov3D_precomp ? cov3D_precomp : cov3D_state;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) c6[k] = csrc[6 * (size_t)i + k];
+        Ewa e;
+        ewa_project(pr, x, y, z, c6, e);
+        const float a = e.a, b = e.b, c = e.c;
+        const float denom = fma_(-b, b, a * c);
+        const float d2inv = 1.0f / fma_(denom, denom, 1e-7f);
+        const float dL_da = d2inv * fma_(-(b * b), gcz, fma_(2.0f * b * c, gcy, -(c * c) * gcx));
+        const float dL_dc = d2inv * fma_(-(b * b), gcx, fma_(2.0f * a * b, gcy, -(a * a) * gcz));
+        const float dL_db = d2inv * 2.0f * fma_(-fma_(2.0f * b, b, denom), gcy, fma_(a * b, gcz, (b * c) * gcx));
+        const float *T0 = e.T0, *T1 = e.T1;
+        g6[0] = fma_(T1[0] * T1[0], dL_dc, fma_(T0[0] * T1[0], dL_db, (T0[0] * T0[0]) * dL_da));
+        g6[3] = fma_(T1[1] * T1[1], dL_dc, fma_(T0[1] * T1[1], dL_db, (T0[1] * T0[1]) * dL_da));
+        g6[5] = fma_(T1[2] * T1[2], dL_dc, fma_(T0[2] * T1[2], dL_db, (T0[2] * T0[2]) * dL_da));
+        g6[1] = fma_(2.0f * T1[0] * T1[1], dL_dc, fma_(fma_(T0[1], T1[0], T0[0] * T1[1]), dL_db, (2.0f * T0[0] * T0[1]) * dL_da));
+        g6[2] = fma_(2.0f * T1[0] * T1[2], dL_dc, fma_(fma_(T0[2], T1[0], T0[0] * T1[2]), dL_db, (2.0f * T0[0] * T0[2]) * dL_da));
+        g6[4] = fma_(2.0f * T1[1] * T1[2], dL_dc, fma_(fma_(T0[2], T1[1], T0[1] * T1[2]), dL_db, (2.0f * T0[1] * T0[2]) * dL_da));
+        float dT0[3], dT1[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            dT0[j] = fma_(e.u1[j], dL_db, 2.0f * e.u0[j] * dL_da);
+            dT1[j] = fma_(e.u0[j], dL_db, 2.0f * e.u1[j] * dL_dc);
+        }
+        const float *V = pr.V, *PV = pr.PV;
+        const float dJ00 = dot3(V[0], dT0[0], V[4], dT0[1], V[8], dT0[2]);
+        const float dJ02 = dot3(V[2], dT0[0], V[6], dT0[1], V[10], dT0[2]);
+        const float dJ11 = dot3(V[1], dT1[0], V[5], dT1[1], V[9], dT1[2]);
+        const float dJ12 = dot3(V[2], dT1[0], V[6], dT1[1], V[10], dT1[2]);
+        const float xgm = (e.txtz < -pr.limx || e.txtz > pr.limx) ? 0.0f : 1.0f;
+        const float ygm = (e.tytz < -pr.limy || e.tytz > pr.limy) ? 0.0f : 1.0f;
+        const float tzi = 1.0f / e.tz, tz2 = tzi * tzi, tz3 = tz2 * tzi;
+        const float dtx = xgm * (-pr.fx * tz2) * dJ02;
+        const float dty = ygm * (-pr.fy * tz2) * dJ12;
+        const float dtz = fma_((2.0f * pr.fy * e.cy) * tz3, dJ12,
+                               fma_((2.0f * pr.fx * e.cx) * tz3, dJ02, fma_(-pr.fy * tz2, dJ11, (-pr.fx * tz2) * dJ00)));
+#pragma unroll
+        for (int k = 0; k < 3; ++k) gm[k] = dot3(V[4 * k], dtx, V[4 * k + 1], dty, V[4 * k + 2], dtz);
+
+        const float hx = affine3(PV, 0, x, y, z), hy = affine3(PV, 1, x, y, z), hw = affine3(PV, 3, x, y, z);
+        const float mw = 1.0f / (hw + 1e-7f);
+        const float mul1 = hx * mw * mw, mul2 = hy * mw * mw;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float ax = fma_(-PV[4 * k + 3], mul1, PV[4 * k + 0] * mw);
+            const float ay = fma_(-PV[4 * k + 3], mul2, PV[4 * k + 1] * mw);
+            gm[k] += fma_(ay, d2y, ax * d2x);
+        }
+
+        if (shs && dL_dshs) {
+            const float ox = x - pr.cam[0], oy = y - pr.cam[1], oz = z - pr.cam[2];
+            const float s2 = dot3(ox, ox, oy, oy, oz, oz);
+            const float len = sqrtf(s2);
+            const float dxn = ox / len, dyn = oy / len, dzn = oz / len;
+            float bas[16];
+            const int nb = sh_basis(pr.sh_degree, dxn, dyn, dzn, bas);
+            const uint8_t cb = clamped[i];
+            const float4 rgbv = rgb4[i];
+            const float sg[3] = {rgbv.x, rgbv.y, rgbv.z};
+            float ddx = 0, ddy = 0, ddz = 0;
+            const float xx = dxn * dxn, yy = dyn * dyn, zz = dzn * dzn, xy_ = dxn * dyn, yz = dyn * dzn, xz = dxn * dzn;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                float g = dcol[ch];
+                if (pr.sh_act == 0) g = (cb >> ch) & 1 ? 0.0f : g;
+                else g = g * (sg[ch] * (1.0f - sg[ch]));
+                float sv[16];
+                for (int k = 0; k < 16; ++k) {
+                    const size_t idx = pr.sh_layout == 0 ? ((size_t)i * M + k) * 3 + ch : ((size_t)i * 3 + ch) * M + k;
+                    if (k < nb) {
+                        sv[k] = __ldg(shs + idx);
+                        dL_dshs[idx] = bas[k] * g;
+                    } else {
+                        sv[k] = 0.0f;
+                        if (k < M) dL_dshs[idx] = 0.0f;
+                    }
+                }
+                for (int k = 16; k < M; ++k) {
+                    const size_t idx = pr.sh_layout == 0 ? ((size_t)i * M + k) * 3 + ch : ((size_t)i * 3 + ch) * M + k;
+                    dL_dshs[idx] = 0.0f;
+                }
+                if (pr.sh_degree > 0) {
+                    float gx_ = -SH_C1 * sv[3], gy_ = -SH_C1 * sv[1], gz_ = SH_C1 * sv[2];
+                    if (pr.sh_degree > 1) {
+                        gx_ += SH_C2_0 * dyn * sv[4] + SH_C2_2 * 2.0f * -dxn * sv[6] + SH_C2_3 * dzn * sv[7] + SH_C2_4 * 2.0f * dxn * sv[8];
+                        gy_ += SH_C2_0 * dxn * sv[4] + SH_C2_1 * dzn * sv[5] + SH_C2_2 * 2.0f * -dyn * sv[6] + SH_C2_4 * 2.0f * -dyn * sv[8];
+                        gz_ += SH_C2_1 * dyn * sv[5] + SH_C2_2 * 2.0f * 2.0f * dzn * sv[6] + SH_C2_3 * dxn * sv[7];
+                        if (pr.sh_degree > 2) {
+                            gx_ += SH_C3_0 * sv[9] * 3.0f * 2.0f * xy_ + SH_C3_1 * sv[10] * yz + SH_C3_2 * sv[11] * -2.0f * xy_ +
+                                   SH_C3_3 * sv[12] * -3.0f * 2.0f * xz + SH_C3_4 * sv[13] * (-3.0f * xx + 4.0f * zz - yy) +
+                                   SH_C3_5 * sv[14] * 2.0f * xz + SH_C3_6 * sv[15] * 3.0f * (xx - yy);
+                            gy_ += SH_C3_0 * sv[9] * 3.0f * (xx - yy) + SH_C3_1 * sv[10] * xz +
+                                   SH_C3_2 * sv[11] * (-3.0f * yy + 4.0f * zz - xx) + SH_C3_3 * sv[12] * -3.0f * 2.0f * yz +
+                                   SH_C3_4 * sv[13] * -2.0f * xy_ + SH_C3_5 * sv[14] * -2.0f * yz + SH_C3_6 * sv[15] * -3.0f * 2.0f * xy_;
+                            gz_ += SH_C3_1 * sv[10] * xy_ + SH_C3_2 * sv[11] * 4.0f * 2.0f * yz +
+                                   SH_C3_3 * sv[12] * 3.0f * (2.0f * zz - xx - yy) + SH_C3_4 * sv[13] * 4.0f * 2.0f * xz +
+                                   SH_C3_5 * sv[14] * (xx - yy);
+                        }
+                    }
+                    ddx = fma_(gx_, g, ddx);
+                    ddy = fma_(gy_, g, ddy);
+                    ddz = fma_(gz_, g, ddz);
+                }
+            }
+            if (pr.sh_degree > 0) {
+                const float inv3 = 1.0f / sqrtf(s2 * s2 * s2);
+                gm[0] += ((s2 - ox * ox) * ddx - oy * ox * ddy - oz * ox * ddz) * inv3;
+                gm[1] += (-ox * oy * ddx + (s2 - oy * oy) * ddy - oz * oy * ddz) * inv3;
+                gm[2] += (-ox * oz * ddx - oy * oz * ddy + (s2 - oz * oz) * ddz) * inv3;
+            }
+        }
+
+        if (scales && rotations && dL_dscales && dL_drots) {
+            const float s[3] = {pr.mod * scales[3 * i], pr.mod * scales[3 * i + 1], pr.mod * scales[3 * i + 2]};
+            const float4 q4 = reinterpret_cast<const float4 *>(rotations)[i];
+            const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+            float R[3][3];
+            quat_to_rot(q, R);
+            const float Gs[3][3] = {{g6[0], 0.5f * g6[1], 0.5f * g6[2]}, {0.5f * g6[1], g6[3], 0.5f * g6[4]}, {0.5f * g6[2], 0.5f * g6[4], g6[5]}};
+            float dR[3][3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                float dMk[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    dMk[j] = 2.0f * dot3(s[k] * R[0][k], Gs[0][j], s[k] * R[1][k], Gs[1][j], s[k] * R[2][k], Gs[2][j]);
+                gs[k] = pr.mod * dot3(R[0][k], dMk[0], R[1][k], dMk[1], R[2][k], dMk[2]);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) dR[j][k] = s[k] * dMk[j];
+            }
+            const float r = q[0], qx = q[1], qy = q[2], qz = q[3];
+            gq[0] = 2.0f * (qz * (dR[1][0] - dR[0][1]) + qy * (dR[0][2] - dR[2][0]) + qx * (dR[2][1] - dR[1][2]));
+            gq[1] = 2.0f * (qy * (dR[0][1] + dR[1][0]) + qz * (dR[0][2] + dR[2][0]) + r * (dR[2][1] - dR[1][2])) - 4.0f * qx * (dR[1][1] + dR[2][2]);
+            gq[2] = 2.0f * (qx * (dR[0][1] + dR[1][0]) + r * (dR[0][2] - dR[2][0]) + qz * (dR[1][2] + dR[2][1])) - 4.0f * qy * (dR[0][0] + dR[2][2]);
+            gq[3] = 2.0f * (r * (dR[1][0] - dR[0][1]) + qx * (dR[0][2] + dR[2][0]) + qy * (dR[1][2] + dR[2][1])) - 4.0f * qz * (dR[0][0] + dR[1][1]);
+        }
+    } else if (shs && dL_dshs) {
+        for (int k = 0; k < 3 * M; ++k) dL_dshs[(size_t)i * 3 * M + k] = 0.0f;
+    }
+
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dL_dmeans3D[3 * (size_t)i + k] = gm[k];
+    dL_dmeans2D[3 * (size_t)i] = d2x;
+    dL_dmeans2D[3 * (size_t)i + 1] = d2y;
+    dL_dmeans2D[3 * (size_t)i + 2] = 0.0f;
+    dL_dopacity[i] = dop;
+    if (dL_dcolprec) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) dL_dcolprec[3 * (size_t)i + k] = dcol[k];
+    }
+    if (dL_dcov3D) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) dL_dcov3D[6 * (size_t)i + k] = g6[k];
+    }
+    if (dL_dscales) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) dL_dscales[3 * (size_t)i + k] = gs[k];
+    }
+    if (dL_drots) reinterpret_cast<float4 *>(dL_drots)[i] = make_float4(gq[0], gq[1], gq[2], gq[3]);
+}
+
+int launch_preprocess_bwd(const dmgs_params *prm, const float *means3D, const float *scales, const float *rotations,
+                          const float *cov3D_precomp, const float *shs, const int32_t *radii, const void *geom,
+                          const GeomLayout &L, const float *grad_blend, float *dL_dmeans3D, float *dL_dmeans2D,
+                          float *dL_dopacity, float *dL_dcolprec, float *dL_dshs, float *dL_dscales, float *dL_drots,
+                          float *dL_dcov3D, cudaStream_t s)
+{
+    const int P = prm->P;
+    if (P <= 0) return 0;
+    preprocess_bwd_kernel<<<(P + 255) / 256, 256, 0, s>>>(
+        make_dev_params(prm), means3D, scales, rotations, cov3D_precomp, shs, radii, at<float>(geom, L.cov3D), at<uint8_t>(geom, L.clamped),
+        at<float4>(geom, L.rgb), reinterpret_cast<const float4 *>(grad_blend), dL_dmeans3D, dL_dmeans2D, dL_dopacity,
+        dL_dcolprec, dL_dshs, dL_dscales, dL_drots, dL_dcov3D);
+    DMGS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------ markVisible
+__global__ void mark_visible_kernel(int P, const float *__restrict__ means3D, const float *__restrict__ view,
+                                    uint8_t *__restrict__ visible)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const float tz = affine3(view, 2, means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]);
+    visible[i] = tz > DMGS_NEAR;
+}
+
+int launch_mark_visible(int P, const float *means3D, const float *view_dev, uint8_t *visible, cudaStream_t s)
+{
+    if (P <= 0) return 0;
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, view_dev, visible);
+    DMGS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+__global__ void exp_array_kernel(const float *x, float *y, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = dmgs_exp(x[i]);
+}
+int launch_exp_array(const float *x, float *y, int64_t n, cudaStream_t s)
+{
+    if (n <= 0) return 0;
+    exp_array_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, y, n);
+    DMGS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace dmgs

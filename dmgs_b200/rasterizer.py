@@ -1,0 +1,251 @@
+"""`GaussianRasterizationSettings` / `GaussianRasterizer` -- same Python surface as the
+`diff_gaussian_rasterization` package DMGS imports (gaussian_renderer/__init__.py:14, settings
+tuple :36-49, call :86-94), backed by libdmgs_raster.so through ctypes.
+
+Extensions that keep the drop-in intact (all optional, default = upstream behaviour):
+  * ``GaussianRasterizer(raster_settings, sh_activation="clamp"|"sigmoid", sh_layout="PM3"|"P3M")``
+    lets DMGS's python ``eval_sh`` + ``sigmoid`` (gaussian_renderer/__init__.py:74-78, :166-170) run
+    inside preprocess: pass ``shs=features`` instead of ``colors_precomp``.
+  * ``rasterizer.last`` keeps the state buffers of the last forward for inspection (tests).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import NamedTuple, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+def _cached_host(t: torch.Tensor):
+    """Flat float list of a small camera tensor (one D2H per distinct tensor version)."""
+    key = (t.data_ptr(), t._version, tuple(t.shape), str(t.device))
+    hit = _cached_host.cache.get(key)
+    if hit is None:
+        if len(_cached_host.cache) > 4096:
+            _cached_host.cache.clear()
+        hit = [float(v) for v in t.detach().reshape(-1).to("cpu", torch.float32).tolist()]
+        _cached_host.cache[key] = hit
+    return hit
+
+
+_cached_host.cache = {}
+
+
+def make_params(settings: GaussianRasterizationSettings, P: int, sh_coeffs: int, sh_layout: int,
+                sh_activation: int) -> L.DmgsParams:
+    prm = L.DmgsParams()
+    prm.P = int(P)
+    prm.sh_degree = int(settings.sh_degree)
+    prm.sh_coeffs = int(sh_coeffs)
+    prm.image_width, prm.image_height = int(settings.image_width), int(settings.image_height)
+    prm.sh_layout, prm.sh_activation = int(sh_layout), int(sh_activation)
+    prm.debug = int(bool(settings.debug))
+    prm.tanfovx, prm.tanfovy = float(settings.tanfovx), float(settings.tanfovy)
+    prm.scale_modifier = float(settings.scale_modifier)
+    prm.bg[:] = _cached_host(settings.bg)
+    prm.viewmatrix[:] = _cached_host(settings.viewmatrix)
+    prm.projmatrix[:] = _cached_host(settings.projmatrix)
+    prm.campos[:] = _cached_host(settings.campos)
+    return prm
+
+
+def _f32c(t: Optional[torch.Tensor]):
+    if t is None or t.numel() == 0:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class RasterState:
+    """Caller-owned state of one forward (the geom / binning / image byte buffers)."""
+
+    def __init__(self, prm, geom, binning, image, num_rendered, radii):
+        self.prm, self.geom, self.binning, self.image = prm, geom, binning, image
+        self.num_rendered, self.radii = num_rendered, radii
+
+    # typed views for the parity tests -------------------------------------------------
+    def _view(self, buf, off, dtype, shape):
+        n = 1
+        for s in shape:
+            n *= s
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        return buf[off:off + nbytes].view(dtype).view(*shape)
+
+    def geom_arrays(self):
+        P = self.prm.P
+        o = (C.c_int64 * 9)()
+        L.lib().dmgs_geom_layout(P, o)
+        v = self._view
+        return {"depths": v(self.geom, o[0], torch.float32, (P,)), "rec": v(self.geom, o[1], torch.float32, (P, 8)),
+                "rgb": v(self.geom, o[2], torch.float32, (P, 4)), "clamped": v(self.geom, o[3], torch.uint8, (P,)),
+                "cov3D": v(self.geom, o[4], torch.float32, (P, 6)), "tiles_touched": v(self.geom, o[5], torch.int32, (P,)),
+                "rect": v(self.geom, o[6], torch.int16, (P, 4)), "order": v(self.geom, o[7], torch.int32, (P,)),
+                "offsets": v(self.geom, o[8], torch.int32, (P,))}
+
+    def binning_arrays(self):
+        R, W, H = self.num_rendered, self.prm.image_width, self.prm.image_height
+        T = ((W + 15) // 16) * ((H + 15) // 16)
+        o = (C.c_int64 * 3)()
+        L.lib().dmgs_binning_layout(self.prm.P, R, W, H, o)
+        v = self._view
+        return {"tiles": v(self.binning, o[0], torch.int32, (R,)), "gidx": v(self.binning, o[1], torch.int32, (R,)),
+                "ranges": v(self.binning, o[2], torch.int32, (T, 2))}
+
+    def image_arrays(self):
+        W, H = self.prm.image_width, self.prm.image_height
+        o = (C.c_int64 * 2)()
+        L.lib().dmgs_image_layout(W, H, o)
+        v = self._view
+        return {"final_T": v(self.image, o[0], torch.float32, (H, W)),
+                "n_contrib": v(self.image, o[1], torch.int32, (H, W))}
+
+    def sorted_keys(self):
+        R = self.num_rendered
+        keys = torch.empty(max(R, 1), dtype=torch.int64, device=self.geom.device)
+        L.check(L.lib().dmgs_sorted_keys(L.ptr(self.geom), L.ptr(self.binning), self.prm.P, R, self.prm.image_width,
+                                         self.prm.image_height, L.ptr(keys), _stream()), "dmgs_sorted_keys")
+        return keys[:R]
+
+
+def rasterize_forward(settings, means3D, opacities, shs, colors_precomp, scales, rotations, cov3D_precomp,
+                      sh_layout=0, sh_activation=0):
+    """Runs the three forward stages; returns (color [3,H,W], radii [P] int32, RasterState)."""
+    dev = means3D.device
+    if dev.type != "cuda":
+        raise RuntimeError("dmgs_b200 rasteriser needs CUDA tensors; there is no CPU path")
+    lib = L.lib()
+    P = int(means3D.shape[0])
+    H, W = int(settings.image_height), int(settings.image_width)
+    M = 0
+    if shs is not None:
+        M = int(shs.shape[1] if sh_layout == 0 else shs.shape[2])
+    prm = make_params(settings, P, M, sh_layout, sh_activation)
+    stream = _stream()
+    radii = torch.zeros(P, dtype=torch.int32, device=dev)
+    color = torch.empty(3, H, W, dtype=torch.float32, device=dev)
+    geom = torch.empty(lib.dmgs_geom_bytes(P), dtype=torch.uint8, device=dev)
+    image = torch.empty(lib.dmgs_image_bytes(W, H), dtype=torch.uint8, device=dev)
+    nr = torch.zeros(1, dtype=torch.int32, device=dev)
+    L.check(lib.dmgs_preprocess_forward(C.byref(prm), L.ptr(means3D), L.ptr(scales), L.ptr(rotations),
+                                        L.ptr(cov3D_precomp), L.ptr(opacities), L.ptr(shs), L.ptr(colors_precomp),
+                                        L.ptr(radii), L.ptr(geom), L.ptr(nr), stream), "dmgs_preprocess_forward")
+    R = int(nr.item())  # the one host read-back of the forward (upstream does the same after its scan)
+    binning = torch.empty(lib.dmgs_binning_bytes(P, R, W, H), dtype=torch.uint8, device=dev)
+    L.check(lib.dmgs_bin_forward(C.byref(prm), L.ptr(geom), R, L.ptr(binning), stream), "dmgs_bin_forward")
+    L.check(lib.dmgs_blend_forward(C.byref(prm), L.ptr(geom), L.ptr(binning), R, L.ptr(color), L.ptr(image), stream),
+            "dmgs_blend_forward")
+    return color, radii, RasterState(prm, geom, binning, image, R, radii)
+
+
+def rasterize_backward(state: RasterState, grad_color, means3D, shs, scales, rotations, cov3D_precomp,
+                       want_colors_precomp):
+    lib = L.lib()
+    prm, P, dev = state.prm, state.prm.P, means3D.device
+    z = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+    g_means3D, g_means2D, g_op = z(P, 3), z(P, 3), z(P, 1)
+    g_col = z(P, 3) if want_colors_precomp else None
+    g_shs = torch.empty_like(shs) if shs is not None else None
+    g_scales = z(P, 3) if scales is not None else None
+    g_rots = z(P, 4) if rotations is not None else None
+    g_cov = z(P, 6) if cov3D_precomp is not None else None
+    scratch = torch.empty(lib.dmgs_backward_scratch_bytes(P), dtype=torch.uint8, device=dev)
+    L.check(lib.dmgs_backward(C.byref(prm), L.ptr(means3D), L.ptr(scales), L.ptr(rotations), L.ptr(cov3D_precomp),
+                              L.ptr(shs), L.ptr(state.radii), L.ptr(state.geom), L.ptr(state.binning),
+                              L.ptr(state.image), state.num_rendered, L.ptr(grad_color), L.ptr(g_means3D),
+                              L.ptr(g_means2D), L.ptr(g_op), L.ptr(g_col), L.ptr(g_shs), L.ptr(g_scales), L.ptr(g_rots),
+                              L.ptr(g_cov), L.ptr(scratch), _stream()), "dmgs_backward")
+    return g_means3D, g_means2D, g_shs, g_col, g_op, g_scales, g_rots, g_cov
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                raster_settings, sh_layout, sh_activation, holder):
+        means3D_c, op_c = _f32c(means3D), _f32c(opacities)
+        sh_c, col_c = _f32c(sh), _f32c(colors_precomp)
+        sc_c, rot_c, cov_c = _f32c(scales), _f32c(rotations), _f32c(cov3Ds_precomp)
+        if means3D_c is None:  # P == 0
+            H, W = int(raster_settings.image_height), int(raster_settings.image_width)
+            color = raster_settings.bg.float().view(3, 1, 1).expand(3, H, W).contiguous()
+            ctx.state = None
+            return color, torch.zeros(0, dtype=torch.int32, device=color.device)
+        color, radii, state = rasterize_forward(raster_settings, means3D_c, op_c, sh_c, col_c, sc_c, rot_c, cov_c,
+                                                sh_layout, sh_activation)
+        ctx.state = state
+        ctx.save_for_backward(means3D_c, sh_c, sc_c, rot_c, cov_c)
+        ctx.has_col = col_c is not None
+        if holder is not None:
+            holder.last = state
+        ctx.mark_non_differentiable(radii)
+        return color, radii
+
+    @staticmethod
+    def backward(ctx, grad_color, _grad_radii):
+        if ctx.state is None:
+            return (None,) * 12
+        means3D, sh, scales, rotations, cov = ctx.saved_tensors
+        g = rasterize_backward(ctx.state, grad_color.contiguous().float(), means3D, sh, scales, rotations, cov,
+                               ctx.has_col)
+        g_means3D, g_means2D, g_shs, g_col, g_op, g_scales, g_rots, g_cov = g
+        return (g_means3D, g_means2D, g_shs, g_col, g_op, g_scales, g_rots, g_cov, None, None, None, None)
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                        raster_settings, sh_layout=0, sh_activation=0, holder=None):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                     cov3Ds_precomp, raster_settings, sh_layout, sh_activation, holder)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings, sh_activation: str = "clamp", sh_layout: str = "PM3"):
+        super().__init__()
+        self.raster_settings = raster_settings
+        self.sh_activation = {"clamp": 0, "sigmoid": 1}[sh_activation]
+        self.sh_layout = {"PM3": 0, "P3M": 1}[sh_layout]
+        self.last: Optional[RasterState] = None
+
+    def markVisible(self, positions):
+        with torch.no_grad():
+            rs = self.raster_settings
+            pos = _f32c(positions)
+            P = int(positions.shape[0])
+            vis = torch.zeros(P, dtype=torch.uint8, device=positions.device)
+            if P:
+                view = rs.viewmatrix.float().contiguous()
+                proj = rs.projmatrix.float().contiguous()
+                L.check(L.lib().dmgs_mark_visible(P, L.ptr(pos), L.ptr(view), L.ptr(proj), L.ptr(vis), _stream()),
+                        "dmgs_mark_visible")
+            return vis.bool()
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
+                                   self.raster_settings, self.sh_layout, self.sh_activation, self)

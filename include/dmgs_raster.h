@@ -1,0 +1,129 @@
+/*
+ * dmgs_raster.h -- C ABI of libdmgs_raster.so (B200 / sm_100a).
+ *
+ * This is the drop-in boundary for DMGS's differentiable Gaussian-splatting rasteriser and the
+ * mesh-face -> Gaussian binding that feeds it.  The reference binds this path through the
+ * pybind11/torch module `diff_gaussian_rasterization._C` (imported at
+ * /root/reference/gaussian_renderer/__init__.py:14; settings tuple at :36-49 / :129-142; call at
+ * :86-94 / :178-186).  Here the same work is exposed as plain `extern "C"` functions taking raw
+ * device pointers, sizes and a CUDA stream -- no torch types -- and dmgs_b200/rasterizer.py binds
+ * them with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the library never allocates or frees device memory: state lives in three caller-owned
+ *     byte buffers (geom / binning / image) whose sizes the *_bytes functions return -- the
+ *     counterpart of the upstream module growing torch byte tensors through callbacks;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises
+ *     unless params.debug != 0, in which case every stage is followed by a stream sync + check;
+ *   - return value: 0 ok, < 0 argument error, > 0 a cudaError_t; dmgs_last_error() explains.
+ *   - optional inputs are NULL when absent (exactly one of shs|colors_precomp and exactly one of
+ *     (scales,rotations)|cov3D_precomp must be given, as the reference op demands).
+ */
+#ifndef DMGS_RASTER_H
+#define DMGS_RASTER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Mirrors GaussianRasterizationSettings (gaussian_renderer/__init__.py:36-49) plus the two
+ * switches needed to fold DMGS's Python SH path (gaussian_renderer/__init__.py:74-78, :166-170)
+ * into preprocess. */
+typedef struct dmgs_params {
+    int32_t P;              /* number of Gaussians */
+    int32_t sh_degree;      /* active SH degree (settings.sh_degree) */
+    int32_t sh_coeffs;      /* stored coefficients per channel M (shs.shape[1] or features.shape[2]) */
+    int32_t image_width;
+    int32_t image_height;
+    int32_t sh_layout;      /* 0: shs [P,M,3] (rasteriser layout); 1: features [P,3,M] (DMGS gs_info layout) */
+    int32_t sh_activation;  /* 0: max(sh+0.5, 0) (rasteriser); 1: sigmoid(sh) (DMGS convert_SHs_python path) */
+    int32_t debug;          /* settings.debug: sync + check after every stage */
+    float tanfovx, tanfovy;
+    float scale_modifier;
+    float bg[3];
+    float viewmatrix[16];   /* world_view_transform, flat row-major torch layout (= column-major W2C) */
+    float projmatrix[16];   /* full_proj_transform, same layout */
+    float campos[3];
+} dmgs_params;
+
+/* ---- buffer sizes (host-only, no CUDA calls) ------------------------------------------- */
+size_t dmgs_geom_bytes(int32_t P);
+size_t dmgs_binning_bytes(int32_t P, int64_t num_rendered, int32_t W, int32_t H);
+size_t dmgs_image_bytes(int32_t W, int32_t H);
+
+/* ---- forward, stage 1: replaces preprocessCUDA + InclusiveSum ----------
+ * Per-Gaussian EWA projection / SH colour / tile rectangle, a stable depth sort of the
+ * Gaussians, and the prefix sum of tiles touched in depth order.  Writes radii[P] (int32) and
+ * the number of (Gaussian, tile) instances to *num_rendered (device uint32). */
+int dmgs_preprocess_forward(const dmgs_params *prm, const float *means3D, const float *scales,
+                            const float *rotations, const float *cov3D_precomp, const float *opacities,
+                            const float *shs, const float *colors_precomp, int32_t *radii, void *geom,
+                            uint32_t *num_rendered, void *stream);
+
+/* ---- forward, stage 2: replaces duplicateWithKeys + SortPairs + identifyTileRanges (K3-K5) --
+ * num_rendered is the value stage 1 produced (read back by the caller, as the upstream host
+ * code does).  Produces the tile-major, depth-ordered instance list and per-tile ranges. */
+int dmgs_bin_forward(const dmgs_params *prm, const void *geom, int64_t num_rendered, void *binning, void *stream);
+
+/* ---- forward, stage 3: replaces renderCUDA forward (K6). out_color is [3,H,W]. */
+int dmgs_blend_forward(const dmgs_params *prm, const void *geom, const void *binning, int64_t num_rendered,
+                       float *out_color, void *image, void *stream);
+
+/* ---- backward: replaces renderCUDA backward + computeCov2DCUDA + preprocessCUDA backward (K7-K9).
+ * dL_dpix is [3,H,W].  Gradient outputs may be NULL when the corresponding input was not given;
+ * dL_dmeans2D is [P,3] (x,y filled, z = 0), the contract scene/gaussian_model.py:405-407 reads. */
+int dmgs_backward(const dmgs_params *prm, const float *means3D, const float *scales, const float *rotations,
+                  const float *cov3D_precomp, const float *shs, const int32_t *radii, const void *geom,
+                  const void *binning, const void *image, int64_t num_rendered, const float *dL_dpix,
+                  float *dL_dmeans3D, float *dL_dmeans2D, float *dL_dopacity, float *dL_dcolors_precomp,
+                  float *dL_dshs, float *dL_dscales, float *dL_drotations, float *dL_dcov3D, void *scratch,
+                  void *stream);
+size_t dmgs_backward_scratch_bytes(int32_t P);
+
+/* ---- markVisible (K10): visible[i] = view-space z > 0.2 */
+int dmgs_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,
+                      uint8_t *visible, void *stream);
+
+/* ---- mesh-face -> Gaussian binding (scene/gaussian_geo_model_mlp_flex.py:267-311, :370-385;
+ *      stage-3 frame scene/gaussian_geo_model_finetune.py:414-421).
+ * faces: int64 [F,3]; bc: [k,3]; g: device pointer to ONE float = tanh(scale_factor) * max_scale
+ * (computed by the caller with two tiny torch ops, so no host read-back; NULL means g = 1, the
+ * COLMAP variant scene/gaussian_geo_model_mlp_flex_colmap.py:500-504).
+ * Outputs xyz [F*k,3], cov6 [F*k,6] (either may be NULL); rot_t2w [F,9] optional.           */
+int dmgs_bind_forward(int64_t F, int32_t k, const float *verts, const int64_t *faces, const float *bc,
+                      float rad_base, float thin_z, const float *g, int32_t adaptive, float *xyz, float *cov6,
+                      float *rot_t2w, void *stream);
+/* The gradient the reference's autograd produces (cov3D_L is a constant): accumulates into
+ * dverts [V,3] and dg [1] (both must be zeroed by the caller). dL_dxyz / dL_dcov6 may be NULL;
+ * dL_drot [F,9] is an optional extra gradient on the face frame (stage 3). */
+int dmgs_bind_backward(int64_t F, int32_t k, const float *verts, const int64_t *faces, const float *bc,
+                       float rad_base, float thin_z, const float *g, int32_t adaptive, const float *dL_dxyz,
+                       const float *dL_dcov6, const float *dL_drot, float *dverts, float *dg, void *stream);
+
+/* ---- inspection (parity tests): byte offsets of the named arrays inside the state buffers.
+ * geom:    [0] depths f32[P]  [1] rec f32[P][8]={x,y,conA,conB,conC,opacity,cut,_}  [2] rgb f32[P][4]
+ *          [3] clamped u8[P] (bit ch)  [4] cov3D f32[P][6]  [5] tiles_touched u32[P]
+ *          [6] rect u16[P][4]={x0,x1,y0,y1}  [7] depth-sorted Gaussian index u32[P]
+ *          [8] instance offsets (exclusive scan in depth order) u32[P]
+ * binning: [0] sorted tile ids u32[R]  [1] sorted Gaussian indices u32[R]  [2] ranges u32[T][2]
+ * image:   [0] final_T f32[H*W]  [1] n_contrib u32[H*W]                                        */
+int dmgs_geom_layout(int32_t P, int64_t *offsets9);
+int dmgs_binning_layout(int32_t P, int64_t num_rendered, int32_t W, int32_t H, int64_t *offsets3);
+int dmgs_image_layout(int32_t W, int32_t H, int64_t *offsets2);
+/* Materialises the 64-bit sort keys (tile << 32 | depth bits) of the sorted instance list. */
+int dmgs_sorted_keys(const void *geom, const void *binning, int32_t P, int64_t num_rendered, int32_t W, int32_t H,
+                     uint64_t *keys_out, void *stream);
+/* y[i] = the library's exp() (the arithmetic-contract exp used for alpha). */
+int dmgs_exp_array(const float *x, float *y, int64_t n, void *stream);
+
+const char *dmgs_last_error(void);
+int dmgs_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMGS_RASTER_H */
