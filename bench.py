@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- fwd+bwd frames/s of the splatting hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload h0|c1|c3]
+
+Workload (N=1 default) = H0, the shape the metric is quoted on: 1 M random Gaussians, SH degree 3,
+`shs`+`scales`+`rotations` mode, 800x800 NeRF-synthetic cameras.  A step renders
+`views_per_rank` (8) views forward+backward per rank against seeded dL/dimage tensors and sums
+their per-Gaussian gradients into one flat buffer; with N > 1 ranks the views of a step are
+partitioned over the ranks (weak scaling: 8 views per rank) and the flat gradient buffer is
+all-reduced over NCCL once per step.  `value` = frames (views) per second over all ranks.
+
+Reference arm (`--impl reference`): the reference's own rasteriser is an un-vendored submodule
+that is neither in /root/reference nor on the GPU box, so this arm times the CPU oracle (a port of
+the same splat math, oracle/splat_oracle.c, all host threads) on one frame per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fwd+bwd frames/sec @1M Gaussians 800x800"
+WORKLOADS = {
+    # name: (P, W, H, camera kind, extent, log-scale mean)
+    "h0": (1_000_000, 800, 800, "nerf", 1.3, math.log(0.01)),
+    "c1": (100_000, 800, 800, "nerf", 1.3, math.log(0.01)),
+    "c3": (1_000_000, 1245, 825, "bicycle", 3.0, math.log(0.008)),
+}
+VIEWS_PER_RANK = int(os.environ.get("DMGS_BENCH_VIEWS", "8"))
+
+
+def make_camera(kind, idx, W, H):
+    from dmgs_b200 import synthetic as S
+    return S.nerf_synthetic_camera(idx, W, H) if kind == "nerf" else S.bicycle_camera(idx, W, H)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k] == "Active" for r in self.rows)]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def oracle_frame(O, pr, cl_np, dL):
+    fwd = O.render_forward(pr, cl_np["means3D"], cl_np["opacities"], scales=cl_np["scales"],
+                           rotations=cl_np["rotations"], shs=cl_np["shs"])
+    O.render_backward(pr, fwd, dL, cl_np["means3D"], scales=cl_np["scales"], rotations=cl_np["rotations"],
+                      shs=cl_np["shs"])
+    return fwd
+
+
+def cpu_baseline(workload, frames, warm=1):
+    """Times the CPU oracle (port of the same splat math) on `frames` frames of the workload."""
+    import numpy as np
+    import torch
+    from dmgs_b200 import synthetic as S
+    from oracle import oracle as O
+    P, W, H, kind, extent, lsm = WORKLOADS[workload]
+    cl = S.random_cloud(P, seed=0, extent=extent, log_scale_mean=lsm)
+    cl_np = {k: v.numpy() for k, v in cl.items()}
+    dL = torch.randn(3, H, W, generator=torch.Generator().manual_seed(77)).numpy()
+    times = []
+    for f in range(warm + frames):
+        cam = make_camera(kind, f, W, H)
+        pr = O.make_params(P, W, H, math.tan(cam.FoVx / 2), math.tan(cam.FoVy / 2), [0, 0, 0],
+                           cam.world_view_transform.numpy(), cam.full_proj_transform.numpy(),
+                           cam.camera_center.numpy())
+        t0 = time.perf_counter()
+        oracle_frame(O, pr, cl_np, dL)
+        times.append(time.perf_counter() - t0)
+    t = sum(times[warm:])
+    return {"value": frames / t, "unit": "frames/s", "cores": O.num_threads(), "kind": "port",
+            "sample": f"{frames} full frames (fwd+bwd) of workload {workload} ({P} Gaussians, {W}x{H}), "
+                      f"OpenMP over Gaussians/tiles, {warm} warm-up frame"}, t / frames
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    K, Wm = max(args.steps, 1), max(args.warmup, 0)
+    P, W, H, kind, _, _ = WORKLOADS[args.workload]
+    cb, sec_per_frame = cpu_baseline(args.workload, K, warm=min(Wm, 2))
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": K, "warmup": Wm, "ms_per_step": 1e3 * sec_per_frame, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload.upper()}: {P} random Gaussians SH-3, {W}x{H}, shs+scales+rotations, "
+                                   "fwd+bwd; reference arm = CPU oracle (reference rasteriser sources/install unavailable), "
+                                   "one frame per step"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from dmgs_b200 import GaussianRasterizationSettings, GaussianRasterizer, _lib as L, synthetic as S
+    from dmgs_b200.rasterizer import rasterize_backward, rasterize_forward
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a GPU (there is no CPU path in the product)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = L.lib()
+
+    P, W, H, kind, extent, lsm = WORKLOADS[args.workload]
+    K, Wm = args.steps, max(args.warmup, 3)
+    cl = S.random_cloud(P, seed=0, extent=extent, log_scale_mean=lsm)  # replicated on every rank
+    names = ["means3D", "scales", "rotations", "opacities", "shs"]
+    host = {k: cl[k].pin_memory() for k in names}
+    d = {k: host[k].to(dev) for k in names}
+    n_views = VIEWS_PER_RANK * world
+    cams = [make_camera(kind, v, W, H).to(dev) for v in range(n_views)]
+    my_views = [v for v in range(n_views) if v % world == rank]
+    bg = torch.zeros(3, device=dev)
+    settings = [GaussianRasterizationSettings(H, W, math.tan(c.FoVx / 2), math.tan(c.FoVy / 2), bg, 1.0,
+                                              c.world_view_transform, c.full_proj_transform, 3, c.camera_center,
+                                              False, False) for c in cams]
+    gen = torch.Generator().manual_seed(77)
+    dLs = [torch.randn(3, H, W, generator=gen).to(dev) for _ in range(min(n_views, 8))]
+    # flat per-Gaussian gradient buffer [P, 59+3]: the all-reduce payload
+    widths = {"means3D": 3, "means2D": 3, "opacities": 1, "scales": 3, "rotations": 4, "shs": 48}
+    flat = torch.zeros(P * sum(widths.values()), dtype=torch.float32, device=dev)
+    acc, o = {}, 0
+    for k, w in widths.items():
+        acc[k] = flat[o:o + P * w].view((P, 16, 3) if k == "shs" else (P, w))
+        o += P * w
+    stage_ms, ev_log = {}, []
+
+    def hook_factory(events):
+        def hook(name):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            events.append((name, e))
+        return hook
+
+    stats = {"R": 0, "frames": 0}
+
+    def step(record):
+        flat.zero_()
+        for j, v in enumerate(my_views):
+            events = []
+            if record:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                events.append(("start", e0))
+            hook = hook_factory(events) if record else None
+            color, radii, st = rasterize_forward(settings[v], d["means3D"], d["opacities"], d["shs"], None,
+                                                 d["scales"], d["rotations"], None, stage_hook=hook)
+            rasterize_backward(st, dLs[j % len(dLs)], d["means3D"], d["shs"], d["scales"], d["rotations"], None, False,
+                               stage_hook=hook, accumulate_into=acc)
+            stats["R"] += st.num_rendered
+            stats["frames"] += 1
+            if record:
+                ev_log.append(events)
+        if world > 1:
+            dist.all_reduce(flat)
+
+    for _ in range(Wm):
+        step(False)
+    torch.cuda.synchronize()
+    stats.update(R=0, frames=0)
+    launches0 = lib.dmgs_launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(K):
+        step(True)
+    t1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = t0.elapsed_time(t1)
+    launches = lib.dmgs_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tm = torch.tensor([ms], device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms = float(tm.item())
+        lt = torch.tensor([float(launches)], device=dev)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    for events in ev_log:
+        for (n0, a), (n1, b) in zip(events[:-1], events[1:]):
+            stage_ms[n1] = stage_ms.get(n1, 0.0) + a.elapsed_time(b)
+    frames_rank = stats["frames"]
+    for k in stage_ms:
+        stage_ms[k] /= max(frames_rank, 1)
+    Ravg = stats["R"] / max(frames_rank, 1)
+    value = (VIEWS_PER_RANK * world * K) / (ms / 1e3)
+
+    # ---- end-to-end through the public module with HOST inputs (rank-local; max over ranks)
+    def e2e_step():
+        t = {k: host[k].to(dev, non_blocking=True).requires_grad_() for k in names}
+        loss = torch.zeros((), device=dev)
+        for j, v in enumerate(my_views):
+            ras = GaussianRasterizer(settings[v])
+            m2d = torch.zeros_like(t["means3D"], requires_grad=True)
+            img, radii = ras(means3D=t["means3D"], means2D=m2d, shs=t["shs"], colors_precomp=None,
+                             opacities=t["opacities"], scales=t["scales"], rotations=t["rotations"],
+                             cov3D_precomp=None)
+            l = (img * dLs[j % len(dLs)]).sum()
+            l.backward()
+            loss = loss + l.detach()
+        if world > 1:
+            g = torch.cat([t[k].grad.reshape(-1) for k in names])
+            dist.all_reduce(g)
+        return float(loss.cpu())  # device -> host read of the step's result
+
+    Ke = max(2, K // 4)
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    te = time.perf_counter()
+    for _ in range(Ke):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - te
+    if world > 1:
+        tm = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        e2e_s = float(tm.item())
+    e2e_value = (VIEWS_PER_RANK * world * Ke) / e2e_s
+    h2d = sum(host[k].numel() * 4 for k in names)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (single-kernel stages are timed exactly by the hooks)
+    peak, peak_src = peaks()
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    B_in, B_geo, B_gin = 236, 75, 232
+    alg = {  # algorithmic bytes per frame for each stage
+        "preprocess_sort_scan": P * (B_in + B_geo) + 4 * 16 * P + 8 * P,
+        "binning": 8 * Ravg + 2 * 16 * Ravg + 4 * Ravg + 8 * T,
+        "blend_fwd": 40 * Ravg + 20 * W * H,
+        "blend_bwd": 40 * Ravg + 20 * W * H + 40 * P,
+        "preprocess_bwd": P * (B_in + B_geo + 40) + P * B_gin,
+    }
+    single = ["blend_fwd", "blend_bwd", "preprocess_bwd"]
+    dom = max(single, key=lambda k: stage_ms.get(k, 0.0))
+    ach = alg[dom] / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms.get(dom) else 0.0
+    stages = {k: {"ms": round(v, 4), "alg_GBps": round(alg[k] / (v * 1e-3) / 1e9, 1) if v > 0 else None}
+              for k, v in stage_ms.items()}
+    cb = None
+    if world == 1 and not args.no_cpu_baseline:
+        cb, _ = cpu_baseline(args.workload, 3)
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{args.workload.upper()}: {P} random Gaussians SH-3, {W}x{H}, shs+scales+rotations, fwd+bwd",
+                   "views_per_rank_per_step": VIEWS_PER_RANK, "parallelism": f"views x{world} (replicated Gaussians, "
+                   "NCCL all-reduce of the flat gradient buffer once per step)" if world > 1 else "single GPU",
+                   "avg_instances_R": Ravg, "l2": "inputs (236 MB) + state (>230 MB) exceed the 126 MB L2; no flush needed"},
+        "stages": stages,
+        "roofline": {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                     "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                     "note": "blend kernels are FP32-issue bound, not HBM bound (DESIGN.md section 5)"},
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "steps": Ke},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if cb is not None:
+        line["cpu_baseline"] = cb
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="h0", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,5 +1,6 @@
 // api.cu -- the extern "C" surface declared in include/dmgs_raster.h.
 #include <stdarg.h>
+#include <atomic>
 #include <string.h>
 
 #include "common.cuh"
@@ -8,6 +9,8 @@
 namespace dmgs {
 
 static thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add((uint64_t)n); }
 
 void set_error(const char *fmt, ...)
 {
@@ -52,6 +55,7 @@ using namespace dmgs;
 extern "C" {
 
 int dmgs_abi_version(void) { return 1; }
+uint64_t dmgs_launch_count(void) { return g_launches.load(); }
 const char *dmgs_last_error(void) { return g_err; }
 
 size_t dmgs_geom_bytes(int32_t P) { return geom_layout(P).total; }
@@ -175,21 +179,15 @@ int dmgs_blend_forward(const dmgs_params *prm, const void *geom, const void *bin
     return check_stage(prm, s, "blend forward");
 }
 
-int dmgs_backward(const dmgs_params *prm, const float *means3D, const float *scales, const float *rotations,
-                  const float *cov3D_precomp, const float *shs, const int32_t *radii, const void *geom,
-                  const void *binning, const void *image, int64_t R, const float *dL_dpix, float *dL_dmeans3D,
-                  float *dL_dmeans2D, float *dL_dopacity, float *dL_dcolors_precomp, float *dL_dshs, float *dL_dscales,
-                  float *dL_drotations, float *dL_dcov3D, void *scratch, void *stream)
+int dmgs_blend_backward(const dmgs_params *prm, const void *geom, const void *binning, const void *image, int64_t R,
+                        const float *dL_dpix, void *scratch, void *stream)
 {
     int rc = validate(prm);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const int P = prm->P;
     if (P == 0) return 0;
-    if (!means3D || !radii || !geom || !binning || !image || !dL_dpix || !dL_dmeans3D || !dL_dmeans2D || !dL_dopacity || !scratch) {
-        set_error("NULL required pointer");
-        return -6;
-    }
+    if (!geom || !binning || !image || !dL_dpix || !scratch) { set_error("NULL required pointer"); return -6; }
     const GeomLayout GL = geom_layout(P);
     const BinLayout BL = bin_layout(P, R, prm->image_width, prm->image_height);
     const ImgLayout IL = img_layout(prm->image_width, prm->image_height);
@@ -198,13 +196,44 @@ int dmgs_backward(const dmgs_params *prm, const float *means3D, const float *sca
     if (R > 0) {
         rc = launch_blend_bwd(prm, geom, GL, binning, BL, image, IL, dL_dpix, grad_blend, s);
         if (rc) return rc;
-        if ((rc = check_stage(prm, s, "blend backward"))) return rc;
     }
-    rc = launch_preprocess_bwd(prm, means3D, scales, rotations, cov3D_precomp, shs, radii, geom, GL, grad_blend,
-                               dL_dmeans3D, dL_dmeans2D, dL_dopacity, dL_dcolors_precomp, dL_dshs, dL_dscales,
-                               dL_drotations, dL_dcov3D, s);
+    return check_stage(prm, s, "blend backward");
+}
+
+int dmgs_preprocess_backward(const dmgs_params *prm, const float *means3D, const float *scales, const float *rotations,
+                             const float *cov3D_precomp, const float *shs, const int32_t *radii, const void *geom,
+                             const void *scratch, float *dL_dmeans3D, float *dL_dmeans2D, float *dL_dopacity,
+                             float *dL_dcolors_precomp, float *dL_dshs, float *dL_dscales, float *dL_drotations,
+                             float *dL_dcov3D, int32_t accumulate, void *stream)
+{
+    int rc = validate(prm);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int P = prm->P;
+    if (P == 0) return 0;
+    if (!means3D || !radii || !geom || !dL_dmeans3D || !dL_dmeans2D || !dL_dopacity || !scratch) {
+        set_error("NULL required pointer");
+        return -6;
+    }
+    const GeomLayout GL = geom_layout(P);
+    rc = launch_preprocess_bwd(prm, means3D, scales, rotations, cov3D_precomp, shs, radii, geom, GL,
+                               (const float *)scratch, dL_dmeans3D, dL_dmeans2D, dL_dopacity, dL_dcolors_precomp,
+                               dL_dshs, dL_dscales, dL_drotations, dL_dcov3D, accumulate, s);
     if (rc) return rc;
     return check_stage(prm, s, "preprocess backward");
+}
+
+int dmgs_backward(const dmgs_params *prm, const float *means3D, const float *scales, const float *rotations,
+                  const float *cov3D_precomp, const float *shs, const int32_t *radii, const void *geom,
+                  const void *binning, const void *image, int64_t R, const float *dL_dpix, float *dL_dmeans3D,
+                  float *dL_dmeans2D, float *dL_dopacity, float *dL_dcolors_precomp, float *dL_dshs, float *dL_dscales,
+                  float *dL_drotations, float *dL_dcov3D, void *scratch, void *stream)
+{
+    int rc = dmgs_blend_backward(prm, geom, binning, image, R, dL_dpix, scratch, stream);
+    if (rc) return rc;
+    return dmgs_preprocess_backward(prm, means3D, scales, rotations, cov3D_precomp, shs, radii, geom, scratch,
+                                    dL_dmeans3D, dL_dmeans2D, dL_dopacity, dL_dcolors_precomp, dL_dshs, dL_dscales,
+                                    dL_drotations, dL_dcov3D, 0, stream);
 }
 
 int dmgs_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,

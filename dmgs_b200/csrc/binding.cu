@@ -113,6 +113,7 @@ int launch_bind_fwd(int64_t F, int k, const float *verts, const int64_t *faces, 
     bind_fwd_kernel<<<(unsigned)((F + 255) / 256), 256, 0, s>>>(F, k, verts, faces, bc, rad_base, thin_z, g, adaptive,
                                                                  xyz, cov6, rot_t2w);
     DMGS_CUDA(cudaGetLastError());
+    count_launches(1);
     return 0;
 }
 
@@ -274,6 +275,7 @@ int launch_bind_bwd(int64_t F, int k, const float *verts, const int64_t *faces, 
     bind_bwd_kernel<<<(unsigned)((F + 255) / 256), 256, 0, s>>>(F, k, verts, faces, bc, rad_base, thin_z, g, adaptive,
                                                                  dL_dxyz, dL_dcov6, dL_drot, dverts, dg);
     DMGS_CUDA(cudaGetLastError());
+    count_launches(1);
     return 0;
 }
 

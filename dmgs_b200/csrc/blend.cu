@@ -100,6 +100,7 @@ int launch_blend_fwd(const dmgs_params *prm, const void *geom, const GeomLayout 
                                                       at<float4>(geom, GL.rec), at<float4>(geom, GL.rgb), out_color,
                                                       at<float>(image, IL.final_T), at<uint32_t>(image, IL.n_contrib));
     DMGS_CUDA(cudaGetLastError());
+    count_launches(1);
     return 0;
 }
 
@@ -232,6 +233,7 @@ int launch_blend_bwd(const dmgs_params *prm, const void *geom, const GeomLayout 
                                                       at<float>(image, IL.final_T), at<uint32_t>(image, IL.n_contrib),
                                                       dL_dpix, grad_blend);
     DMGS_CUDA(cudaGetLastError());
+    count_launches(1);
     return 0;
 }
 

@@ -21,6 +21,7 @@ namespace dmgs {
 // ----------------------------------------------------------------------------- errors
 void set_error(const char *fmt, ...);
 int check_stage(const dmgs_params *prm, cudaStream_t s, const char *stage);
+void count_launches(int n);  // kernels launched by this library (bench.py reports it)
 
 #define DMGS_CUDA(call)                                                              \
     do {                                                                             \

@@ -14,7 +14,7 @@ int launch_preprocess_bwd(const dmgs_params *prm, const float *means3D, const fl
                           const float *cov3D_precomp, const float *shs, const int32_t *radii, const void *geom,
                           const GeomLayout &L, const float *grad_blend, float *dL_dmeans3D, float *dL_dmeans2D,
                           float *dL_dopacity, float *dL_dcolprec, float *dL_dshs, float *dL_dscales, float *dL_drots,
-                          float *dL_dcov3D, cudaStream_t s);
+                          float *dL_dcov3D, int accumulate, cudaStream_t s);
 int launch_mark_visible(int P, const float *means3D, const float *view_dev, uint8_t *visible, cudaStream_t s);
 int launch_exp_array(const float *x, float *y, int64_t n, cudaStream_t s);
 

@@ -240,6 +240,7 @@ int launch_preprocess_fwd(const dmgs_params *prm, const float *means3D, const fl
         at<float4>(geom, L.rec), at<float4>(geom, L.rgb), at<uint8_t>(geom, L.clamped), at<float>(geom, L.cov3D),
         at<uint32_t>(geom, L.tiles), at<uint2>(geom, L.rect), at<uint32_t>(geom, L.keys_a), at<uint32_t>(geom, L.order));
     DMGS_CUDA(cudaGetLastError());
+    count_launches(1);
     return 0;
 }
 
@@ -254,7 +255,8 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
                       const float4 *__restrict__ rgb4, const float4 *__restrict__ grad_blend,
                       float *__restrict__ dL_dmeans3D, float *__restrict__ dL_dmeans2D,
                       float *__restrict__ dL_dopacity, float *__restrict__ dL_dcolprec, float *__restrict__ dL_dshs,
-                      float *__restrict__ dL_dscales, float *__restrict__ dL_drots, float *__restrict__ dL_dcov3D)
+                      float *__restrict__ dL_dscales, float *__restrict__ dL_drots, float *__restrict__ dL_dcov3D,
+                      const int accumulate)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pr.P) return;
@@ -344,13 +346,13 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
                     const size_t idx = pr.sh_layout == 0 ? ((size_t)i * M + k) * 3 + ch : ((size_t)i * 3 + ch) * M + k;
                     if (k < nb) {
                         sv[k] = __ldg(shs + idx);
-                        dL_dshs[idx] = bas[k] * g;
+                        dL_dshs[idx] = accumulate ? dL_dshs[idx] + bas[k] * g : bas[k] * g;
                     } else {
                         sv[k] = 0.0f;
-                        if (k < M) dL_dshs[idx] = 0.0f;
+                        if (k < M && !accumulate) dL_dshs[idx] = 0.0f;
                     }
                 }
-                for (int k = 16; k < M; ++k) {
+                for (int k = 16; k < M && !accumulate; ++k) {
                     const size_t idx = pr.sh_layout == 0 ? ((size_t)i * M + k) * 3 + ch : ((size_t)i * 3 + ch) * M + k;
                     dL_dshs[idx] = 0.0f;
                 }
@@ -409,8 +411,33 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
             gq[2] = 2.0f * (qx * (dR[0][1] + dR[1][0]) + r * (dR[0][2] - dR[2][0]) + qz * (dR[1][2] + dR[2][1])) - 4.0f * qy * (dR[0][0] + dR[2][2]);
             gq[3] = 2.0f * (r * (dR[1][0] - dR[0][1]) + qx * (dR[0][2] + dR[2][0]) + qy * (dR[1][2] + dR[2][1])) - 4.0f * qz * (dR[0][0] + dR[1][1]);
         }
-    } else if (shs && dL_dshs) {
+    } else if (shs && dL_dshs && !accumulate) {
         for (int k = 0; k < 3 * M; ++k) dL_dshs[(size_t)i * 3 * M + k] = 0.0f;
+    }
+    if (accumulate) {
+        if (!vis) return;  // nothing to add
+#pragma unroll
+        for (int k = 0; k < 3; ++k) dL_dmeans3D[3 * (size_t)i + k] += gm[k];
+        dL_dmeans2D[3 * (size_t)i] += d2x;
+        dL_dmeans2D[3 * (size_t)i + 1] += d2y;
+        dL_dopacity[i] += dop;
+        if (dL_dcolprec) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) dL_dcolprec[3 * (size_t)i + k] += dcol[k];
+        }
+        if (dL_dcov3D) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) dL_dcov3D[6 * (size_t)i + k] += g6[k];
+        }
+        if (dL_dscales) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) dL_dscales[3 * (size_t)i + k] += gs[k];
+        }
+        if (dL_drots) {
+            float4 o = reinterpret_cast<float4 *>(dL_drots)[i];
+            reinterpret_cast<float4 *>(dL_drots)[i] = make_float4(o.x + gq[0], o.y + gq[1], o.z + gq[2], o.w + gq[3]);
+        }
+        return;
     }
 
 #pragma unroll
@@ -438,15 +465,16 @@ int launch_preprocess_bwd(const dmgs_params *prm, const float *means3D, const fl
                           const float *cov3D_precomp, const float *shs, const int32_t *radii, const void *geom,
                           const GeomLayout &L, const float *grad_blend, float *dL_dmeans3D, float *dL_dmeans2D,
                           float *dL_dopacity, float *dL_dcolprec, float *dL_dshs, float *dL_dscales, float *dL_drots,
-                          float *dL_dcov3D, cudaStream_t s)
+                          float *dL_dcov3D, int accumulate, cudaStream_t s)
 {
     const int P = prm->P;
     if (P <= 0) return 0;
     preprocess_bwd_kernel<<<(P + 255) / 256, 256, 0, s>>>(
         make_dev_params(prm), means3D, scales, rotations, cov3D_precomp, shs, radii, at<float>(geom, L.cov3D), at<uint8_t>(geom, L.clamped),
         at<float4>(geom, L.rgb), reinterpret_cast<const float4 *>(grad_blend), dL_dmeans3D, dL_dmeans2D, dL_dopacity,
-        dL_dcolprec, dL_dshs, dL_dscales, dL_drots, dL_dcov3D);
+        dL_dcolprec, dL_dshs, dL_dscales, dL_drots, dL_dcov3D, accumulate);
     DMGS_CUDA(cudaGetLastError());
+    count_launches(1);
     return 0;
 }
 
@@ -465,6 +493,7 @@ int launch_mark_visible(int P, const float *means3D, const float *view_dev, uint
     if (P <= 0) return 0;
     mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, view_dev, visible);
     DMGS_CUDA(cudaGetLastError());
+    count_launches(1);
     return 0;
 }
 
@@ -478,6 +507,7 @@ int launch_exp_array(const float *x, float *y, int64_t n, cudaStream_t s)
     if (n <= 0) return 0;
     exp_array_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, y, n);
     DMGS_CUDA(cudaGetLastError());
+    count_launches(1);
     return 0;
 }
 

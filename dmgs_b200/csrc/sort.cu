@@ -114,6 +114,7 @@ int exclusive_scan_u32(const uint32_t *in, const uint32_t *gather, uint32_t *out
     scan_spine_kernel<<<1, SCAN_THREADS, 0, s>>>(scan_tmp, nb, total);
     scan_apply_kernel<<<nb, SCAN_THREADS, 0, s>>>(in, gather, out, n, scan_tmp);
     DMGS_CUDA(cudaGetLastError());
+    count_launches(3);
     return 0;
 }
 
@@ -204,6 +205,7 @@ int radix_pass(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_
     if (rc) return rc;
     radix_scatter_kernel<<<nblocks, RP_THREADS, 0, s>>>(keys_in, vals_in, keys_out, vals_out, n, shift, bins, nblocks, hist);
     DMGS_CUDA(cudaGetLastError());
+    count_launches(2);
     return 0;
 }
 
@@ -260,6 +262,7 @@ int launch_emit_instances(int P, const uint32_t *order, const uint32_t *offsets,
     if (P <= 0) return 0;
     emit_instances_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, order, offsets, tiles, rect, gx, inst_tile, inst_gidx);
     DMGS_CUDA(cudaGetLastError());
+    count_launches(1);
     return 0;
 }
 
@@ -280,6 +283,7 @@ int launch_tile_ranges(int64_t R, const uint32_t *sorted_tiles, uint2 *ranges, i
     if (R <= 0) return 0;
     tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(R, sorted_tiles, ranges);
     DMGS_CUDA(cudaGetLastError());
+    count_launches(1);
     return 0;
 }
 
@@ -298,6 +302,7 @@ int launch_sorted_keys(int64_t R, const uint32_t *sorted_tiles, const uint32_t *
     if (R <= 0) return 0;
     sorted_keys_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(R, sorted_tiles, sorted_gidx, depths, keys_out);
     DMGS_CUDA(cudaGetLastError());
+    count_launches(1);
     return 0;
 }
 

@@ -11,6 +11,7 @@ Extensions that keep the drop-in intact (all optional, default = upstream behavi
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import NamedTuple, Optional
 
 import torch
@@ -34,19 +35,37 @@ class GaussianRasterizationSettings(NamedTuple):
     debug: bool
 
 
-def _cached_host(t: torch.Tensor):
-    """Flat float list of a small camera tensor (one D2H per distinct tensor version)."""
-    key = (t.data_ptr(), t._version, tuple(t.shape), str(t.device))
-    hit = _cached_host.cache.get(key)
-    if hit is None:
-        if len(_cached_host.cache) > 4096:
-            _cached_host.cache.clear()
-        hit = [float(v) for v in t.detach().reshape(-1).to("cpu", torch.float32).tolist()]
-        _cached_host.cache[key] = hit
-    return hit
+_HOST_CACHE: dict = {}
 
 
-_cached_host.cache = {}
+def _host_values(tensors):
+    """Flat float lists of the small camera tensors (bg, viewmatrix, projmatrix, campos).
+
+    Values are cached per tensor OBJECT (weak reference + in-place version counter), never per
+    data pointer: the caching allocator hands the same address to unrelated tensors.  All misses
+    of one call share a single device->host copy."""
+    out, miss = [None] * len(tensors), []
+    for i, t in enumerate(tensors):
+        hit = _HOST_CACHE.get(id(t))
+        if hit is not None and hit[0]() is t and hit[1] == t._version:
+            out[i] = hit[2]
+        else:
+            miss.append(i)
+    if miss:
+        flat = torch.cat([tensors[i].detach().reshape(-1).float() for i in miss]).cpu().tolist()
+        o = 0
+        for i in miss:
+            t = tensors[i]
+            n = t.numel()
+            vals = flat[o:o + n]
+            o += n
+            out[i] = vals
+            key = id(t)
+            try:
+                _HOST_CACHE[key] = (weakref.ref(t, lambda _r, k=key: _HOST_CACHE.pop(k, None)), t._version, vals)
+            except TypeError:
+                pass
+    return out
 
 
 def make_params(settings: GaussianRasterizationSettings, P: int, sh_coeffs: int, sh_layout: int,
@@ -60,10 +79,8 @@ def make_params(settings: GaussianRasterizationSettings, P: int, sh_coeffs: int,
     prm.debug = int(bool(settings.debug))
     prm.tanfovx, prm.tanfovy = float(settings.tanfovx), float(settings.tanfovy)
     prm.scale_modifier = float(settings.scale_modifier)
-    prm.bg[:] = _cached_host(settings.bg)
-    prm.viewmatrix[:] = _cached_host(settings.viewmatrix)
-    prm.projmatrix[:] = _cached_host(settings.projmatrix)
-    prm.campos[:] = _cached_host(settings.campos)
+    bg, view, proj, campos = _host_values([settings.bg, settings.viewmatrix, settings.projmatrix, settings.campos])
+    prm.bg[:], prm.viewmatrix[:], prm.projmatrix[:], prm.campos[:] = bg, view, proj, campos
     return prm
 
 
@@ -131,7 +148,7 @@ class RasterState:
 
 
 def rasterize_forward(settings, means3D, opacities, shs, colors_precomp, scales, rotations, cov3D_precomp,
-                      sh_layout=0, sh_activation=0):
+                      sh_layout=0, sh_activation=0, stage_hook=None):
     """Runs the three forward stages; returns (color [3,H,W], radii [P] int32, RasterState)."""
     dev = means3D.device
     if dev.type != "cuda":
@@ -152,16 +169,24 @@ def rasterize_forward(settings, means3D, opacities, shs, colors_precomp, scales,
     L.check(lib.dmgs_preprocess_forward(C.byref(prm), L.ptr(means3D), L.ptr(scales), L.ptr(rotations),
                                         L.ptr(cov3D_precomp), L.ptr(opacities), L.ptr(shs), L.ptr(colors_precomp),
                                         L.ptr(radii), L.ptr(geom), L.ptr(nr), stream), "dmgs_preprocess_forward")
+    if stage_hook is not None:
+        stage_hook("preprocess_sort_scan")
     R = int(nr.item())  # the one host read-back of the forward (upstream does the same after its scan)
     binning = torch.empty(lib.dmgs_binning_bytes(P, R, W, H), dtype=torch.uint8, device=dev)
     L.check(lib.dmgs_bin_forward(C.byref(prm), L.ptr(geom), R, L.ptr(binning), stream), "dmgs_bin_forward")
+    if stage_hook is not None:
+        stage_hook("binning")
     L.check(lib.dmgs_blend_forward(C.byref(prm), L.ptr(geom), L.ptr(binning), R, L.ptr(color), L.ptr(image), stream),
             "dmgs_blend_forward")
+    if stage_hook is not None:
+        stage_hook("blend_fwd")
     return color, radii, RasterState(prm, geom, binning, image, R, radii)
 
 
 def rasterize_backward(state: RasterState, grad_color, means3D, shs, scales, rotations, cov3D_precomp,
-                       want_colors_precomp):
+                       want_colors_precomp, stage_hook=None, accumulate_into=None):
+    """accumulate_into: optional dict of preallocated gradient tensors (keys means3D, means2D, opacities,
+    colors_precomp, shs, scales, rotations, cov3D_precomp) that the gradients are ADDED to."""
     lib = L.lib()
     prm, P, dev = state.prm, state.prm.P, means3D.device
     z = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
@@ -171,12 +196,29 @@ def rasterize_backward(state: RasterState, grad_color, means3D, shs, scales, rot
     g_scales = z(P, 3) if scales is not None else None
     g_rots = z(P, 4) if rotations is not None else None
     g_cov = z(P, 6) if cov3D_precomp is not None else None
+    if accumulate_into is not None:
+        a = accumulate_into
+        g_means3D, g_means2D, g_op = a["means3D"], a["means2D"], a["opacities"]
+        g_col = a.get("colors_precomp") if want_colors_precomp else None
+        g_shs = a.get("shs") if shs is not None else None
+        g_scales = a.get("scales") if scales is not None else None
+        g_rots = a.get("rotations") if rotations is not None else None
+        g_cov = a.get("cov3D_precomp") if cov3D_precomp is not None else None
     scratch = torch.empty(lib.dmgs_backward_scratch_bytes(P), dtype=torch.uint8, device=dev)
-    L.check(lib.dmgs_backward(C.byref(prm), L.ptr(means3D), L.ptr(scales), L.ptr(rotations), L.ptr(cov3D_precomp),
-                              L.ptr(shs), L.ptr(state.radii), L.ptr(state.geom), L.ptr(state.binning),
-                              L.ptr(state.image), state.num_rendered, L.ptr(grad_color), L.ptr(g_means3D),
-                              L.ptr(g_means2D), L.ptr(g_op), L.ptr(g_col), L.ptr(g_shs), L.ptr(g_scales), L.ptr(g_rots),
-                              L.ptr(g_cov), L.ptr(scratch), _stream()), "dmgs_backward")
+    stream = _stream()
+    L.check(lib.dmgs_blend_backward(C.byref(prm), L.ptr(state.geom), L.ptr(state.binning), L.ptr(state.image),
+                                    state.num_rendered, L.ptr(grad_color), L.ptr(scratch), stream),
+            "dmgs_blend_backward")
+    if stage_hook is not None:
+        stage_hook("blend_bwd")
+    L.check(lib.dmgs_preprocess_backward(C.byref(prm), L.ptr(means3D), L.ptr(scales), L.ptr(rotations),
+                                         L.ptr(cov3D_precomp), L.ptr(shs), L.ptr(state.radii), L.ptr(state.geom),
+                                         L.ptr(scratch), L.ptr(g_means3D), L.ptr(g_means2D), L.ptr(g_op), L.ptr(g_col),
+                                         L.ptr(g_shs), L.ptr(g_scales), L.ptr(g_rots), L.ptr(g_cov),
+                                         1 if accumulate_into is not None else 0, stream),
+            "dmgs_preprocess_backward")
+    if stage_hook is not None:
+        stage_hook("preprocess_bwd")
     return g_means3D, g_means2D, g_shs, g_col, g_op, g_scales, g_rots, g_cov
 
 

@@ -83,6 +83,18 @@ int dmgs_backward(const dmgs_params *prm, const float *means3D, const float *sca
                   float *dL_dshs, float *dL_dscales, float *dL_drotations, float *dL_dcov3D, void *scratch,
                   void *stream);
 size_t dmgs_backward_scratch_bytes(int32_t P);
+/* The two halves of dmgs_backward, callable separately (bench.py brackets them with CUDA events):
+ * K7 accumulates per-Gaussian blend gradients into `scratch`; K8+K9 consume it.  With
+ * accumulate != 0 the gradients are ADDED to the output buffers (view-batched training:
+ * one flat gradient buffer summed over the views of a step, no extra accumulation pass). */
+int dmgs_blend_backward(const dmgs_params *prm, const void *geom, const void *binning, const void *image,
+                        int64_t num_rendered, const float *dL_dpix, void *scratch, void *stream);
+int dmgs_preprocess_backward(const dmgs_params *prm, const float *means3D, const float *scales,
+                             const float *rotations, const float *cov3D_precomp, const float *shs,
+                             const int32_t *radii, const void *geom, const void *scratch, float *dL_dmeans3D,
+                             float *dL_dmeans2D, float *dL_dopacity, float *dL_dcolors_precomp, float *dL_dshs,
+                             float *dL_dscales, float *dL_drotations, float *dL_dcov3D, int32_t accumulate,
+                             void *stream);
 
 /* ---- markVisible (K10): visible[i] = view-space z > 0.2 */
 int dmgs_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,
@@ -122,6 +134,8 @@ int dmgs_exp_array(const float *x, float *y, int64_t n, void *stream);
 
 const char *dmgs_last_error(void);
 int dmgs_abi_version(void);
+/* Number of CUDA kernels this library has launched in this process (monotonic). */
+uint64_t dmgs_launch_count(void);
 
 #ifdef __cplusplus
 }
