@@ -5,6 +5,7 @@
 // gaussian_renderer/__init__.py:74-78).  One thread per Gaussian; HBM-bound.
 #include "common.cuh"
 #include "kernels.cuh"
+#include "sh_stage.cuh"
 
 namespace dmgs {
 
@@ -111,11 +112,18 @@ __device__ __forceinline__ void ewa_project(const DevParams &pr, float x, float 
     e.c = dot3(e.T1[0], e.u1[0], e.T1[1], e.u1[1], e.T1[2], e.u1[2]) + 0.3f;
 }
 
-__device__ __forceinline__ float sh_load(const float *__restrict__ shs, const DevParams &pr, int i, int k, int ch)
+// SHMODE 0: coefficients read straight from global memory (any M);
+// SHMODE 1 / 2: M == 16 rows staged through shared memory by TMA, layout [P,16,3] / [P,3,16].
+template <int SHMODE>
+__device__ __forceinline__ float sh_get(const float *__restrict__ shs, const DevParams &pr, const float *r, int i, int k,
+                                        int ch)
 {
+    if (SHMODE == 1) return r[k * 3 + ch];
+    if (SHMODE == 2) return r[ch * 16 + k];
     return pr.sh_layout == 0 ? __ldg(shs + ((size_t)i * pr.M + k) * 3 + ch) : __ldg(shs + ((size_t)i * 3 + ch) * pr.M + k);
 }
 
+template <int SHMODE>
 __global__ void __launch_bounds__(256)
 preprocess_fwd_kernel(const __grid_constant__ DevParams pr, const float *__restrict__ means3D, const float *__restrict__ scales,
                       const float *__restrict__ rotations, const float *__restrict__ cov3D_precomp,
@@ -125,8 +133,12 @@ preprocess_fwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
                       uint8_t *__restrict__ clamped, float *__restrict__ cov3D, uint32_t *__restrict__ tiles,
                       uint2 *__restrict__ rect, uint32_t *__restrict__ sort_key, uint32_t *__restrict__ sort_val)
 {
+    extern __shared__ __align__(16) unsigned char dsm[];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= pr.P) return;
+    const bool inb = i < pr.P;
+    ShStage stage;
+    if (SHMODE) stage.init(dsm);
+
     // invisible defaults
     int rad = 0;
     uint32_t ntiles = 0, key = 0xFFFFFFFFu;
@@ -135,10 +147,16 @@ preprocess_fwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
     uint2 rc = make_uint2(0, 0);
     uint8_t clampbits = 0;
     float c6[6] = {0, 0, 0, 0, 0, 0};
+    float x = 0, y = 0, z = 0, tz = 0;
+    if (inb) {
+        x = means3D[3 * i]; y = means3D[3 * i + 1]; z = means3D[3 * i + 2];
+        tz = affine3(pr.V, 2, x, y, z);
+    }
+    const bool near_ok = inb && tz > DMGS_NEAR;
+    // fetch the SH row while the projection math runs (rows of near-culled Gaussians are skipped)
+    if (SHMODE) stage.load(near_ok, shs + (size_t)i * SH_ROW_FLOATS);
 
-    const float x = means3D[3 * i], y = means3D[3 * i + 1], z = means3D[3 * i + 2];
-    const float tz = affine3(pr.V, 2, x, y, z);
-    if (tz > DMGS_NEAR) {
+    if (near_ok) {
         const float hx = affine3(pr.PV, 0, x, y, z), hy = affine3(pr.PV, 1, x, y, z), hw = affine3(pr.PV, 3, x, y, z);
         const float pw = 1.0f / (hw + 1e-7f);
         const float ppx = hx * pw, ppy = hy * pw;
@@ -176,29 +194,6 @@ preprocess_fwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
             const int y0 = clampi_f((py - rf) * 0.0625f, pr.gy), y1 = clampi_f((py + rf + 15.0f) * 0.0625f, pr.gy);
             const int nt = (x1 - x0) * (y1 - y0);
             if (nt > 0) {
-                if (colors_precomp) {
-                    col = make_float4(colors_precomp[3 * i], colors_precomp[3 * i + 1], colors_precomp[3 * i + 2], 0.0f);
-                } else {
-                    const float dx = x - pr.cam[0], dy = y - pr.cam[1], dz = z - pr.cam[2];
-                    const float len = sqrtf(dot3(dx, dx, dy, dy, dz, dz));
-                    float bas[16];
-                    const int nb = sh_basis(pr.sh_degree, dx / len, dy / len, dz / len, bas);
-                    float v[3];
-#pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) {
-                        float acc = bas[0] * sh_load(shs, pr, i, 0, ch);
-                        for (int k = 1; k < nb; ++k) acc = fma_(bas[k], sh_load(shs, pr, i, k, ch), acc);
-                        if (pr.sh_act == 0) {
-                            acc = acc + 0.5f;
-                            if (acc < 0.0f) clampbits |= (uint8_t)(1u << ch);
-                            acc = fmaxf(acc, 0.0f);
-                        } else {
-                            acc = 1.0f / (1.0f + dmgs_exp(-acc));
-                        }
-                        v[ch] = acc;
-                    }
-                    col = make_float4(v[0], v[1], v[2], 0.0f);
-                }
                 const float op = opacities[i];
                 // conservative blend cut-off: power < -cut  =>  opacity*exp(power) < 1/255 for sure
                 const float cut = op > 0.0f ? logf(255.0f * op) + 1.0e-3f : -1.0f;
@@ -212,6 +207,37 @@ preprocess_fwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
             }
         }
     }
+    if (SHMODE) stage.wait();  // warp-uniform: every issued row has landed (also required before exit)
+    if (ntiles) {
+        if (colors_precomp) {
+            col = make_float4(colors_precomp[3 * i], colors_precomp[3 * i + 1], colors_precomp[3 * i + 2], 0.0f);
+        } else {
+            float r[SHMODE ? SH_ROW_FLOATS : 1];
+            if (SHMODE) stage.read(r);
+            const float dx = x - pr.cam[0], dy = y - pr.cam[1], dz = z - pr.cam[2];
+            const float len = sqrtf(dot3(dx, dx, dy, dy, dz, dz));
+            float bas[16];
+            const int nb = sh_basis(pr.sh_degree, dx / len, dy / len, dz / len, bas);
+            float v[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                float acc = bas[0] * sh_get<SHMODE>(shs, pr, r, i, 0, ch);
+#pragma unroll
+                for (int k = 1; k < 16; ++k)
+                    if (k < nb) acc = fma_(bas[k], sh_get<SHMODE>(shs, pr, r, i, k, ch), acc);
+                if (pr.sh_act == 0) {
+                    acc = acc + 0.5f;
+                    if (acc < 0.0f) clampbits |= (uint8_t)(1u << ch);
+                    acc = fmaxf(acc, 0.0f);
+                } else {
+                    acc = 1.0f / (1.0f + dmgs_exp(-acc));
+                }
+                v[ch] = acc;
+            }
+            col = make_float4(v[0], v[1], v[2], 0.0f);
+        }
+    }
+    if (!inb) return;
     radii[i] = rad;
     depths[i] = depth;
     rec[2 * (size_t)i] = ra;
@@ -228,6 +254,13 @@ preprocess_fwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
     }
 }
 
+// staged SH rows need 16 coefficients per channel and a 16-byte aligned tensor
+static int sh_mode(const dmgs_params *prm, const float *shs)
+{
+    if (!shs || prm->sh_coeffs != 16 || (reinterpret_cast<uintptr_t>(shs) & 15)) return 0;
+    return prm->sh_layout == 0 ? 1 : 2;
+}
+
 int launch_preprocess_fwd(const dmgs_params *prm, const float *means3D, const float *scales, const float *rotations,
                           const float *cov3D_precomp, const float *opacities, const float *shs,
                           const float *colors_precomp, int32_t *radii, void *geom, const GeomLayout &L,
@@ -235,10 +268,23 @@ int launch_preprocess_fwd(const dmgs_params *prm, const float *means3D, const fl
 {
     const int P = prm->P;
     if (P <= 0) return 0;
-    preprocess_fwd_kernel<<<(P + 255) / 256, 256, 0, s>>>(
-        make_dev_params(prm), means3D, scales, rotations, cov3D_precomp, opacities, shs, colors_precomp, radii, at<float>(geom, L.depths),
-        at<float4>(geom, L.rec), at<float4>(geom, L.rgb), at<uint8_t>(geom, L.clamped), at<float>(geom, L.cov3D),
-        at<uint32_t>(geom, L.tiles), at<uint2>(geom, L.rect), at<uint32_t>(geom, L.keys_a), at<uint32_t>(geom, L.order));
+    static bool attr_set = false;
+    if (!attr_set) {
+        DMGS_CUDA(cudaFuncSetAttribute(preprocess_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_STAGE_SMEM));
+        DMGS_CUDA(cudaFuncSetAttribute(preprocess_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_STAGE_SMEM));
+        attr_set = true;
+    }
+    const int mode = sh_mode(prm, shs);
+    const DevParams dp = make_dev_params(prm);
+#define DMGS_FWD_ARGS                                                                                               \
+    dp, means3D, scales, rotations, cov3D_precomp, opacities, shs, colors_precomp, radii, at<float>(geom, L.depths), \
+        at<float4>(geom, L.rec), at<float4>(geom, L.rgb), at<uint8_t>(geom, L.clamped), at<float>(geom, L.cov3D),    \
+        at<uint32_t>(geom, L.tiles), at<uint2>(geom, L.rect), at<uint32_t>(geom, L.keys_a), at<uint32_t>(geom, L.order)
+    const int grid = (P + 255) / 256;
+    if (mode == 1) preprocess_fwd_kernel<1><<<grid, 256, SH_STAGE_SMEM, s>>>(DMGS_FWD_ARGS);
+    else if (mode == 2) preprocess_fwd_kernel<2><<<grid, 256, SH_STAGE_SMEM, s>>>(DMGS_FWD_ARGS);
+    else preprocess_fwd_kernel<0><<<grid, 256, 0, s>>>(DMGS_FWD_ARGS);
+#undef DMGS_FWD_ARGS
     DMGS_CUDA(cudaGetLastError());
     count_launches(1);
     return 0;
@@ -247,6 +293,7 @@ int launch_preprocess_fwd(const dmgs_params *prm, const float *means3D, const fl
 // ------------------------------------------------------------------------------ backward
 // grad_blend: per Gaussian 12 floats {dmean2D.x, dmean2D.y, dconic.a, dconic.b(half), dconic.c,
 // dopacity, dcolor.r, dcolor.g, dcolor.b, pad x3} accumulated by the blend backward.
+template <int SHMODE>
 __global__ void __launch_bounds__(256)
 preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restrict__ means3D, const float *__restrict__ scales,
                       const float *__restrict__ rotations, const float *__restrict__ cov3D_precomp,
@@ -258,12 +305,20 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
                       float *__restrict__ dL_dscales, float *__restrict__ dL_drots, float *__restrict__ dL_dcov3D,
                       const int accumulate)
 {
+    extern __shared__ __align__(16) unsigned char dsm[];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= pr.P) return;
-    const bool vis = radii[i] > 0;
+    const bool inb = i < pr.P;
+    const bool vis = inb && radii[i] > 0;
+    const bool do_sh = shs && dL_dshs;
+    ShStage stage;
+    if (SHMODE) {
+        stage.init(dsm);
+        stage.load(vis && do_sh, shs + (size_t)i * SH_ROW_FLOATS);
+    }
     float gm[3] = {0, 0, 0}, g6[6] = {0, 0, 0, 0, 0, 0};
     float gs[3] = {0, 0, 0}, gq[4] = {0, 0, 0, 0};
     float d2x = 0, d2y = 0, dop = 0, dcol[3] = {0, 0, 0};
+    float x = 0, y = 0, z = 0;
     const int M = pr.M;
 
     if (vis) {
@@ -273,7 +328,7 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
         dop = gb.y;
         dcol[0] = gb.z; dcol[1] = gb.w; dcol[2] = gc.x;
 
-        const float x = means3D[3 * i], y = means3D[3 * i + 1], z = means3D[3 * i + 2];
+        x = means3D[3 * i]; y = means3D[3 * i + 1]; z = means3D[3 * i + 2];
         float c6[6];
         const float *csrc = cov3D_precomp ? cov3D_precomp : cov3D_state;
 #pragma unroll
@@ -324,7 +379,42 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
             gm[k] += fma_(ay, d2y, ax * d2x);
         }
 
-        if (shs && dL_dshs) {
+        if (scales && rotations && dL_dscales && dL_drots) {
+            const float s[3] = {pr.mod * scales[3 * i], pr.mod * scales[3 * i + 1], pr.mod * scales[3 * i + 2]};
+            const float4 q4 = reinterpret_cast<const float4 *>(rotations)[i];
+            const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+            float R[3][3];
+            quat_to_rot(q, R);
+            const float Gs[3][3] = {{g6[0], 0.5f * g6[1], 0.5f * g6[2]}, {0.5f * g6[1], g6[3], 0.5f * g6[4]}, {0.5f * g6[2], 0.5f * g6[4], g6[5]}};
+            float dR[3][3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                float dMk[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    dMk[j] = 2.0f * dot3(s[k] * R[0][k], Gs[0][j], s[k] * R[1][k], Gs[1][j], s[k] * R[2][k], Gs[2][j]);
+                gs[k] = pr.mod * dot3(R[0][k], dMk[0], R[1][k], dMk[1], R[2][k], dMk[2]);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) dR[j][k] = s[k] * dMk[j];
+            }
+            const float r = q[0], qx = q[1], qy = q[2], qz = q[3];
+            gq[0] = 2.0f * (qz * (dR[1][0] - dR[0][1]) + qy * (dR[0][2] - dR[2][0]) + qx * (dR[2][1] - dR[1][2]));
+            gq[1] = 2.0f * (qy * (dR[0][1] + dR[1][0]) + qz * (dR[0][2] + dR[2][0]) + r * (dR[2][1] - dR[1][2])) - 4.0f * qx * (dR[1][1] + dR[2][2]);
+            gq[2] = 2.0f * (qx * (dR[0][1] + dR[1][0]) + r * (dR[0][2] - dR[2][0]) + qz * (dR[1][2] + dR[2][1])) - 4.0f * qy * (dR[0][0] + dR[2][2]);
+            gq[3] = 2.0f * (r * (dR[1][0] - dR[0][1]) + qx * (dR[0][2] + dR[2][0]) + qy * (dR[1][2] + dR[2][1])) - 4.0f * qz * (dR[0][0] + dR[1][1]);
+        }
+    }
+
+    // ---- SH backward: dL/dsh rows and the view-direction term of dL/dmean
+    if (SHMODE) stage.wait();  // warp-uniform
+    if (do_sh) {
+        float r[SHMODE ? SH_ROW_FLOATS : 1];
+        if (SHMODE) {
+#pragma unroll
+            for (int k = 0; k < SH_ROW_FLOATS; ++k) r[k] = 0.0f;
+        }
+        if (vis) {
+            if (SHMODE) stage.read(r);
             const float ox = x - pr.cam[0], oy = y - pr.cam[1], oz = z - pr.cam[2];
             const float s2 = dot3(ox, ox, oy, oy, oz, oz);
             const float len = sqrtf(s2);
@@ -342,19 +432,28 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
                 if (pr.sh_act == 0) g = (cb >> ch) & 1 ? 0.0f : g;
                 else g = g * (sg[ch] * (1.0f - sg[ch]));
                 float sv[16];
+#pragma unroll
                 for (int k = 0; k < 16; ++k) {
-                    const size_t idx = pr.sh_layout == 0 ? ((size_t)i * M + k) * 3 + ch : ((size_t)i * 3 + ch) * M + k;
-                    if (k < nb) {
-                        sv[k] = __ldg(shs + idx);
-                        dL_dshs[idx] = accumulate ? dL_dshs[idx] + bas[k] * g : bas[k] * g;
+                    if (SHMODE) {
+                        const int ri = SHMODE == 1 ? k * 3 + ch : ch * 16 + k;
+                        sv[k] = k < nb ? r[ri] : 0.0f;
+                        r[ri] = k < nb ? bas[k] * g : 0.0f;
                     } else {
-                        sv[k] = 0.0f;
-                        if (k < M && !accumulate) dL_dshs[idx] = 0.0f;
+                        const size_t idx = pr.sh_layout == 0 ? ((size_t)i * M + k) * 3 + ch : ((size_t)i * 3 + ch) * M + k;
+                        if (k < nb) {
+                            sv[k] = __ldg(shs + idx);
+                            dL_dshs[idx] = accumulate ? dL_dshs[idx] + bas[k] * g : bas[k] * g;
+                        } else {
+                            sv[k] = 0.0f;
+                            if (k < M && !accumulate) dL_dshs[idx] = 0.0f;
+                        }
                     }
                 }
-                for (int k = 16; k < M && !accumulate; ++k) {
-                    const size_t idx = pr.sh_layout == 0 ? ((size_t)i * M + k) * 3 + ch : ((size_t)i * 3 + ch) * M + k;
-                    dL_dshs[idx] = 0.0f;
+                if (!SHMODE) {
+                    for (int k = 16; k < M && !accumulate; ++k) {
+                        const size_t idx = pr.sh_layout == 0 ? ((size_t)i * M + k) * 3 + ch : ((size_t)i * 3 + ch) * M + k;
+                        dL_dshs[idx] = 0.0f;
+                    }
                 }
                 if (pr.sh_degree > 0) {
                     float gx_ = -SH_C1 * sv[3], gy_ = -SH_C1 * sv[1], gz_ = SH_C1 * sv[2];
@@ -385,80 +484,63 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
                 gm[1] += (-ox * oy * ddx + (s2 - oy * oy) * ddy - oz * oy * ddz) * inv3;
                 gm[2] += (-ox * oz * ddx - oy * oz * ddy + (s2 - oz * oz) * ddz) * inv3;
             }
+        } else if (!SHMODE && inb && !accumulate) {
+            for (int k = 0; k < 3 * M; ++k) dL_dshs[(size_t)i * 3 * M + k] = 0.0f;
         }
+        if (SHMODE) {
+            // store: every in-range row (zeros for culled Gaussians); accumulate: only rows with a gradient
+            if (inb && (vis || !accumulate)) stage.write_out(r, dL_dshs + (size_t)i * SH_ROW_FLOATS, accumulate != 0);
+        }
+    }
 
-        if (scales && rotations && dL_dscales && dL_drots) {
-            const float s[3] = {pr.mod * scales[3 * i], pr.mod * scales[3 * i + 1], pr.mod * scales[3 * i + 2]};
-            const float4 q4 = reinterpret_cast<const float4 *>(rotations)[i];
-            const float q[4] = {q4.x, q4.y, q4.z, q4.w};
-            float R[3][3];
-            quat_to_rot(q, R);
-            const float Gs[3][3] = {{g6[0], 0.5f * g6[1], 0.5f * g6[2]}, {0.5f * g6[1], g6[3], 0.5f * g6[4]}, {0.5f * g6[2], 0.5f * g6[4], g6[5]}};
-            float dR[3][3];
+    if (inb) {
+        if (accumulate) {
+            if (vis) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                float dMk[3];
+                for (int k = 0; k < 3; ++k) dL_dmeans3D[3 * (size_t)i + k] += gm[k];
+                dL_dmeans2D[3 * (size_t)i] += d2x;
+                dL_dmeans2D[3 * (size_t)i + 1] += d2y;
+                dL_dopacity[i] += dop;
+                if (dL_dcolprec) {
 #pragma unroll
-                for (int j = 0; j < 3; ++j)
-                    dMk[j] = 2.0f * dot3(s[k] * R[0][k], Gs[0][j], s[k] * R[1][k], Gs[1][j], s[k] * R[2][k], Gs[2][j]);
-                gs[k] = pr.mod * dot3(R[0][k], dMk[0], R[1][k], dMk[1], R[2][k], dMk[2]);
+                    for (int k = 0; k < 3; ++k) dL_dcolprec[3 * (size_t)i + k] += dcol[k];
+                }
+                if (dL_dcov3D) {
 #pragma unroll
-                for (int j = 0; j < 3; ++j) dR[j][k] = s[k] * dMk[j];
+                    for (int k = 0; k < 6; ++k) dL_dcov3D[6 * (size_t)i + k] += g6[k];
+                }
+                if (dL_dscales) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) dL_dscales[3 * (size_t)i + k] += gs[k];
+                }
+                if (dL_drots) {
+                    float4 o = reinterpret_cast<float4 *>(dL_drots)[i];
+                    reinterpret_cast<float4 *>(dL_drots)[i] = make_float4(o.x + gq[0], o.y + gq[1], o.z + gq[2], o.w + gq[3]);
+                }
             }
-            const float r = q[0], qx = q[1], qy = q[2], qz = q[3];
-            gq[0] = 2.0f * (qz * (dR[1][0] - dR[0][1]) + qy * (dR[0][2] - dR[2][0]) + qx * (dR[2][1] - dR[1][2]));
-            gq[1] = 2.0f * (qy * (dR[0][1] + dR[1][0]) + qz * (dR[0][2] + dR[2][0]) + r * (dR[2][1] - dR[1][2])) - 4.0f * qx * (dR[1][1] + dR[2][2]);
-            gq[2] = 2.0f * (qx * (dR[0][1] + dR[1][0]) + r * (dR[0][2] - dR[2][0]) + qz * (dR[1][2] + dR[2][1])) - 4.0f * qy * (dR[0][0] + dR[2][2]);
-            gq[3] = 2.0f * (r * (dR[1][0] - dR[0][1]) + qx * (dR[0][2] + dR[2][0]) + qy * (dR[1][2] + dR[2][1])) - 4.0f * qz * (dR[0][0] + dR[1][1]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) dL_dmeans3D[3 * (size_t)i + k] = gm[k];
+            dL_dmeans2D[3 * (size_t)i] = d2x;
+            dL_dmeans2D[3 * (size_t)i + 1] = d2y;
+            dL_dmeans2D[3 * (size_t)i + 2] = 0.0f;
+            dL_dopacity[i] = dop;
+            if (dL_dcolprec) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) dL_dcolprec[3 * (size_t)i + k] = dcol[k];
+            }
+            if (dL_dcov3D) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) dL_dcov3D[6 * (size_t)i + k] = g6[k];
+            }
+            if (dL_dscales) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) dL_dscales[3 * (size_t)i + k] = gs[k];
+            }
+            if (dL_drots) reinterpret_cast<float4 *>(dL_drots)[i] = make_float4(gq[0], gq[1], gq[2], gq[3]);
         }
-    } else if (shs && dL_dshs && !accumulate) {
-        for (int k = 0; k < 3 * M; ++k) dL_dshs[(size_t)i * 3 * M + k] = 0.0f;
     }
-    if (accumulate) {
-        if (!vis) return;  // nothing to add
-#pragma unroll
-        for (int k = 0; k < 3; ++k) dL_dmeans3D[3 * (size_t)i + k] += gm[k];
-        dL_dmeans2D[3 * (size_t)i] += d2x;
-        dL_dmeans2D[3 * (size_t)i + 1] += d2y;
-        dL_dopacity[i] += dop;
-        if (dL_dcolprec) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) dL_dcolprec[3 * (size_t)i + k] += dcol[k];
-        }
-        if (dL_dcov3D) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) dL_dcov3D[6 * (size_t)i + k] += g6[k];
-        }
-        if (dL_dscales) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) dL_dscales[3 * (size_t)i + k] += gs[k];
-        }
-        if (dL_drots) {
-            float4 o = reinterpret_cast<float4 *>(dL_drots)[i];
-            reinterpret_cast<float4 *>(dL_drots)[i] = make_float4(o.x + gq[0], o.y + gq[1], o.z + gq[2], o.w + gq[3]);
-        }
-        return;
-    }
-
-#pragma unroll
-    for (int k = 0; k < 3; ++k) dL_dmeans3D[3 * (size_t)i + k] = gm[k];
-    dL_dmeans2D[3 * (size_t)i] = d2x;
-    dL_dmeans2D[3 * (size_t)i + 1] = d2y;
-    dL_dmeans2D[3 * (size_t)i + 2] = 0.0f;
-    dL_dopacity[i] = dop;
-    if (dL_dcolprec) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) dL_dcolprec[3 * (size_t)i + k] = dcol[k];
-    }
-    if (dL_dcov3D) {
-#pragma unroll
-        for (int k = 0; k < 6; ++k) dL_dcov3D[6 * (size_t)i + k] = g6[k];
-    }
-    if (dL_dscales) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) dL_dscales[3 * (size_t)i + k] = gs[k];
-    }
-    if (dL_drots) reinterpret_cast<float4 *>(dL_drots)[i] = make_float4(gq[0], gq[1], gq[2], gq[3]);
+    if (SHMODE) stage.flush();  // shared rows must stay valid until the bulk stores have read them
 }
 
 int launch_preprocess_bwd(const dmgs_params *prm, const float *means3D, const float *scales, const float *rotations,
@@ -469,10 +551,23 @@ int launch_preprocess_bwd(const dmgs_params *prm, const float *means3D, const fl
 {
     const int P = prm->P;
     if (P <= 0) return 0;
-    preprocess_bwd_kernel<<<(P + 255) / 256, 256, 0, s>>>(
-        make_dev_params(prm), means3D, scales, rotations, cov3D_precomp, shs, radii, at<float>(geom, L.cov3D), at<uint8_t>(geom, L.clamped),
-        at<float4>(geom, L.rgb), reinterpret_cast<const float4 *>(grad_blend), dL_dmeans3D, dL_dmeans2D, dL_dopacity,
-        dL_dcolprec, dL_dshs, dL_dscales, dL_drots, dL_dcov3D, accumulate);
+    static bool attr_set = false;
+    if (!attr_set) {
+        DMGS_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_STAGE_SMEM));
+        DMGS_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_STAGE_SMEM));
+        attr_set = true;
+    }
+    int mode = (dL_dshs && !(reinterpret_cast<uintptr_t>(dL_dshs) & 15)) ? sh_mode(prm, shs) : 0;
+    const DevParams dp = make_dev_params(prm);
+#define DMGS_BWD_ARGS                                                                                                  \
+    dp, means3D, scales, rotations, cov3D_precomp, shs, radii, at<float>(geom, L.cov3D), at<uint8_t>(geom, L.clamped), \
+        at<float4>(geom, L.rgb), reinterpret_cast<const float4 *>(grad_blend), dL_dmeans3D, dL_dmeans2D, dL_dopacity,   \
+        dL_dcolprec, dL_dshs, dL_dscales, dL_drots, dL_dcov3D, accumulate
+    const int grid = (P + 255) / 256;
+    if (mode == 1) preprocess_bwd_kernel<1><<<grid, 256, SH_STAGE_SMEM, s>>>(DMGS_BWD_ARGS);
+    else if (mode == 2) preprocess_bwd_kernel<2><<<grid, 256, SH_STAGE_SMEM, s>>>(DMGS_BWD_ARGS);
+    else preprocess_bwd_kernel<0><<<grid, 256, 0, s>>>(DMGS_BWD_ARGS);
+#undef DMGS_BWD_ARGS
     DMGS_CUDA(cudaGetLastError());
     count_launches(1);
     return 0;

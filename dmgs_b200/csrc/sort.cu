@@ -119,9 +119,15 @@ int exclusive_scan_u32(const uint32_t *in, const uint32_t *gather, uint32_t *out
 }
 
 // ------------------------------------------------------------------------------ radix pass
+// One stable LSD pass = histogram kernel -> scan of the [bins x blocks] table -> ranked scatter.
+// A block owns 2048 consecutive items; warp w owns the contiguous run [w*256, (w+1)*256) of it and
+// walks it in 8 rounds of 32 (stability = warp order, round order, lane order).  Keys live in
+// registers (all loads issued up front), equal-digit lanes are found with `bits` warp ballots
+// (MATCH.ANY saturates the ADU pipe on sm_100: profiles/r1_v1), and per-warp digit counters in
+// shared memory turn the block's scanned table column into final positions.
 constexpr int RP_THREADS = 256;
 constexpr int RP_WARPS = RP_THREADS / 32;
-constexpr int RP_ROUNDS = SORT_ITEMS_PER_BLOCK / RP_THREADS;  // 32 rounds of 32 items per warp
+constexpr int RP_ROUNDS = SORT_ITEMS_PER_BLOCK / RP_THREADS;  // 8
 
 __global__ void __launch_bounds__(RP_THREADS)
 radix_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift, int bins, int nblocks,
@@ -129,87 +135,186 @@ radix_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift, int b
 {
     __shared__ uint32_t h[SORT_MAX_BINS];
     for (int d = threadIdx.x; d < bins; d += RP_THREADS) h[d] = 0;
-    __syncthreads();
     const int64_t base = (int64_t)blockIdx.x * SORT_ITEMS_PER_BLOCK;
     const uint32_t mask = (uint32_t)bins - 1;
-#pragma unroll 4
+    uint32_t k[RP_ROUNDS];
+#pragma unroll
     for (int r = 0; r < RP_ROUNDS; ++r) {
         const int64_t i = base + (int64_t)r * RP_THREADS + threadIdx.x;
-        if (i < n) atomicAdd(&h[(keys[i] >> shift) & mask], 1u);
+        k[r] = i < n ? keys[i] : 0xFFFFFFFFu;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RP_ROUNDS; ++r) {
+        const int64_t i = base + (int64_t)r * RP_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&h[(k[r] >> shift) & mask], 1u);
     }
     __syncthreads();
     for (int d = threadIdx.x; d < bins; d += RP_THREADS) hist[(size_t)d * nblocks + blockIdx.x] = h[d];
 }
 
+template <int BITS>
+__device__ __forceinline__ uint32_t digit_peers(uint32_t d, uint32_t act)
+{
+    uint32_t peers = act;
+#pragma unroll
+    for (int b = 0; b < BITS; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const uint32_t m = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? m : ~m;
+    }
+    return peers;
+}
+
+template <int BITS>
 __global__ void __launch_bounds__(RP_THREADS)
 radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
-                     uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n, int shift, int bins,
-                     int nblocks, const uint32_t *__restrict__ hist_scanned)
+                     uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n, int shift,
+                     int nblocks, const uint32_t *__restrict__ row_prefix, const uint32_t *__restrict__ bin_total)
 {
-    __shared__ uint32_t wh[RP_WARPS][SORT_MAX_BINS];
+    constexpr int BINS = 1 << BITS;
+    __shared__ uint32_t wh[RP_WARPS][BINS];
+    __shared__ uint32_t bin_local[BINS];   // first slot of digit d inside the block's reordered chunk
+    __shared__ uint32_t bin_global[BINS];  // global position of that slot
+    __shared__ uint32_t skeys[SORT_ITEMS_PER_BLOCK];
+    __shared__ uint32_t svals[SORT_ITEMS_PER_BLOCK];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int d = threadIdx.x; d < RP_WARPS * SORT_MAX_BINS; d += RP_THREADS) (&wh[0][0])[d] = 0;
-    __syncthreads();
-    const uint32_t mask = (uint32_t)bins - 1;
+    for (int d = threadIdx.x; d < RP_WARPS * BINS; d += RP_THREADS) (&wh[0][0])[d] = 0;
+    const uint32_t mask = (uint32_t)BINS - 1;
     const uint32_t lt = (1u << lane) - 1u;
-    // each warp owns a contiguous run of the block's chunk (stability: warp order, round order, lane order)
-    const int64_t wbase = (int64_t)blockIdx.x * SORT_ITEMS_PER_BLOCK + (int64_t)w * (RP_ROUNDS * 32);
-    for (int r = 0; r < RP_ROUNDS; ++r) {
-        const int64_t i = wbase + r * 32 + lane;
-        const bool valid = i < n;
-        const uint32_t act = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-            const uint32_t d = (keys_in[i] >> shift) & mask;
-            const uint32_t peers = __match_any_sync(act, d);
-            if ((peers & lt) == 0) wh[w][d] += __popc(peers);
-        }
-        __syncwarp();
-    }
-    __syncthreads();
-    for (int d = threadIdx.x; d < bins; d += RP_THREADS) {
-        uint32_t base = hist_scanned[(size_t)d * nblocks + blockIdx.x];
+    const int64_t bbase = (int64_t)blockIdx.x * SORT_ITEMS_PER_BLOCK;
+    const int64_t wbase = bbase + (int64_t)w * (RP_ROUNDS * 32) + lane;
+    uint32_t key[RP_ROUNDS], val[RP_ROUNDS], rank[RP_ROUNDS];
 #pragma unroll
-        for (int k = 0; k < RP_WARPS; ++k) {
-            const uint32_t t = wh[k][d];
-            wh[k][d] = base;
-            base += t;
+    for (int r = 0; r < RP_ROUNDS; ++r) {
+        const int64_t i = wbase + r * 32;
+        key[r] = i < n ? keys_in[i] : 0xFFFFFFFFu;
+    }
+#pragma unroll
+    for (int r = 0; r < RP_ROUNDS; ++r) {
+        const int64_t i = wbase + r * 32;
+        val[r] = i < n ? vals_in[i] : 0u;
+    }
+    __syncthreads();
+    // phase 1: stable rank of every item among the warp's items with the same digit.  Lanes with
+    // equal digits are found with BITS ballots; the lowest such lane bumps the warp's counter with
+    // one shared-memory atomic (same-warp atomics to one address retire in program order, so the
+    // rounds need no barrier between them and overlap freely) and broadcasts the old value.
+#pragma unroll
+    for (int r = 0; r < RP_ROUNDS; ++r) {
+        const bool valid = wbase + r * 32 < n;
+        const uint32_t act = __ballot_sync(0xffffffffu, valid);
+        const uint32_t d = (key[r] >> shift) & mask;
+        const uint32_t peers = digit_peers<BITS>(d, act);
+        uint32_t old = 0;
+        if (valid && (peers & lt) == 0) old = atomicAdd(&wh[w][d], (uint32_t)__popc(peers));
+        old = __shfl_sync(0xffffffffu, old, peers ? __ffs(peers) - 1 : 0);
+        rank[r] = old + __popc(peers & lt);
+    }
+    __syncthreads();
+    // phase 2: per digit, exclusive prefix over warps; block-level exclusive scan over digits;
+    // global base = (scan of the bin totals) + (this block's prefix inside the bin's table row)
+    {
+        const int d = threadIdx.x;
+        uint32_t tot = 0, gtot = 0;
+        if (d < BINS) {
+#pragma unroll
+            for (int k = 0; k < RP_WARPS; ++k) {
+                const uint32_t t = wh[k][d];
+                wh[k][d] = tot;
+                tot += t;
+            }
+            gtot = bin_total[d];
+        }
+        uint32_t dummy;
+        const uint32_t lex = block_excl_scan(tot, &dummy);
+        const uint32_t gex = block_excl_scan(gtot, &dummy);
+        if (d < BINS) {
+            bin_local[d] = lex;
+            bin_global[d] = gex + row_prefix[(size_t)d * nblocks + blockIdx.x];
         }
     }
     __syncthreads();
+    // phase 3: shared-memory reorder
+#pragma unroll
     for (int r = 0; r < RP_ROUNDS; ++r) {
-        const int64_t i = wbase + r * 32 + lane;
-        const bool valid = i < n;
-        const uint32_t act = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-            const uint32_t key = keys_in[i], val = vals_in[i];
-            const uint32_t d = (key >> shift) & mask;
-            const uint32_t peers = __match_any_sync(act, d);
-            const uint32_t pos = wh[w][d] + __popc(peers & lt);
-            __syncwarp(act);
-            if ((peers & lt) == 0) wh[w][d] += __popc(peers);
-            keys_out[pos] = key;
-            vals_out[pos] = val;
+        if (wbase + r * 32 < n) {
+            const uint32_t d = (key[r] >> shift) & mask;
+            const uint32_t pos = bin_local[d] + wh[w][d] + rank[r];
+            skeys[pos] = key[r];
+            svals[pos] = val[r];
         }
-        __syncwarp();
     }
+    __syncthreads();
+    // phase 4: coalesced write-out (each digit's run is contiguous both in shared and in global memory)
+    const int count = (int)min((int64_t)SORT_ITEMS_PER_BLOCK, n - bbase);
+#pragma unroll 4
+    for (int j = threadIdx.x; j < count; j += RP_THREADS) {
+        const uint32_t k = skeys[j];
+        const uint32_t d = (k >> shift) & mask;
+        const uint32_t out = bin_global[d] + ((uint32_t)j - bin_local[d]);
+        keys_out[out] = k;
+        vals_out[out] = svals[j];
+    }
+}
+
+// one block per digit: exclusive scan of the digit's table row (over blocks) + the row total
+__global__ void __launch_bounds__(256)
+radix_rowscan_kernel(uint32_t *__restrict__ hist, int nblocks, uint32_t *__restrict__ bin_total)
+{
+    uint32_t *row = hist + (size_t)blockIdx.x * nblocks;
+    uint32_t carry = 0;
+    for (int b0 = 0; b0 < nblocks; b0 += 256 * 4) {
+        const int i0 = b0 + threadIdx.x * 4;
+        uint32_t v[4], s = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { v[k] = (i0 + k < nblocks) ? row[i0 + k] : 0; s += v[k]; }
+        uint32_t tot;
+        uint32_t ex = carry + block_excl_scan(s, &tot);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { if (i0 + k < nblocks) row[i0 + k] = ex; ex += v[k]; }
+        carry += tot;
+    }
+    if (threadIdx.x == 0) bin_total[blockIdx.x] = carry;
+}
+
+template <int BITS>
+static void launch_scatter(const uint32_t *ki, const uint32_t *vi, uint32_t *ko, uint32_t *vo, int64_t n, int shift,
+                           int nblocks, const uint32_t *hist, const uint32_t *bin_total, cudaStream_t s)
+{
+    radix_scatter_kernel<BITS><<<nblocks, RP_THREADS, 0, s>>>(ki, vi, ko, vo, n, shift, nblocks, hist, bin_total);
 }
 
 int radix_pass(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out, int64_t n,
                int shift, int bits, uint32_t *hist, uint32_t *scan_tmp, cudaStream_t s)
 {
+    (void)scan_tmp;
     if (n <= 0) return 0;
+    if (bits < 1 || bits > 8) { set_error("radix_pass: bits=%d unsupported", bits); return -8; }
     const int bins = 1 << bits;
     const int nblocks = (int)((n + SORT_ITEMS_PER_BLOCK - 1) / SORT_ITEMS_PER_BLOCK);
+    uint32_t *bin_total = hist + (size_t)SORT_MAX_BINS * nblocks;  // 256 spare entries behind the table
     radix_hist_kernel<<<nblocks, RP_THREADS, 0, s>>>(keys_in, n, shift, bins, nblocks, hist);
-    int rc = exclusive_scan_u32(hist, nullptr, hist, (int64_t)bins * nblocks, nullptr, scan_tmp, s);
-    if (rc) return rc;
-    radix_scatter_kernel<<<nblocks, RP_THREADS, 0, s>>>(keys_in, vals_in, keys_out, vals_out, n, shift, bins, nblocks, hist);
+    radix_rowscan_kernel<<<bins, 256, 0, s>>>(hist, nblocks, bin_total);
+    switch (bits) {
+    case 1: launch_scatter<1>(keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
+    case 2: launch_scatter<2>(keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
+    case 3: launch_scatter<3>(keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
+    case 4: launch_scatter<4>(keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
+    case 5: launch_scatter<5>(keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
+    case 6: launch_scatter<6>(keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
+    case 7: launch_scatter<7>(keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
+    default: launch_scatter<8>(keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
+    }
     DMGS_CUDA(cudaGetLastError());
-    count_launches(2);
+    count_launches(3);
     return 0;
 }
 
 // ------------------------------------------------------------------------------ instance emission
+// Load-balanced emission: a warp takes 32 depth-ordered Gaussians whose instances occupy one
+// contiguous output range; lanes walk that range with stride 32 (fully coalesced stores) and find
+// the owning Gaussian of each slot by a 5-step search over the warp's offsets.
 __global__ void __launch_bounds__(256)
 emit_instances_kernel(int P, const uint32_t *__restrict__ order, const uint32_t *__restrict__ offsets,
                       const uint32_t *__restrict__ tiles, const uint2 *__restrict__ rect, int gx,
@@ -222,36 +327,41 @@ emit_instances_kernel(int P, const uint32_t *__restrict__ order, const uint32_t 
     if (sidx < P) {
         g = order[sidx];
         cnt = tiles[g];
-        if (cnt) {
-            off = offsets[sidx];
-            rc = rect[g];
+        off = offsets[sidx];
+        if (cnt) rc = rect[g];
+    }
+    // offsets are an exclusive scan in this order: lane l's instances are [off_l, off_l + cnt_l)
+    const uint32_t first = __shfl_sync(0xffffffffu, off, 0);
+    const uint32_t last_off = __shfl_sync(0xffffffffu, off, 31), last_cnt = __shfl_sync(0xffffffffu, cnt, 31);
+    uint32_t total = last_off + last_cnt - first;
+    if (sidx - lane + 31 >= P) {  // partial warp at the tail: lanes beyond P hold zeros
+        const uint32_t end = off + cnt;
+        uint32_t m = sidx < P ? end : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+        total = m > first ? m - first : 0;
+    }
+    const uint32_t rel = off - first;  // start of this lane's run relative to the warp's range
+    for (uint32_t jb = 0; jb < total; jb += 32) {  // warp-uniform trip count (shuffles inside)
+        const uint32_t j = jb + lane;
+        // largest lane l with rel_l <= j and cnt_l > 0 covering j: binary search on rel (non-decreasing)
+        int lo = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const int cand = lo + step;
+            const uint32_t r2 = __shfl_sync(0xffffffffu, rel, cand & 31);
+            const bool okl = (sidx - lane + cand) < P;
+            if (cand < 32 && okl && r2 <= j) lo = cand;
         }
-    }
-    // small rectangles: one thread each; large ones: the whole warp cooperates
-    const uint32_t big = __ballot_sync(0xffffffffu, cnt > 32);
-    if (cnt && cnt <= 32) {
-        const int x0 = rc.x & 0xffff, x1 = rc.x >> 16, y0 = rc.y & 0xffff, y1 = rc.y >> 16;
-        uint32_t o = off;
-        for (int ty = y0; ty < y1; ++ty)
-            for (int tx = x0; tx < x1; ++tx) {
-                inst_tile[o] = (uint32_t)(ty * gx + tx);
-                inst_gidx[o] = g;
-                ++o;
-            }
-    }
-    uint32_t todo = big;
-    while (todo) {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const uint32_t g2 = __shfl_sync(0xffffffffu, g, src), c2 = __shfl_sync(0xffffffffu, cnt, src);
-        const uint32_t o2 = __shfl_sync(0xffffffffu, off, src);
-        const uint32_t rx = __shfl_sync(0xffffffffu, rc.x, src), ry = __shfl_sync(0xffffffffu, rc.y, src);
+        const uint32_t g2 = __shfl_sync(0xffffffffu, g, lo);
+        const uint32_t rx = __shfl_sync(0xffffffffu, rc.x, lo), ry = __shfl_sync(0xffffffffu, rc.y, lo);
+        const uint32_t r0 = __shfl_sync(0xffffffffu, rel, lo);
         const int x0 = rx & 0xffff, x1 = rx >> 16, y0 = ry & 0xffff;
-        const int wdt = x1 - x0;
-        for (uint32_t j = lane; j < c2; j += 32) {
-            const int ty = y0 + (int)(j / wdt), tx = x0 + (int)(j % wdt);
-            inst_tile[o2 + j] = (uint32_t)(ty * gx + tx);
-            inst_gidx[o2 + j] = g2;
+        const uint32_t wdt = (uint32_t)(x1 - x0), k = j - r0;
+        if (j < total) {
+            const uint32_t ty = y0 + k / wdt, tx = x0 + k % wdt;
+            inst_tile[first + j] = ty * (uint32_t)gx + tx;
+            inst_gidx[first + j] = g2;
         }
     }
 }
@@ -270,18 +380,34 @@ int launch_emit_instances(int P, const uint32_t *order, const uint32_t *offsets,
 __global__ void __launch_bounds__(256)
 tile_ranges_kernel(int64_t R, const uint32_t *__restrict__ sorted_tiles, uint2 *__restrict__ ranges)
 {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= R) return;
-    const uint32_t t = sorted_tiles[j];
-    if (j == 0 || sorted_tiles[j - 1] != t) ranges[t].x = (uint32_t)j;
-    if (j == R - 1 || sorted_tiles[j + 1] != t) ranges[t].y = (uint32_t)(j + 1);
+    // four consecutive entries per thread (one 16-byte load) + the entry before them
+    const int64_t j0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (j0 >= R) return;
+    uint32_t t[5];
+    if (j0 + 3 < R) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(sorted_tiles + j0);
+        t[1] = v.x; t[2] = v.y; t[3] = v.z; t[4] = v.w;
+    } else {
+        for (int k = 0; k < 4; ++k) t[1 + k] = j0 + k < R ? sorted_tiles[j0 + k] : 0xFFFFFFFFu;
+    }
+    t[0] = j0 > 0 ? sorted_tiles[j0 - 1] : 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int64_t j = j0 + k;
+        if (j >= R) break;
+        if (t[k] != t[k + 1]) {
+            ranges[t[k + 1]].x = (uint32_t)j;
+            if (j > 0) ranges[t[k]].y = (uint32_t)j;
+        }
+        if (j == R - 1) ranges[t[k + 1]].y = (uint32_t)R;
+    }
 }
 
 int launch_tile_ranges(int64_t R, const uint32_t *sorted_tiles, uint2 *ranges, int T, cudaStream_t s)
 {
     DMGS_CUDA(cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)T, s));
     if (R <= 0) return 0;
-    tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(R, sorted_tiles, ranges);
+    tile_ranges_kernel<<<(unsigned)((R + 1023) / 1024), 256, 0, s>>>(R, sorted_tiles, ranges);
     DMGS_CUDA(cudaGetLastError());
     count_launches(1);
     return 0;

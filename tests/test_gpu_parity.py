@@ -15,7 +15,7 @@ from util import cam_params, cov6_from_scale_rot, grad_close, small_scene
 
 pytestmark = pytest.mark.gpu
 
-MODES = ["sh_scale_rot", "precomp", "sigmoid_features", "sh_deg1_scale_mod"]
+MODES = ["sh_scale_rot", "precomp", "sigmoid_features", "sh_deg1_scale_mod", "sh_m4_direct"]
 
 
 def mode_inputs(mode, cl, P):
@@ -25,6 +25,9 @@ def mode_inputs(mode, cl, P):
     if mode == "sh_deg1_scale_mod":
         return (dict(scales=cl["scales"], rotations=cl["rotations"], shs=cl["shs"]),
                 dict(sh_degree=1, scale_modifier=0.7), {})
+    if mode == "sh_m4_direct":  # 4 stored coefficients: rows are not staged through TMA (direct loads)
+        return (dict(scales=cl["scales"], rotations=cl["rotations"], shs=cl["shs"][:, :4, :].contiguous()),
+                dict(sh_degree=1, sh_coeffs=4), {})
     if mode == "precomp":
         col = torch.rand(P, 3, generator=torch.Generator().manual_seed(9))
         return dict(cov3D_precomp=cov6_from_scale_rot(cl["scales"], cl["rotations"]), colors_precomp=col), {}, {}
@@ -130,6 +133,37 @@ def test_backward_parity(mode):
         grad_close(g_cov, bw["dL_dcov3D"], name="cov3D")
     for t in (g_means3D, g_means2D, g_op):
         assert np.isfinite(t).all()
+
+
+def test_backward_accumulate_mode():
+    """accumulate=1 adds into existing gradient buffers (TMA reduce-add for the SH rows)."""
+    from dmgs_b200.rasterizer import rasterize_backward
+    cam, cl = small_scene(P=3000, W=200, H=136, scale=0.05)
+    for mode in ("sh_scale_rot", "sigmoid_features", "sh_m4_direct", "precomp"):
+        pr, npin, ref, color, radii, st, arrays = run_both(cam, cl, mode)
+        dL = torch.randn(3, cam.image_height, cam.image_width, generator=torch.Generator().manual_seed(5)).cuda()
+        d = lambda k: None if k not in npin else torch.tensor(npin[k]).cuda()
+        args = (st, dL, cl["means3D"].cuda(), d("shs"), d("scales"), d("rotations"), d("cov3D_precomp"), "colors_precomp" in npin)
+        g1 = rasterize_backward(*args)
+        P = 3000
+        acc = {"means3D": torch.ones(P, 3).cuda(), "means2D": torch.ones(P, 3).cuda(), "opacities": torch.ones(P, 1).cuda(),
+               "colors_precomp": torch.ones(P, 3).cuda(), "scales": torch.ones(P, 3).cuda(), "rotations": torch.ones(P, 4).cuda(),
+               "cov3D_precomp": torch.ones(P, 6).cuda()}
+        if "shs" in npin:
+            acc["shs"] = torch.ones_like(d("shs"))
+        rasterize_backward(*args, accumulate_into=acc)
+        rasterize_backward(*args, accumulate_into=acc)
+        torch.cuda.synchronize()
+        names = ["means3D", "means2D", "shs", "colors_precomp", "opacities", "scales", "rotations", "cov3D_precomp"]
+        for n, g in zip(names, g1):
+            if g is None:
+                continue
+            got = (acc[n] - 1.0) * 0.5  # two accumulations on top of the initial ones
+            if n == "means2D":
+                assert torch.all(acc[n][:, 2] == 1.0)
+                got[:, 2] = 0.0
+            # the blend backward's atomics make every run's summation order different
+            grad_close(got.cpu().numpy(), g.cpu().numpy(), rtol=2e-4, name=f"{mode}/{n}")
 
 
 def test_module_autograd_contract():
