@@ -1,10 +1,21 @@
 // blend.cu -- per-tile front-to-back alpha blending (forward) and its back-to-front adjoint.
 // Replaces upstream renderCUDA forward/backward.
 //
-// One CTA per 16x16 tile, 8 warps; warp w owns the 8x4 pixel sub-rectangle
-// (w & 1, w >> 1) so that warp-level culling has a compact footprint.  Entries of the tile's
-// depth-ordered list are staged through shared memory in rounds of 256 (one gather per thread:
-// a 32-byte record + a 16-byte colour per Gaussian, both sector-aligned in L2).
+// One CTA per 16x16 tile, 8 warps; warp w owns the 8x4 pixel sub-rectangle (w & 1, w >> 1).
+// The tile's depth-ordered entries are staged through shared memory in rounds of 256 (one
+// 32-byte record + one 16-byte colour per Gaussian, both sector-aligned gathers that hit L2).
+//
+// Warp-level culling (the B200-first part): for every group of 32 staged entries the warp first
+// runs ONE pass with lane <-> entry in which each lane bounds the entry's exponent over the
+// warp's whole 8x4 rectangle (exact minimum of the conic's quadratic form over the rectangle);
+// a ballot gives the entries that can reach alpha >= 1/255 somewhere in the rectangle, and only
+// those are evaluated per pixel (lane <-> pixel).  The bound is conservative by construction
+// (margins cover fp32 rounding), skipped entries are exactly the ones the per-pixel tests would
+// skip for all 32 pixels, so images, final T and contributor counts stay bit-identical.
+//
+// Backward: per contributing (warp, entry) the nine partial gradients are reduced across the 32
+// pixels with a transposed butterfly (12 shuffles instead of 45) that leaves each total in a
+// different lane, so ONE predicated atomic instruction adds all nine to the Gaussian's record.
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -17,12 +28,42 @@ struct BlendArgs {
     float bg[3];
 };
 
-__device__ __forceinline__ void pixel_of_thread(int &px, int &py)
+// exact minimum over the pixel rectangle [x0,x1]x[y0,y1] of q(d) = A dx^2 + 2 B dx dy + C dy^2,
+// d = g - p, for a positive-definite conic; returns true when the entry can be skipped for every
+// pixel of the rectangle: 0.5*q_min > cut (+ rounding margin).  cut = log(255*opacity) + 1e-3
+// (preprocess), +inf for conics that are not positive definite, negative for opacity <= 1/255.
+__device__ __forceinline__ bool cull_rect(float gx, float gy, float A, float B, float C, float cut, float x0,
+                                          float x1, float y0, float y1)
 {
-    // warp w -> 8x4 sub-rectangle; lane -> pixel inside it
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    px = blockIdx.x * DMGS_TILE + (w & 1) * 8 + (lane & 7);
-    py = blockIdx.y * DMGS_TILE + (w >> 1) * 4 + (lane >> 3);
+    const float cx = fminf(fmaxf(gx, x0), x1), cy = fminf(fmaxf(gy, y0), y1);
+    const float dx = gx - cx, dy = gy - cy;  // offset to the closest point of the rectangle
+    float qmin = 0.0f, mag = 0.0f;
+    if (dx != 0.0f || dy != 0.0f) {
+        qmin = 3.0e38f;
+        if (dx != 0.0f) {  // vertical edge x = cx: minimise over y in [y0, y1]
+            const float ys = gy + (B * dx) / C;  // stationary point of q along the edge
+            const float dyc = gy - fminf(fmaxf(ys, y0), y1);
+            const float t0 = A * dx * dx, t1 = 2.0f * B * dx * dyc, t2 = C * dyc * dyc;
+            qmin = t0 + t1 + t2;
+            mag = t0 + fabsf(t1) + t2;
+        }
+        if (dy != 0.0f) {  // horizontal edge y = cy
+            const float xs = gx + (B * dy) / A;
+            const float dxc = gx - fminf(fmaxf(xs, x0), x1);
+            const float t0 = A * dxc * dxc, t1 = 2.0f * B * dxc * dy, t2 = C * dy * dy;
+            const float q2 = t0 + t1 + t2;
+            if (q2 < qmin) { qmin = q2; mag = t0 + fabsf(t1) + t2; }
+        }
+    }
+    // skip only when certainly below the 1/255 threshold everywhere (NaNs compare false -> keep)
+    return 0.5f * qmin > cut + 1.0e-5f * mag + 1.0e-3f;
+}
+
+__device__ __forceinline__ void warp_rect(int &px0, int &py0)
+{
+    const int w = threadIdx.x >> 5;
+    px0 = blockIdx.x * DMGS_TILE + (w & 1) * 8;
+    py0 = blockIdx.y * DMGS_TILE + (w >> 1) * 4;
 }
 
 __global__ void __launch_bounds__(BLK)
@@ -31,51 +72,73 @@ blend_fwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
                  float *__restrict__ out_color, float *__restrict__ final_T, uint32_t *__restrict__ n_contrib)
 {
     __shared__ float4 s_ra[BLK];   // x, y, conA, conB
-    __shared__ float2 s_rb[BLK];   // conC, opacity
+    __shared__ float4 s_rb[BLK];   // conC, opacity, cut, -
     __shared__ float4 s_rgb[BLK];
 
-    int px, py;
-    pixel_of_thread(px, py);
+    const int lane = threadIdx.x & 31;
+    int px0, py0;
+    warp_rect(px0, py0);
+    const int px = px0 + (lane & 7), py = py0 + (lane >> 3);
     const bool inside = px < a.W && py < a.H;
     const float pxf = (float)px, pyf = (float)py;
+    const float rx0 = (float)px0, rx1 = (float)(px0 + 7), ry0 = (float)py0, ry1 = (float)(py0 + 3);
     const uint2 rng = ranges[blockIdx.y * a.gx + blockIdx.x];
-    int todo = (int)(rng.y - rng.x);
-    const int rounds = (todo + BLK - 1) / BLK;
+    const int total = (int)(rng.y - rng.x);
+    const int rounds = (total + BLK - 1) / BLK;
 
     bool done = !inside;
     float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f;
-    uint32_t contributor = 0, last = 0;
+    uint32_t last = 0;
 
-    for (int r = 0; r < rounds; ++r, todo -= BLK) {
+    for (int r = 0; r < rounds; ++r) {
         if (__syncthreads_count(done) == BLK) break;
         const int idx = r * BLK + threadIdx.x;
-        if (idx < (int)(rng.y - rng.x)) {
+        if (idx < total) {
             const uint32_t g = gidx[rng.x + idx];
-            const float4 ra = rec[2 * (size_t)g], rb = rec[2 * (size_t)g + 1];
-            s_ra[threadIdx.x] = ra;
-            s_rb[threadIdx.x] = make_float2(rb.x, rb.y);
+            s_ra[threadIdx.x] = rec[2 * (size_t)g];
+            s_rb[threadIdx.x] = rec[2 * (size_t)g + 1];
             s_rgb[threadIdx.x] = rgb4[g];
         }
         __syncthreads();
-        const int nb = min(BLK, todo);
-        for (int j = 0; !done && j < nb; ++j) {
-            ++contributor;
-            const float4 ra = s_ra[j];
-            const float2 rb = s_rb[j];
-            const float dx = ra.x - pxf, dy = ra.y - pyf;
-            const float q = fma_(rb.x * dy, dy, (ra.z * dx) * dx);
-            const float power = fma_(-(ra.w * dx), dy, -0.5f * q);
-            if (power > 0.0f) continue;
-            const float alpha = fminf(0.99f, rb.y * dmgs_exp(power));
-            if (alpha < 1.0f / 255.0f) continue;
-            const float test_T = T * (1.0f - alpha);
-            if (test_T < 0.0001f) { done = true; continue; }
-            const float4 c = s_rgb[j];
-            C0 = fma_(c.x * alpha, T, C0);
-            C1 = fma_(c.y * alpha, T, C1);
-            C2 = fma_(c.z * alpha, T, C2);
-            T = test_T;
-            last = contributor;
+        const int nb = min(BLK, total - r * BLK);
+        if (__all_sync(0xffffffffu, done)) continue;  // this warp's pixels are finished; keep staging
+        for (int s0 = 0; s0 < nb; s0 += 32) {
+            // lane <-> entry: which of these 32 entries can touch the warp's rectangle?
+            const int e = s0 + lane;
+            bool keep = false;
+            if (e < nb) {
+                const float4 ra = s_ra[e], rb = s_rb[e];
+                keep = !cull_rect(ra.x, ra.y, ra.z, ra.w, rb.x, rb.z, rx0, rx1, ry0, ry1);
+            }
+            uint32_t m = __ballot_sync(0xffffffffu, keep);
+            // lane <-> pixel over the surviving entries, in list order
+            while (m) {
+                const int j = s0 + __ffs(m) - 1;
+                m &= m - 1;
+                if (!done) {
+                    const float4 ra = s_ra[j], rb = s_rb[j];
+                    const float dx = ra.x - pxf, dy = ra.y - pyf;
+                    const float q = fma_(rb.x * dy, dy, (ra.z * dx) * dx);
+                    const float power = fma_(-(ra.w * dx), dy, -0.5f * q);
+                    if (power <= 0.0f) {
+                        const float alpha = fminf(0.99f, rb.y * dmgs_exp(power));
+                        if (alpha >= 1.0f / 255.0f) {
+                            const float test_T = T * (1.0f - alpha);
+                            if (test_T < 0.0001f) {
+                                done = true;
+                            } else {
+                                const float4 c = s_rgb[j];
+                                C0 = fma_(c.x * alpha, T, C0);
+                                C1 = fma_(c.y * alpha, T, C1);
+                                C2 = fma_(c.z * alpha, T, C2);
+                                T = test_T;
+                                last = (uint32_t)(r * BLK + j + 1);
+                            }
+                        }
+                    }
+                }
+            }
+            if (__all_sync(0xffffffffu, done)) break;
         }
     }
     if (inside) {
@@ -105,11 +168,39 @@ int launch_blend_fwd(const dmgs_params *prm, const void *geom, const GeomLayout 
 }
 
 // ------------------------------------------------------------------------------ backward
-__device__ __forceinline__ float warp_sum(float v)
+// Transposed butterfly: N per-lane values -> N totals over the warp.  At every step a lane keeps
+// one half of its values and hands the other half to its partner, so the payload halves with the
+// distance: 5+3+2+1+1 = 12 shuffles for N = 9.  The total of slot `tr_slot9(lane)` ends in v[0].
+template <int N, int OFF>
+__device__ __forceinline__ void tr_reduce(float *v, int lane)
 {
+    if constexpr (N == 1) {
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    return v;
+        for (int o = OFF; o > 0; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+    } else {
+        constexpr int LO = (N + 1) / 2;
+        const bool up = lane & OFF;
+#pragma unroll
+        for (int i = 0; i < LO; ++i) {
+            const float hi = (LO + i < N) ? v[LO + i] : 0.0f;
+            const float send = up ? v[i] : hi;
+            const float keepv = up ? hi : v[i];
+            v[i] = keepv + __shfl_xor_sync(0xffffffffu, send, OFF);
+        }
+        tr_reduce<LO, OFF / 2>(v, lane);
+    }
+}
+// slot whose total lands in this lane's v[0] after tr_reduce<9,16> (-1: a padding slot)
+__device__ __forceinline__ int tr_slot9(int lane)
+{
+    int n = 9, base = 0, cnt = 9;
+#pragma unroll
+    for (int off = 16; off >= 2; off >>= 1) {
+        const int lo = (n + 1) / 2;
+        if (lane & off) { base += lo; cnt -= lo; } else { cnt = min(cnt, lo); }
+        n = lo;
+    }
+    return cnt >= 1 ? base : -1;
 }
 
 __global__ void __launch_bounds__(BLK)
@@ -119,18 +210,20 @@ blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
                  const float *__restrict__ dL_dpix, float *__restrict__ grad_blend)
 {
     __shared__ float4 s_ra[BLK];
-    __shared__ float2 s_rb[BLK];
+    __shared__ float4 s_rb[BLK];
     __shared__ float4 s_rgb[BLK];
     __shared__ uint32_t s_id[BLK];
     __shared__ int s_max;
 
-    int px, py;
-    pixel_of_thread(px, py);
+    const int lane = threadIdx.x & 31;
+    int px0, py0;
+    warp_rect(px0, py0);
+    const int px = px0 + (lane & 7), py = py0 + (lane >> 3);
     const bool inside = px < a.W && py < a.H;
     const float pxf = (float)px, pyf = (float)py;
+    const float rx0 = (float)px0, rx1 = (float)(px0 + 7), ry0 = (float)py0, ry1 = (float)(py0 + 3);
     const uint2 rng = ranges[blockIdx.y * a.gx + blockIdx.x];
     const size_t pix = (size_t)py * a.W + px, HW = (size_t)a.H * a.W;
-    const int lane = threadIdx.x & 31;
 
     const float T_final = inside ? final_T[pix] : 0.0f;
     const int last = inside ? (int)n_contrib[pix] : 0;
@@ -138,8 +231,10 @@ blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
     if (inside) { dp0 = dL_dpix[pix]; dp1 = dL_dpix[HW + pix]; dp2 = dL_dpix[2 * HW + pix]; }
     const float bg_dot = dot3(a.bg[0], dp0, a.bg[1], dp1, a.bg[2], dp2);
     const float ddelx_dx = 0.5f * (float)a.W, ddely_dy = 0.5f * (float)a.H;
+    const int slot = tr_slot9(lane);
+    const bool owner = slot >= 0 && !(lane & 1);
 
-    // only the first max(n_contrib) entries of the list matter
+    // only the first max(n_contrib) entries of the list matter: per tile for staging, per warp for work
     if (threadIdx.x == 0) s_max = 0;
     __syncthreads();
     const int wmax = __reduce_max_sync(0xffffffffu, last);
@@ -155,65 +250,69 @@ blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
         const int idx = r * BLK + threadIdx.x;
         if (idx < count) {
             const uint32_t g = gidx[rng.x + idx];
-            const float4 ra = rec[2 * (size_t)g], rb = rec[2 * (size_t)g + 1];
             s_id[threadIdx.x] = g;
-            s_ra[threadIdx.x] = ra;
-            s_rb[threadIdx.x] = make_float2(rb.x, rb.y);
+            s_ra[threadIdx.x] = rec[2 * (size_t)g];
+            s_rb[threadIdx.x] = rec[2 * (size_t)g + 1];
             s_rgb[threadIdx.x] = rgb4[g];
         }
         __syncthreads();
-        const int nb = min(BLK, count - r * BLK);
-        for (int j = nb - 1; j >= 0; --j) {
-            const int pos = r * BLK + j;  // 0-based list position
-            float g0 = 0, g1 = 0, g2 = 0, g3 = 0, g4 = 0, g5 = 0, g6 = 0, g7 = 0, g8 = 0;
-            bool hit = false;
-            if (pos < last) {
-                const float4 ra = s_ra[j];
-                const float2 rb = s_rb[j];
-                const float dx = ra.x - pxf, dy = ra.y - pyf;
-                const float q = fma_(rb.x * dy, dy, (ra.z * dx) * dx);
-                const float power = fma_(-(ra.w * dx), dy, -0.5f * q);
-                if (power <= 0.0f) {
-                    const float G = dmgs_exp(power);
-                    const float alpha = fminf(0.99f, rb.y * G);
-                    if (alpha >= 1.0f / 255.0f) {
-                        hit = true;
-                        T = T / (1.0f - alpha);
-                        const float w = alpha * T;
-                        const float4 c = s_rgb[j];
-                        float dL_dalpha;
-                        acc0 = fma_(last_alpha, lc0, (1.0f - last_alpha) * acc0);
-                        acc1 = fma_(last_alpha, lc1, (1.0f - last_alpha) * acc1);
-                        acc2 = fma_(last_alpha, lc2, (1.0f - last_alpha) * acc2);
-                        lc0 = c.x; lc1 = c.y; lc2 = c.z;
-                        dL_dalpha = (c.x - acc0) * dp0;
-                        dL_dalpha = fma_(c.y - acc1, dp1, dL_dalpha);
-                        dL_dalpha = fma_(c.z - acc2, dp2, dL_dalpha);
-                        g6 = w * dp0; g7 = w * dp1; g8 = w * dp2;
-                        dL_dalpha *= T;
-                        last_alpha = alpha;
-                        dL_dalpha = fma_(-T_final / (1.0f - alpha), bg_dot, dL_dalpha);
-                        const float dL_dG = rb.y * dL_dalpha;
-                        const float gdx = G * dx, gdy = G * dy;
-                        const float dG_ddelx = fma_(-gdy, ra.w, -gdx * ra.z);
-                        const float dG_ddely = fma_(-gdx, ra.w, -gdy * rb.x);
-                        g0 = (dL_dG * dG_ddelx) * ddelx_dx;
-                        g1 = (dL_dG * dG_ddely) * ddely_dy;
-                        g2 = (-0.5f * gdx) * dx * dL_dG;
-                        g3 = (-0.5f * gdx) * dy * dL_dG;
-                        g4 = (-0.5f * gdy) * dy * dL_dG;
-                        g5 = G * dL_dalpha;
+        if (r * BLK >= wmax) continue;  // nothing in this round is a contributor for this warp
+        const int nb = min(BLK, min(count, wmax) - r * BLK);
+        for (int s0 = ((nb - 1) / 32) * 32; s0 >= 0; s0 -= 32) {
+            const int e = s0 + lane;
+            bool keep = false;
+            if (e < nb) {
+                const float4 ra = s_ra[e], rb = s_rb[e];
+                keep = !cull_rect(ra.x, ra.y, ra.z, ra.w, rb.x, rb.z, rx0, rx1, ry0, ry1);
+            }
+            uint32_t m = __ballot_sync(0xffffffffu, keep);
+            while (m) {
+                const int jb = 31 - __clz(m);  // back to front
+                m &= ~(1u << jb);
+                const int j = s0 + jb;
+                const int pos = r * BLK + j;  // 0-based list position
+                float v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                bool hit = false;
+                if (pos < last) {
+                    const float4 ra = s_ra[j], rb = s_rb[j];
+                    const float dx = ra.x - pxf, dy = ra.y - pyf;
+                    const float q = fma_(rb.x * dy, dy, (ra.z * dx) * dx);
+                    const float power = fma_(-(ra.w * dx), dy, -0.5f * q);
+                    if (power <= 0.0f) {
+                        const float G = dmgs_exp(power);
+                        const float alpha = fminf(0.99f, rb.y * G);
+                        if (alpha >= 1.0f / 255.0f) {
+                            hit = true;
+                            T = T / (1.0f - alpha);
+                            const float w = alpha * T;
+                            const float4 c = s_rgb[j];
+                            acc0 = fma_(last_alpha, lc0, (1.0f - last_alpha) * acc0);
+                            acc1 = fma_(last_alpha, lc1, (1.0f - last_alpha) * acc1);
+                            acc2 = fma_(last_alpha, lc2, (1.0f - last_alpha) * acc2);
+                            lc0 = c.x; lc1 = c.y; lc2 = c.z;
+                            float dL_dalpha = (c.x - acc0) * dp0;
+                            dL_dalpha = fma_(c.y - acc1, dp1, dL_dalpha);
+                            dL_dalpha = fma_(c.z - acc2, dp2, dL_dalpha);
+                            v[6] = w * dp0; v[7] = w * dp1; v[8] = w * dp2;
+                            dL_dalpha *= T;
+                            last_alpha = alpha;
+                            dL_dalpha = fma_(-T_final / (1.0f - alpha), bg_dot, dL_dalpha);
+                            const float dL_dG = rb.y * dL_dalpha;
+                            const float gdx = G * dx, gdy = G * dy;
+                            const float dG_ddelx = fma_(-gdy, ra.w, -gdx * ra.z);
+                            const float dG_ddely = fma_(-gdx, ra.w, -gdy * rb.x);
+                            v[0] = (dL_dG * dG_ddelx) * ddelx_dx;
+                            v[1] = (dL_dG * dG_ddely) * ddely_dy;
+                            v[2] = (-0.5f * gdx) * dx * dL_dG;
+                            v[3] = (-0.5f * gdx) * dy * dL_dG;
+                            v[4] = (-0.5f * gdy) * dy * dL_dG;
+                            v[5] = G * dL_dalpha;
+                        }
                     }
                 }
-            }
-            if (!__any_sync(0xffffffffu, hit)) continue;
-            g0 = warp_sum(g0); g1 = warp_sum(g1); g2 = warp_sum(g2); g3 = warp_sum(g3); g4 = warp_sum(g4);
-            g5 = warp_sum(g5); g6 = warp_sum(g6); g7 = warp_sum(g7); g8 = warp_sum(g8);
-            if (lane == 0) {
-                float *dst = grad_blend + 12 * (size_t)s_id[j];
-                atomicAdd(dst + 0, g0); atomicAdd(dst + 1, g1); atomicAdd(dst + 2, g2); atomicAdd(dst + 3, g3);
-                atomicAdd(dst + 4, g4); atomicAdd(dst + 5, g5); atomicAdd(dst + 6, g6); atomicAdd(dst + 7, g7);
-                atomicAdd(dst + 8, g8);
+                if (!__any_sync(0xffffffffu, hit)) continue;
+                tr_reduce<9, 16>(v, lane);
+                if (owner) atomicAdd(grad_blend + 12 * (size_t)s_id[j] + slot, v[0]);
             }
         }
     }

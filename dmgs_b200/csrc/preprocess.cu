@@ -196,7 +196,9 @@ preprocess_fwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
             if (nt > 0) {
                 const float op = opacities[i];
                 // conservative blend cut-off: power < -cut  =>  opacity*exp(power) < 1/255 for sure
-                const float cut = op > 0.0f ? logf(255.0f * op) + 1.0e-3f : -1.0f;
+                // (+inf, i.e. never culled, when a caller-supplied covariance makes the conic indefinite)
+                const bool pd = det > 0.0f && e.a > 0.0f && e.c > 0.0f;
+                const float cut = !pd ? __int_as_float(0x7f800000) : (op > 0.0f ? logf(255.0f * op) + 1.0e-3f : -1.0f);
                 rad = (int)rf;
                 ntiles = (uint32_t)nt;
                 depth = e.tz;

@@ -146,11 +146,12 @@ def test_backward_accumulate_mode():
         args = (st, dL, cl["means3D"].cuda(), d("shs"), d("scales"), d("rotations"), d("cov3D_precomp"), "colors_precomp" in npin)
         g1 = rasterize_backward(*args)
         P = 3000
-        acc = {"means3D": torch.ones(P, 3).cuda(), "means2D": torch.ones(P, 3).cuda(), "opacities": torch.ones(P, 1).cuda(),
-               "colors_precomp": torch.ones(P, 3).cuda(), "scales": torch.ones(P, 3).cuda(), "rotations": torch.ones(P, 4).cuda(),
-               "cov3D_precomp": torch.ones(P, 6).cuda()}
+        acc = {"means3D": torch.zeros(P, 3).cuda(), "means2D": torch.zeros(P, 3).cuda(), "opacities": torch.zeros(P, 1).cuda(),
+               "colors_precomp": torch.zeros(P, 3).cuda(), "scales": torch.zeros(P, 3).cuda(), "rotations": torch.zeros(P, 4).cuda(),
+               "cov3D_precomp": torch.zeros(P, 6).cuda()}
         if "shs" in npin:
-            acc["shs"] = torch.ones_like(d("shs"))
+            acc["shs"] = torch.zeros_like(d("shs"))
+        acc["means2D"][:, 2] = 7.0  # never touched
         rasterize_backward(*args, accumulate_into=acc)
         rasterize_backward(*args, accumulate_into=acc)
         torch.cuda.synchronize()
@@ -158,9 +159,9 @@ def test_backward_accumulate_mode():
         for n, g in zip(names, g1):
             if g is None:
                 continue
-            got = (acc[n] - 1.0) * 0.5  # two accumulations on top of the initial ones
+            got = acc[n] * 0.5  # two accumulations
             if n == "means2D":
-                assert torch.all(acc[n][:, 2] == 1.0)
+                assert torch.all(acc[n][:, 2] == 7.0)
                 got[:, 2] = 0.0
             # the blend backward's atomics make every run's summation order different
             grad_close(got.cpu().numpy(), g.cpu().numpy(), rtol=2e-4, name=f"{mode}/{n}")
