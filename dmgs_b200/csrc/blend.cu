@@ -22,11 +22,46 @@
 namespace dmgs {
 
 constexpr int BLK = 256;
+#ifndef BWD_MIN_BLOCKS
+#define BWD_MIN_BLOCKS 4
+#endif
 
 struct BlendArgs {
     int W, H, gx, gy;
     float bg[3];
 };
+
+// Shared-memory reads in the inner loops go through explicit 32-bit shared addresses: with C++
+// indexing nvcc rebuilds the cluster-window base (S2UR SR_CgaCtaId + ULEA) inside the hot loop,
+// ~12 instructions and a scoreboard stall per entry (profiles/r1a).
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds128(uint32_t a)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void reds_add(uint32_t a, float v)
+{
+    asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_global_v4(float *p, float4 v)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// 1/x for x in [0.01, 1]: MUFU.RCP refined by one Newton step (error < 1 ulp, no slow path)
+__device__ __forceinline__ float rcp_nr(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fma_(r, fma_(-x, r, 1.0f), r);
+}
 
 // exact minimum over the pixel rectangle [x0,x1]x[y0,y1] of q(d) = A dx^2 + 2 B dx dy + C dy^2,
 // d = g - p, for a positive-definite conic; returns true when the entry can be skipped for every
@@ -89,6 +124,7 @@ blend_fwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
     bool done = !inside;
     float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f;
     uint32_t last = 0;
+    const uint32_t a_ra = smem_addr(s_ra), a_rb = smem_addr(s_rb), a_rgb = smem_addr(s_rgb);
 
     for (int r = 0; r < rounds; ++r) {
         if (__syncthreads_count(done) == BLK) break;
@@ -107,7 +143,7 @@ blend_fwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
             const int e = s0 + lane;
             bool keep = false;
             if (e < nb) {
-                const float4 ra = s_ra[e], rb = s_rb[e];
+                const float4 ra = lds128(a_ra + 16u * e), rb = lds128(a_rb + 16u * e);
                 keep = !cull_rect(ra.x, ra.y, ra.z, ra.w, rb.x, rb.z, rx0, rx1, ry0, ry1);
             }
             uint32_t m = __ballot_sync(0xffffffffu, keep);
@@ -116,7 +152,7 @@ blend_fwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
                 const int j = s0 + __ffs(m) - 1;
                 m &= m - 1;
                 if (!done) {
-                    const float4 ra = s_ra[j], rb = s_rb[j];
+                    const float4 ra = lds128(a_ra + 16u * j), rb = lds128(a_rb + 16u * j);
                     const float dx = ra.x - pxf, dy = ra.y - pyf;
                     const float q = fma_(rb.x * dy, dy, (ra.z * dx) * dx);
                     const float power = fma_(-(ra.w * dx), dy, -0.5f * q);
@@ -127,7 +163,7 @@ blend_fwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
                             if (test_T < 0.0001f) {
                                 done = true;
                             } else {
-                                const float4 c = s_rgb[j];
+                                const float4 c = lds128(a_rgb + 16u * j);
                                 C0 = fma_(c.x * alpha, T, C0);
                                 C1 = fma_(c.y * alpha, T, C1);
                                 C2 = fma_(c.z * alpha, T, C2);
@@ -203,7 +239,7 @@ __device__ __forceinline__ int tr_slot9(int lane)
     return cnt >= 1 ? base : -1;
 }
 
-__global__ void __launch_bounds__(BLK)
+__global__ void __launch_bounds__(BLK, BWD_MIN_BLOCKS)
 blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ ranges,
                  const uint32_t *__restrict__ gidx, const float4 *__restrict__ rec, const float4 *__restrict__ rgb4,
                  const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
@@ -212,6 +248,7 @@ blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
     __shared__ float4 s_ra[BLK];
     __shared__ float4 s_rb[BLK];
     __shared__ float4 s_rgb[BLK];
+    __shared__ float4 s_acc[BLK * 3];  // per staged entry: the 9 (+3 pad) gradient sums of this tile
     __shared__ uint32_t s_id[BLK];
     __shared__ int s_max;
 
@@ -229,13 +266,18 @@ blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
     const int last = inside ? (int)n_contrib[pix] : 0;
     float dp0 = 0, dp1 = 0, dp2 = 0;
     if (inside) { dp0 = dL_dpix[pix]; dp1 = dL_dpix[HW + pix]; dp2 = dL_dpix[2 * HW + pix]; }
-    const float bg_dot = dot3(a.bg[0], dp0, a.bg[1], dp1, a.bg[2], dp2);
+    const float bgT = -T_final * dot3(a.bg[0], dp0, a.bg[1], dp1, a.bg[2], dp2);
     const float ddelx_dx = 0.5f * (float)a.W, ddely_dy = 0.5f * (float)a.H;
     const int slot = tr_slot9(lane);
     const bool owner = slot >= 0 && !(lane & 1);
+    const uint32_t a_ra = smem_addr(s_ra), a_rb = smem_addr(s_rb), a_rgb = smem_addr(s_rgb);
+    const uint32_t a_acc = smem_addr(s_acc) + 4u * (uint32_t)(slot < 0 ? 0 : slot);
 
     // only the first max(n_contrib) entries of the list matter: per tile for staging, per warp for work
     if (threadIdx.x == 0) s_max = 0;
+    s_acc[threadIdx.x] = make_float4(0, 0, 0, 0);
+    s_acc[BLK + threadIdx.x] = make_float4(0, 0, 0, 0);
+    s_acc[2 * BLK + threadIdx.x] = make_float4(0, 0, 0, 0);
     __syncthreads();
     const int wmax = __reduce_max_sync(0xffffffffu, last);
     if (lane == 0) atomicMax(&s_max, wmax);
@@ -246,7 +288,6 @@ blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
     float T = T_final, acc0 = 0, acc1 = 0, acc2 = 0, lc0 = 0, lc1 = 0, lc2 = 0, last_alpha = 0;
     const int rounds = (count + BLK - 1) / BLK;
     for (int r = rounds - 1; r >= 0; --r) {
-        __syncthreads();
         const int idx = r * BLK + threadIdx.x;
         if (idx < count) {
             const uint32_t g = gidx[rng.x + idx];
@@ -256,65 +297,90 @@ blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
             s_rgb[threadIdx.x] = rgb4[g];
         }
         __syncthreads();
-        if (r * BLK >= wmax) continue;  // nothing in this round is a contributor for this warp
-        const int nb = min(BLK, min(count, wmax) - r * BLK);
-        for (int s0 = ((nb - 1) / 32) * 32; s0 >= 0; s0 -= 32) {
-            const int e = s0 + lane;
-            bool keep = false;
-            if (e < nb) {
-                const float4 ra = s_ra[e], rb = s_rb[e];
-                keep = !cull_rect(ra.x, ra.y, ra.z, ra.w, rb.x, rb.z, rx0, rx1, ry0, ry1);
-            }
-            uint32_t m = __ballot_sync(0xffffffffu, keep);
-            while (m) {
-                const int jb = 31 - __clz(m);  // back to front
-                m &= ~(1u << jb);
-                const int j = s0 + jb;
-                const int pos = r * BLK + j;  // 0-based list position
-                float v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-                bool hit = false;
-                if (pos < last) {
-                    const float4 ra = s_ra[j], rb = s_rb[j];
-                    const float dx = ra.x - pxf, dy = ra.y - pyf;
-                    const float q = fma_(rb.x * dy, dy, (ra.z * dx) * dx);
-                    const float power = fma_(-(ra.w * dx), dy, -0.5f * q);
-                    if (power <= 0.0f) {
-                        const float G = dmgs_exp(power);
-                        const float alpha = fminf(0.99f, rb.y * G);
-                        if (alpha >= 1.0f / 255.0f) {
-                            hit = true;
-                            T = T / (1.0f - alpha);
-                            const float w = alpha * T;
-                            const float4 c = s_rgb[j];
-                            acc0 = fma_(last_alpha, lc0, (1.0f - last_alpha) * acc0);
-                            acc1 = fma_(last_alpha, lc1, (1.0f - last_alpha) * acc1);
-                            acc2 = fma_(last_alpha, lc2, (1.0f - last_alpha) * acc2);
-                            lc0 = c.x; lc1 = c.y; lc2 = c.z;
-                            float dL_dalpha = (c.x - acc0) * dp0;
-                            dL_dalpha = fma_(c.y - acc1, dp1, dL_dalpha);
-                            dL_dalpha = fma_(c.z - acc2, dp2, dL_dalpha);
-                            v[6] = w * dp0; v[7] = w * dp1; v[8] = w * dp2;
-                            dL_dalpha *= T;
-                            last_alpha = alpha;
-                            dL_dalpha = fma_(-T_final / (1.0f - alpha), bg_dot, dL_dalpha);
-                            const float dL_dG = rb.y * dL_dalpha;
-                            const float gdx = G * dx, gdy = G * dy;
-                            const float dG_ddelx = fma_(-gdy, ra.w, -gdx * ra.z);
-                            const float dG_ddely = fma_(-gdx, ra.w, -gdy * rb.x);
-                            v[0] = (dL_dG * dG_ddelx) * ddelx_dx;
-                            v[1] = (dL_dG * dG_ddely) * ddely_dy;
-                            v[2] = (-0.5f * gdx) * dx * dL_dG;
-                            v[3] = (-0.5f * gdx) * dy * dL_dG;
-                            v[4] = (-0.5f * gdy) * dy * dL_dG;
-                            v[5] = G * dL_dalpha;
+        if (r * BLK < wmax) {  // else nothing in this round is a contributor for this warp
+            const int nb = min(BLK, min(count, wmax) - r * BLK);
+            for (int s0 = ((nb - 1) / 32) * 32; s0 >= 0; s0 -= 32) {
+                const int e = s0 + lane;
+                bool keep = false;
+                if (e < nb) {
+                    const float4 ra = lds128(a_ra + 16u * e), rb = lds128(a_rb + 16u * e);
+                    keep = !cull_rect(ra.x, ra.y, ra.z, ra.w, rb.x, rb.z, rx0, rx1, ry0, ry1);
+                }
+                uint32_t m = __ballot_sync(0xffffffffu, keep);
+                while (m) {
+                    const int jb = 31 - __clz(m);  // back to front
+                    m &= ~(1u << jb);
+                    const int j = s0 + jb;
+                    const int pos = r * BLK + j;  // 0-based list position
+                    float v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                    bool hit = false;
+                    if (pos < last) {
+                        const float4 ra = lds128(a_ra + 16u * j), rb = lds128(a_rb + 16u * j);
+                        const float dx = ra.x - pxf, dy = ra.y - pyf;
+                        const float q = fma_(rb.x * dy, dy, (ra.z * dx) * dx);
+                        const float power = fma_(-(ra.w * dx), dy, -0.5f * q);
+                        if (power <= 0.0f) {
+                            // same exp / alpha arithmetic as the forward: the contributor set is identical
+                            const float G = dmgs_exp(power);
+                            const float alpha = fminf(0.99f, rb.y * G);
+                            if (alpha >= 1.0f / 255.0f) {
+                                hit = true;
+                                // one refined reciprocal replaces two IEEE divisions by (1 - alpha) (no FCHK /
+                                // slow-path branches; operands are in [0.01, 1] so no special cases exist)
+                                const float oma = 1.0f - alpha;
+                                const float inv = rcp_nr(oma);
+                                const float t0 = T * inv;  // T / (1 - alpha), residual-corrected: the error must
+                                T = fma_(fma_(-t0, oma, T), inv, t0);  // not accumulate along the list
+                                const float w = alpha * T;
+                                const float4 c = lds128(a_rgb + 16u * j);
+                                const float om = 1.0f - last_alpha;
+                                acc0 = fma_(last_alpha, lc0, om * acc0);
+                                acc1 = fma_(last_alpha, lc1, om * acc1);
+                                acc2 = fma_(last_alpha, lc2, om * acc2);
+                                lc0 = c.x; lc1 = c.y; lc2 = c.z;
+                                float dL_dalpha = (c.x - acc0) * dp0;
+                                dL_dalpha = fma_(c.y - acc1, dp1, dL_dalpha);
+                                dL_dalpha = fma_(c.z - acc2, dp2, dL_dalpha);
+                                v[6] = w * dp0; v[7] = w * dp1; v[8] = w * dp2;
+                                last_alpha = alpha;
+                                dL_dalpha = fma_(bgT, inv, dL_dalpha * T);
+                                const float dL_dG = rb.y * dL_dalpha;
+                                const float gdx = G * dx, gdy = G * dy;
+                                const float dG_ddelx = fma_(-gdy, ra.w, -gdx * ra.z);
+                                const float dG_ddely = fma_(-gdx, ra.w, -gdy * rb.x);
+                                const float hg = -0.5f * dL_dG;
+                                v[0] = (dL_dG * dG_ddelx) * ddelx_dx;
+                                v[1] = (dL_dG * dG_ddely) * ddely_dy;
+                                v[2] = (hg * gdx) * dx;
+                                v[3] = (hg * gdx) * dy;
+                                v[4] = (hg * gdy) * dy;
+                                v[5] = G * dL_dalpha;
+                            }
                         }
                     }
+                    if (!__any_sync(0xffffffffu, hit)) continue;
+                    tr_reduce<9, 16>(v, lane);
+                    if (owner) reds_add(a_acc + 48u * j, v[0]);
                 }
-                if (!__any_sync(0xffffffffu, hit)) continue;
-                tr_reduce<9, 16>(v, lane);
-                if (owner) atomicAdd(grad_blend + 12 * (size_t)s_id[j] + slot, v[0]);
             }
         }
+        __syncthreads();
+        // flush the round's tile-level sums: three 16-byte vector reductions per touched Gaussian
+        if (idx < count) {
+            const float4 g0 = s_acc[3 * threadIdx.x], g1 = s_acc[3 * threadIdx.x + 1], g2 = s_acc[3 * threadIdx.x + 2];
+            const bool nz = g0.x != 0.0f || g0.y != 0.0f || g0.z != 0.0f || g0.w != 0.0f || g1.x != 0.0f || g1.y != 0.0f ||
+                            g1.z != 0.0f || g1.w != 0.0f || g2.x != 0.0f;
+            if (nz) {
+                float *dst = grad_blend + 12 * (size_t)s_id[threadIdx.x];
+                red_global_v4(dst, g0);
+                red_global_v4(dst + 4, g1);
+                red_global_v4(dst + 8, g2);
+                s_acc[3 * threadIdx.x] = make_float4(0, 0, 0, 0);
+                s_acc[3 * threadIdx.x + 1] = make_float4(0, 0, 0, 0);
+                s_acc[3 * threadIdx.x + 2] = make_float4(0, 0, 0, 0);
+            }
+        }
+        __syncthreads();
     }
 }
 
