@@ -1,0 +1,120 @@
+"""View-partitioned multi-GPU training step: replicated Gaussians, the camera batch of a step split
+over the ranks of one box, one all-reduce of the flat per-Gaussian gradient buffer per step.
+
+The reference is single-view, single-GPU (train_geo_stage2.py:91-93 pops ONE camera per iteration,
+utils/general_utils.py:133 pins cuda:0), so this module is new capability,
+not a mirror.  One process per GPU (torchrun); `torch.distributed` is the plumbing (NCCL over
+NVLink on the GPU box, gloo in the CPU tests).  There is no data-path collective other than the one
+gradient all-reduce: every view's render is independent given identical Gaussians.
+
+    buf  = FlatGradBuffer(P, RASTER_WIDTHS_SH, device)
+    vp   = ViewParallel()                      # reads the default process group
+    loss = vp.step(n_views, lambda v, acc: render_and_accumulate(v, acc), buf)
+    # buf.views["means3D"] ... now hold the gradient summed over ALL views of the step, on every rank
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+# floats per Gaussian of every gradient the rasteriser returns, per input mode
+RASTER_WIDTHS_SH = {"means3D": (3,), "means2D": (3,), "opacities": (1,), "scales": (3,), "rotations": (4,),
+                    "shs": (16, 3)}
+RASTER_WIDTHS_PRECOMP = {"means3D": (3,), "means2D": (3,), "opacities": (1,), "colors_precomp": (3,),
+                         "cov3D_precomp": (6,)}
+RASTER_WIDTHS_STAGE2_FUSED = {"means3D": (3,), "means2D": (3,), "opacities": (1,), "cov3D_precomp": (6,),
+                              "shs": (3, 16)}
+
+
+def partition_views(n_views: int, world: int, rank: int) -> List[int]:
+    """Views of a step rendered by `rank`: v = rank (mod world) -- round-robin keeps ranks within one
+    view of each other for any n_views."""
+    if not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside world of {world}")
+    return list(range(rank, n_views, world))
+
+
+class FlatGradBuffer:
+    """One contiguous fp32 buffer holding every per-Gaussian gradient, field-major, with named
+    [P, ...] views.  The views are what `rasterize_backward(..., accumulate_into=views)` adds to and
+    the flat tensor is the single all-reduce payload of a step."""
+
+    def __init__(self, P: int, widths: Dict[str, Tuple[int, ...]], device, dtype=torch.float32):
+        self.P, self.widths = int(P), dict(widths)
+        n = 0
+        self.offsets: Dict[str, Tuple[int, int]] = {}
+        for name, tail in self.widths.items():
+            w = 1
+            for t in tail:
+                w *= int(t)
+            # 16-byte aligned fields: the SH rows are written with bulk (TMA) reductions
+            n = (n + 3) // 4 * 4
+            self.offsets[name] = (n, self.P * w)
+            n += self.P * w
+        self.flat = torch.zeros(n, dtype=dtype, device=device)
+        self.views = {name: self.flat[o:o + m].view(self.P, *self.widths[name]) for name, (o, m) in self.offsets.items()}
+
+    def zero_(self):
+        self.flat.zero_()
+        return self
+
+    def nbytes(self) -> int:
+        return self.flat.numel() * self.flat.element_size()
+
+
+class ViewParallel:
+    """Runs the local views of a step and all-reduces the flat gradient buffer."""
+
+    def __init__(self, group: Optional[dist.ProcessGroup] = None):
+        self.group = group
+        on = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if on else 1
+        self.rank = dist.get_rank(group) if on else 0
+
+    def local_views(self, n_views: int) -> List[int]:
+        return partition_views(n_views, self.world, self.rank)
+
+    def step(self, n_views: int, render_view: Callable[[int, Dict[str, torch.Tensor]], Optional[torch.Tensor]],
+             buf: FlatGradBuffer, average: bool = False, extra: Sequence[torch.Tensor] = ()) -> Optional[torch.Tensor]:
+        """render_view(v, buf.views) must ADD view v's gradients into the views and may return the
+        view's loss (a 0-d tensor).  Returns the loss summed (or averaged) over all views of the
+        step.  `extra` tensors (e.g. dL/dverts of a mesh-bound model) are all-reduced as well."""
+        buf.zero_()
+        loss = None
+        for v in self.local_views(n_views):
+            l = render_view(v, buf.views)
+            if l is not None:
+                loss = l.detach().clone() if loss is None else loss + l.detach()
+        if self.world > 1:
+            dist.all_reduce(buf.flat, op=dist.ReduceOp.SUM, group=self.group)
+            for t in extra:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            if loss is None:
+                loss = torch.zeros((), dtype=buf.flat.dtype, device=buf.flat.device)
+            dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)
+        if average and n_views > 0:
+            buf.flat.div_(n_views)
+            for t in extra:
+                t.div_(n_views)
+            if loss is not None:
+                loss = loss / n_views
+        return loss
+
+
+def accumulate_view(settings, inputs: Dict[str, Optional[torch.Tensor]], image_grad: Callable, acc: Dict[str, torch.Tensor],
+                    sh_layout: int = 0, sh_activation: int = 0):
+    """One view forward + backward on the CUDA path with gradients ADDED into `acc`.
+
+    inputs: means3D, opacities and the optional shs / colors_precomp / scales / rotations / cov3D_precomp.
+    image_grad(image) -> (loss 0-d tensor or None, dL/dimage [3,H,W]).  Returns (loss, image, radii)."""
+    from .rasterizer import rasterize_backward, rasterize_forward
+    g = inputs.get
+    color, radii, state = rasterize_forward(settings, inputs["means3D"], inputs["opacities"], g("shs"),
+                                            g("colors_precomp"), g("scales"), g("rotations"), g("cov3D_precomp"),
+                                            sh_layout, sh_activation)
+    loss, dL = image_grad(color)
+    rasterize_backward(state, dL.contiguous(), inputs["means3D"], g("shs"), g("scales"), g("rotations"),
+                       g("cov3D_precomp"), g("colors_precomp") is not None, accumulate_into=acc)
+    return loss, color, radii

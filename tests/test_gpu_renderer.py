@@ -1,0 +1,110 @@
+"""GPU tests of the host-side mirrors: render / render_dyn (dmgs_b200/renderer.py) against the
+reference's data flow (python SH -> colors_precomp), and the view-batched accumulation of
+dmgs_b200/multiview.py against per-view autograd."""
+import math
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from dmgs_b200 import synthetic as S
+from oracle import torch_oracle as TO
+from util import grad_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _stage2_scene(F=4000, k=3, seed=2):
+    from dmgs_b200.binding import renew_gaussian
+    verts, faces = S.jittered_sphere_mesh(F, seed=seed, jitter=0.05)
+    bc, rad = S.barycentric_layout(k)
+    P = faces.shape[0] * k
+    feats = (torch.randn(P, 3, 16, generator=torch.Generator().manual_seed(seed)) * 0.3).cuda().requires_grad_()
+    v = verts.cuda().requires_grad_()
+    sf = torch.tensor([math.atanh(0.5)], device="cuda", requires_grad=True)
+    gs = renew_gaussian(v, faces.cuda(), bc.cuda(), rad, 4.43, sf, feats)
+    return gs, v, sf, feats
+
+
+def test_render_dyn_fused_sh_matches_python_sh():
+    """render_dyn with the SH folded into preprocess == the reference's flow
+    (gaussian_renderer/__init__.py:166-186: python eval_sh + sigmoid -> colors_precomp)."""
+    from dmgs_b200 import GaussianRasterizer
+    from dmgs_b200.renderer import render_dyn
+    from gpu_util import settings_for
+    cam = S.nerf_synthetic_camera(1, 320, 240)
+    bg = torch.ones(3, device="cuda")
+    pipe = SimpleNamespace(compute_cov3D_python=True, convert_SHs_python=True, debug=False)
+    dL = torch.randn(3, 240, 320, generator=torch.Generator().manual_seed(4)).cuda()
+
+    gs, v, sf, feats = _stage2_scene()
+    out = render_dyn(cam, gs, pipe, bg)
+    assert set(out) == {"render", "viewspace_points", "visibility_filter", "radii"}
+    (out["render"] * dL).sum().backward()
+    g_fused = [t.grad.clone() for t in (v, sf, feats)]
+    assert out["viewspace_points"].grad.shape == (gs["xyz"].shape[0], 3)
+
+    gs2, v2, sf2, feats2 = _stage2_scene()
+    campos = cam.camera_center.cuda()
+    col = TO.eval_sh_colors(3, feats2.transpose(1, 2), gs2["xyz"], campos, 1)
+    ras = GaussianRasterizer(settings_for(cam, (1, 1, 1)))
+    img, radii = ras(means3D=gs2["xyz"], means2D=torch.zeros_like(gs2["xyz"]), shs=None, colors_precomp=col,
+                     opacities=gs2["opacity"], scales=None, rotations=None, cov3D_precomp=gs2["covariance"])
+    (img * dL).sum().backward()
+    assert torch.equal(radii, out["radii"])
+    assert (img - out["render"]).abs().max().item() <= 1e-5
+    for a, b, name in zip(g_fused, (v2.grad, sf2.grad, feats2.grad), ("verts", "scale_factor", "features")):
+        grad_close(a.cpu().numpy().reshape(a.shape[0], -1), b.cpu().numpy().reshape(b.shape[0], -1), rtol=2e-4, name=name)
+
+
+def test_render_stage1_surface():
+    from dmgs_b200.renderer import render
+    cam = S.nerf_synthetic_camera(0, 200, 160)
+    cl = S.random_cloud(3000, seed=1, extent=1.0, log_scale_mean=math.log(0.05))
+    t = {k: x.cuda().requires_grad_() for k, x in cl.items()}
+    pc = SimpleNamespace(get_xyz=t["means3D"], get_opacity=t["opacities"], get_scaling=t["scales"],
+                         get_rotation=t["rotations"], get_features=t["shs"], active_sh_degree=3, max_sh_degree=3)
+    pipe = SimpleNamespace(compute_cov3D_python=False, convert_SHs_python=False, debug=False)
+    out = render(cam, pc, pipe, torch.zeros(3, device="cuda"))
+    out["render"].mean().backward()
+    assert out["render"].shape == (3, 160, 200)
+    assert out["visibility_filter"].dtype == torch.bool and out["visibility_filter"].sum() > 0
+    assert torch.isfinite(t["shs"].grad).all() and t["shs"].grad.abs().sum() > 0
+    # sigmoid variant (DMGS's convert_SHs_python flow, __init__.py:74-78) == python sigmoid(eval_sh) -> colors_precomp
+    pipe2 = SimpleNamespace(compute_cov3D_python=False, convert_SHs_python=True, debug=False)
+    out2 = render(cam, pc, pipe2, torch.zeros(3, device="cuda"))
+    col = TO.eval_sh_colors(3, t["shs"].detach(), t["means3D"].detach(), cam.camera_center.cuda(), 1)
+    out3 = render(cam, pc, pipe2, torch.zeros(3, device="cuda"), override_color=col)
+    assert (out2["render"] - out3["render"]).abs().max().item() <= 1e-5
+
+
+def test_multiview_accumulate_equals_sum_of_views():
+    from dmgs_b200 import GaussianRasterizer, multiview as MV
+    from gpu_util import settings_for
+    P, W, H, NV = 5000, 160, 120, 3
+    cl = S.random_cloud(P, seed=8, extent=1.0, log_scale_mean=math.log(0.05))
+    d = {k: v.cuda() for k, v in cl.items()}
+    cams = [S.nerf_synthetic_camera(v, W, H) for v in range(NV)]
+    sets = [settings_for(c, (0, 0, 0)) for c in cams]
+    dLs = [torch.randn(3, H, W, generator=torch.Generator().manual_seed(v)).cuda() for v in range(NV)]
+    buf = MV.FlatGradBuffer(P, MV.RASTER_WIDTHS_SH, "cuda")
+    vp = MV.ViewParallel()
+    inputs = dict(means3D=d["means3D"], opacities=d["opacities"], shs=d["shs"], scales=d["scales"], rotations=d["rotations"])
+
+    def rv(v, acc):
+        loss, _, _ = MV.accumulate_view(sets[v], inputs, lambda img: ((img * dLs[v]).sum(), dLs[v]), acc)
+        return loss
+
+    loss = vp.step(NV, rv, buf)
+    t = {k: x.clone().requires_grad_() for k, x in d.items()}
+    tot = 0
+    for v in range(NV):
+        img, _ = GaussianRasterizer(sets[v])(means3D=t["means3D"], means2D=torch.zeros_like(t["means3D"]), shs=t["shs"],
+                                             opacities=t["opacities"], scales=t["scales"], rotations=t["rotations"])
+        tot = tot + (img * dLs[v]).sum()
+    tot.backward()
+    assert abs(loss.item() - tot.item()) <= 1e-4 * abs(tot.item())
+    for name in ("means3D", "opacities", "scales", "rotations", "shs"):
+        a, b = buf.views[name].cpu().numpy(), t[name].grad.cpu().numpy()
+        grad_close(a.reshape(P, -1), b.reshape(P, -1), rtol=2e-4, name=name)
