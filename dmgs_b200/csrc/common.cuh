@@ -50,7 +50,8 @@ struct ImgLayout {
     size_t final_T, n_contrib, total;
 };
 
-constexpr int SORT_ITEMS_PER_BLOCK = 2048;  // 256 threads x 8 rounds
+constexpr int SORT_MIN_ITEMS_PER_BLOCK = 1024;  // 256 threads x 4 rounds (8 rounds above RADIX_SMALL_N items)
+constexpr int64_t RADIX_SMALL_N = 2 * 1024 * 1024;
 constexpr int SORT_MAX_BINS = 256;
 
 static inline size_t scan_tmp_bytes(size_t n) { return align_up((n / 2048 + 2) * sizeof(uint32_t) * 2); }
@@ -71,7 +72,7 @@ static inline GeomLayout geom_layout(int32_t P)
     L.keys_a = o;  o += align_up(n * 4);
     L.keys_b = o;  o += align_up(n * 4);
     L.vals_b = o;  o += align_up(n * 4);
-    L.sort_blocks = (int)((n + SORT_ITEMS_PER_BLOCK - 1) / SORT_ITEMS_PER_BLOCK);
+    L.sort_blocks = (int)((n + SORT_MIN_ITEMS_PER_BLOCK - 1) / SORT_MIN_ITEMS_PER_BLOCK);
     size_t hist_n = (size_t)(L.sort_blocks + 1) * SORT_MAX_BINS + 1;  // table + bin totals
     L.hist = o;    o += align_up(hist_n * 4);
     size_t big = hist_n > n ? hist_n : n;
@@ -91,7 +92,7 @@ static inline BinLayout bin_layout(int32_t P, int64_t R, int32_t W, int32_t H)
     L.ranges = o;  o += align_up(T * 8);
     L.tiles_b = o; o += align_up(n * 4);
     L.gidx_b = o;  o += align_up(n * 4);
-    L.sort_blocks = (int)((n + SORT_ITEMS_PER_BLOCK - 1) / SORT_ITEMS_PER_BLOCK);
+    L.sort_blocks = (int)((n + SORT_MIN_ITEMS_PER_BLOCK - 1) / SORT_MIN_ITEMS_PER_BLOCK);
     size_t hist_n = (size_t)(L.sort_blocks + 1) * SORT_MAX_BINS + 1;  // table + bin totals
     L.hist = o;    o += align_up(hist_n * 4);
     L.scan_tmp = o; o += scan_tmp_bytes(hist_n);

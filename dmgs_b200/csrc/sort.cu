@@ -127,15 +127,19 @@ int exclusive_scan_u32(const uint32_t *in, const uint32_t *gather, uint32_t *out
 // shared memory turn the block's scanned table column into final positions.
 constexpr int RP_THREADS = 256;
 constexpr int RP_WARPS = RP_THREADS / 32;
-constexpr int RP_ROUNDS = SORT_ITEMS_PER_BLOCK / RP_THREADS;  // 8
+#ifndef SCATTER_MIN_BLOCKS
+#define SCATTER_MIN_BLOCKS 4
+#endif
 
+template <int RP_ROUNDS>
 __global__ void __launch_bounds__(RP_THREADS)
 radix_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift, int bins, int nblocks,
                   uint32_t *__restrict__ hist)
 {
     __shared__ uint32_t h[SORT_MAX_BINS];
     for (int d = threadIdx.x; d < bins; d += RP_THREADS) h[d] = 0;
-    const int64_t base = (int64_t)blockIdx.x * SORT_ITEMS_PER_BLOCK;
+    constexpr int ITEMS = RP_ROUNDS * RP_THREADS;
+    const int64_t base = (int64_t)blockIdx.x * ITEMS;
     const uint32_t mask = (uint32_t)bins - 1;
     uint32_t k[RP_ROUNDS];
 #pragma unroll
@@ -166,23 +170,24 @@ __device__ __forceinline__ uint32_t digit_peers(uint32_t d, uint32_t act)
     return peers;
 }
 
-template <int BITS>
-__global__ void __launch_bounds__(RP_THREADS)
+template <int BITS, int RP_ROUNDS>
+__global__ void __launch_bounds__(RP_THREADS, SCATTER_MIN_BLOCKS)
 radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                      uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n, int shift,
                      int nblocks, const uint32_t *__restrict__ row_prefix, const uint32_t *__restrict__ bin_total)
 {
     constexpr int BINS = 1 << BITS;
+    constexpr int ITEMS = RP_ROUNDS * RP_THREADS;
     __shared__ uint32_t wh[RP_WARPS][BINS];
     __shared__ uint32_t bin_local[BINS];   // first slot of digit d inside the block's reordered chunk
     __shared__ uint32_t bin_global[BINS];  // global position of that slot
-    __shared__ uint32_t skeys[SORT_ITEMS_PER_BLOCK];
-    __shared__ uint32_t svals[SORT_ITEMS_PER_BLOCK];
+    __shared__ uint32_t skeys[ITEMS];
+    __shared__ uint32_t svals[ITEMS];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int d = threadIdx.x; d < RP_WARPS * BINS; d += RP_THREADS) (&wh[0][0])[d] = 0;
     const uint32_t mask = (uint32_t)BINS - 1;
     const uint32_t lt = (1u << lane) - 1u;
-    const int64_t bbase = (int64_t)blockIdx.x * SORT_ITEMS_PER_BLOCK;
+    const int64_t bbase = (int64_t)blockIdx.x * ITEMS;
     const int64_t wbase = bbase + (int64_t)w * (RP_ROUNDS * 32) + lane;
     uint32_t key[RP_ROUNDS], val[RP_ROUNDS], rank[RP_ROUNDS];
 #pragma unroll
@@ -247,7 +252,7 @@ radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
     }
     __syncthreads();
     // phase 4: coalesced write-out (each digit's run is contiguous both in shared and in global memory)
-    const int count = (int)min((int64_t)SORT_ITEMS_PER_BLOCK, n - bbase);
+    const int count = (int)min((int64_t)ITEMS, n - bbase);
 #pragma unroll 4
     for (int j = threadIdx.x; j < count; j += RP_THREADS) {
         const uint32_t k = skeys[j];
@@ -279,10 +284,11 @@ radix_rowscan_kernel(uint32_t *__restrict__ hist, int nblocks, uint32_t *__restr
 }
 
 template <int BITS>
-static void launch_scatter(const uint32_t *ki, const uint32_t *vi, uint32_t *ko, uint32_t *vo, int64_t n, int shift,
-                           int nblocks, const uint32_t *hist, const uint32_t *bin_total, cudaStream_t s)
+static void launch_scatter(int rounds, const uint32_t *ki, const uint32_t *vi, uint32_t *ko, uint32_t *vo, int64_t n,
+                           int shift, int nblocks, const uint32_t *hist, const uint32_t *bin_total, cudaStream_t s)
 {
-    radix_scatter_kernel<BITS><<<nblocks, RP_THREADS, 0, s>>>(ki, vi, ko, vo, n, shift, nblocks, hist, bin_total);
+    if (rounds == 4) radix_scatter_kernel<BITS, 4><<<nblocks, RP_THREADS, 0, s>>>(ki, vi, ko, vo, n, shift, nblocks, hist, bin_total);
+    else radix_scatter_kernel<BITS, 8><<<nblocks, RP_THREADS, 0, s>>>(ki, vi, ko, vo, n, shift, nblocks, hist, bin_total);
 }
 
 int radix_pass(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out, int64_t n,
@@ -292,19 +298,23 @@ int radix_pass(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_
     if (n <= 0) return 0;
     if (bits < 1 || bits > 8) { set_error("radix_pass: bits=%d unsupported", bits); return -8; }
     const int bins = 1 << bits;
-    const int nblocks = (int)((n + SORT_ITEMS_PER_BLOCK - 1) / SORT_ITEMS_PER_BLOCK);
+    // small inputs get 1024-item tiles: more blocks than resident slots (148 SMs x 3-4 CTAs)
+    const int rounds = n <= RADIX_SMALL_N ? 4 : 8;
+    const int items = rounds * RP_THREADS;
+    const int nblocks = (int)((n + items - 1) / items);
     uint32_t *bin_total = hist + (size_t)SORT_MAX_BINS * nblocks;  // 256 spare entries behind the table
-    radix_hist_kernel<<<nblocks, RP_THREADS, 0, s>>>(keys_in, n, shift, bins, nblocks, hist);
+    if (rounds == 4) radix_hist_kernel<4><<<nblocks, RP_THREADS, 0, s>>>(keys_in, n, shift, bins, nblocks, hist);
+    else radix_hist_kernel<8><<<nblocks, RP_THREADS, 0, s>>>(keys_in, n, shift, bins, nblocks, hist);
     radix_rowscan_kernel<<<bins, 256, 0, s>>>(hist, nblocks, bin_total);
     switch (bits) {
-    case 1: launch_scatter<1>(keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
-    case 2: launch_scatter<2>(keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
-    case 3: launch_scatter<3>(keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
-    case 4: launch_scatter<4>(keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
-    case 5: launch_scatter<5>(keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
-    case 6: launch_scatter<6>(keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
-    case 7: launch_scatter<7>(keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
-    default: launch_scatter<8>(keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
+    case 1: launch_scatter<1>(rounds, keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
+    case 2: launch_scatter<2>(rounds, keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
+    case 3: launch_scatter<3>(rounds, keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
+    case 4: launch_scatter<4>(rounds, keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
+    case 5: launch_scatter<5>(rounds, keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
+    case 6: launch_scatter<6>(rounds, keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
+    case 7: launch_scatter<7>(rounds, keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
+    default: launch_scatter<8>(rounds, keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
     }
     DMGS_CUDA(cudaGetLastError());
     count_launches(3);
