@@ -104,8 +104,13 @@ int dmgs_preprocess_forward(const dmgs_params *prm, const float *means3D, const 
     }
     if (!means3D || !opacities || !radii || !geom) { set_error("NULL required pointer"); return -6; }
     const GeomLayout L = geom_layout(P);
+    // with direct tile placement (place.cu) only the TOTAL of tiles-touched is needed: preprocess reduces
+    // it on the fly; the radix tile partition also needs the per-Gaussian offsets (scan below)
+    const int T = ((prm->image_width + DMGS_TILE - 1) / DMGS_TILE) * ((prm->image_height + DMGS_TILE - 1) / DMGS_TILE);
+    const bool placed = place_plan(P, T).ok != 0;
+    if (placed) DMGS_CUDA(cudaMemsetAsync(num_rendered, 0, sizeof(uint32_t), s));
     rc = launch_preprocess_fwd(prm, means3D, scales, rotations, cov3D_precomp, opacities, shs, colors_precomp, radii,
-                               geom, L, s);
+                               geom, L, placed ? num_rendered : nullptr, s);
     if (rc) return rc;
     if ((rc = check_stage(prm, s, "preprocess"))) return rc;
     // stable depth sort of the Gaussians: keys_a/order -> (4 passes) -> keys_a/order
@@ -118,6 +123,7 @@ int dmgs_preprocess_forward(const dmgs_params *prm, const float *means3D, const 
         if (rc) return rc;
     }
     if ((rc = check_stage(prm, s, "depth sort"))) return rc;
+    if (placed) return 0;
     rc = exclusive_scan_u32(at<uint32_t>(geom, L.tiles), va, at<uint32_t>(geom, L.offsets), P, num_rendered, tmp, s);
     if (rc) return rc;
     return check_stage(prm, s, "tile scan");
@@ -134,6 +140,20 @@ int dmgs_bin_forward(const dmgs_params *prm, const void *geom, int64_t R, void *
     if (!binning) { set_error("binning buffer is NULL"); return -6; }
     const GeomLayout GL = geom_layout(P);
     const BinLayout BL = bin_layout(P, R, W, H);
+    const PlacePlan pl = place_plan(P, T);
+    if (pl.ok) {
+        // direct placement from the depth-sorted Gaussian order (place.cu); ranges fall out of the scan
+        if (R > 0 && P > 0) {
+            rc = launch_tile_placement(pl, P, T, gx, at<uint32_t>(geom, GL.order), at<uint2>(geom, GL.rect),
+                                       at<uint4>(binning, BL.srec), at<uint32_t>(binning, BL.table),
+                                       at<uint32_t>(binning, BL.gsum), at<uint32_t>(binning, BL.tile_start),
+                                       at<uint2>(binning, BL.ranges), at<uint32_t>(binning, BL.gidx), s);
+            if (rc) return rc;
+        } else {
+            DMGS_CUDA(cudaMemsetAsync(at<uint2>(binning, BL.ranges), 0, sizeof(uint2) * (size_t)T, s));
+        }
+        return check_stage(prm, s, "tile placement");
+    }
     uint32_t *ta = at<uint32_t>(binning, BL.tiles), *tb = at<uint32_t>(binning, BL.tiles_b);
     uint32_t *ga = at<uint32_t>(binning, BL.gidx), *gb = at<uint32_t>(binning, BL.gidx_b);
     uint32_t *hist = at<uint32_t>(binning, BL.hist), *tmp = at<uint32_t>(binning, BL.scan_tmp);
@@ -265,6 +285,12 @@ int dmgs_sorted_keys(const void *geom, const void *binning, int32_t P, int64_t R
 {
     const GeomLayout GL = geom_layout(P);
     const BinLayout BL = bin_layout(P, R, W, H);
+    const int T = ((W + DMGS_TILE - 1) / DMGS_TILE) * ((H + DMGS_TILE - 1) / DMGS_TILE);
+    if (place_plan(P, T).ok && R > 0) {  // the placement path never materialises the sorted tile ids
+        int rc = launch_fill_tiles(T, at<uint2>(binning, BL.ranges), at<uint32_t>(const_cast<void *>(binning), BL.tiles),
+                                   (cudaStream_t)stream);
+        if (rc) return rc;
+    }
     return launch_sorted_keys(R, at<uint32_t>(binning, BL.tiles), at<uint32_t>(binning, BL.gidx),
                               at<float>(geom, GL.depths), keys_out, (cudaStream_t)stream);
 }

@@ -10,11 +10,15 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/dmgs_raster.h"
 
 #define DMGS_TILE 16
 #define DMGS_NEAR 0.2f
+#define DMGS_NUM_SMS 148        /* B200 */
+#define PLACE_MAX_GROUPS 256     /* row groups of the placement table scan */
+#define PLACE_MAX_TILES 16384   /* direct tile placement (place.cu) up to this many tiles, radix partition above */
 
 namespace dmgs {
 
@@ -43,9 +47,17 @@ struct GeomLayout {
 };
 struct BinLayout {
     size_t tiles, gidx, ranges;  // inspection arrays (final sorted list)
-    size_t tiles_b, gidx_b, hist, scan_tmp, total;
+    size_t tiles_b, gidx_b, hist, scan_tmp;  // radix tile partition (sort.cu)
+    size_t srec, table, gsum, tile_start;    // direct tile placement (place.cu)
+    size_t total;
     int sort_blocks;
 };
+// direct tile placement plan (place.cu): nseg depth-ordered segments of seg Gaussians, one per warp
+struct PlacePlan {
+    int ok, wpb, seg, nseg, groups, rows_per_group;
+    size_t smem;
+};
+PlacePlan place_plan(int32_t P, int T);
 struct ImgLayout {
     size_t final_T, n_contrib, total;
 };
@@ -83,19 +95,27 @@ static inline GeomLayout geom_layout(int32_t P)
 
 static inline BinLayout bin_layout(int32_t P, int64_t R, int32_t W, int32_t H)
 {
-    (void)P;
     BinLayout L;
+    memset(&L, 0, sizeof(L));
     size_t n = (size_t)(R > 0 ? R : 1), o = 0;
     size_t T = (size_t)((W + DMGS_TILE - 1) / DMGS_TILE) * ((H + DMGS_TILE - 1) / DMGS_TILE);
     L.tiles = o;   o += align_up(n * 4);
     L.gidx = o;    o += align_up(n * 4);
     L.ranges = o;  o += align_up(T * 8);
-    L.tiles_b = o; o += align_up(n * 4);
-    L.gidx_b = o;  o += align_up(n * 4);
-    L.sort_blocks = (int)((n + SORT_MIN_ITEMS_PER_BLOCK - 1) / SORT_MIN_ITEMS_PER_BLOCK);
-    size_t hist_n = (size_t)(L.sort_blocks + 1) * SORT_MAX_BINS + 1;  // table + bin totals
-    L.hist = o;    o += align_up(hist_n * 4);
-    L.scan_tmp = o; o += scan_tmp_bytes(hist_n);
+    const PlacePlan pl = place_plan(P, (int)T);
+    if (pl.ok) {
+        L.srec = o;       o += align_up((size_t)(P > 0 ? P : 1) * 16);
+        L.table = o;      o += align_up((size_t)pl.nseg * T * 4);
+        L.gsum = o;       o += align_up((size_t)pl.groups * T * 4);
+        L.tile_start = o; o += align_up(T * 4);
+    } else {
+        L.tiles_b = o; o += align_up(n * 4);
+        L.gidx_b = o;  o += align_up(n * 4);
+        L.sort_blocks = (int)((n + SORT_MIN_ITEMS_PER_BLOCK - 1) / SORT_MIN_ITEMS_PER_BLOCK);
+        size_t hist_n = (size_t)(L.sort_blocks + 1) * SORT_MAX_BINS + 1;  // table + bin totals
+        L.hist = o;    o += align_up(hist_n * 4);
+        L.scan_tmp = o; o += scan_tmp_bytes(hist_n);
+    }
     L.total = o;
     return L;
 }

@@ -9,7 +9,8 @@ DevParams make_dev_params(const dmgs_params *p);
 // preprocess.cu
 int launch_preprocess_fwd(const dmgs_params *prm, const float *means3D, const float *scales, const float *rotations,
                           const float *cov3D_precomp, const float *opacities, const float *shs,
-                          const float *colors_precomp, int32_t *radii, void *geom, const GeomLayout &L, cudaStream_t s);
+                          const float *colors_precomp, int32_t *radii, void *geom, const GeomLayout &L,
+                          uint32_t *total_instances, cudaStream_t s);
 int launch_preprocess_bwd(const dmgs_params *prm, const float *means3D, const float *scales, const float *rotations,
                           const float *cov3D_precomp, const float *shs, const int32_t *radii, const void *geom,
                           const GeomLayout &L, const float *grad_blend, float *dL_dmeans3D, float *dL_dmeans2D,
@@ -30,6 +31,12 @@ int launch_emit_instances(int P, const uint32_t *order, const uint32_t *offsets,
 int launch_tile_ranges(int64_t R, const uint32_t *sorted_tiles, uint2 *ranges, int T, cudaStream_t s);
 int launch_sorted_keys(int64_t R, const uint32_t *sorted_tiles, const uint32_t *sorted_gidx, const float *depths,
                        uint64_t *keys_out, cudaStream_t s);
+
+// place.cu
+int launch_tile_placement(const PlacePlan &pl, int P, int T, int gx, const uint32_t *order, const uint2 *rect,
+                          uint4 *srec, uint32_t *table, uint32_t *gsum, uint32_t *tile_start, uint2 *ranges,
+                          uint32_t *out_gidx, cudaStream_t s);
+int launch_fill_tiles(int T, const uint2 *ranges, uint32_t *sorted_tiles, cudaStream_t s);
 
 // blend.cu
 int launch_blend_fwd(const dmgs_params *prm, const void *geom, const GeomLayout &GL, const void *binning,

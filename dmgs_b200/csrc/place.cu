@@ -1,0 +1,292 @@
+// place.cu -- direct tile placement: the per-tile, depth-ordered Gaussian lists without moving
+// (tile, Gaussian) pairs through a radix sort.
+//
+// Replaces duplicateWithKeys + SortPairs(64-bit) + identifyTileRanges for images of
+// up to PLACE_MAX_TILES tiles; larger images use the radix tile partition in sort.cu.  Input is the
+// depth-sorted Gaussian order produced by dmgs_preprocess_forward (stable, ties in ascending index).
+//
+//   0  sorted_rect_kernel  packs every Gaussian's tile rectangle in depth order (16-byte records);
+//   A  tile_count_kernel   the depth-ordered Gaussians are cut into `nseg` contiguous segments, one
+//                          per warp; each warp counts the tiles its Gaussians touch in its own
+//                          shared-memory counters and writes one row of table[nseg][T];
+//   B  col_sum / group_scan / tile_scan / col_apply
+//                          column-wise exclusive scan of the table (two-level over row groups) and
+//                          the exclusive scan of the tile totals: table[s][t] becomes the position of
+//                          segment s's first entry in tile t's list, and ranges[t] falls out for free;
+//   C  tile_place_kernel   each warp re-walks its segment IN ORDER, one Gaussian per step with lanes
+//                          over the tiles of its rectangle (distinct tiles, so no conflicts), bumping
+//                          its shared-memory cursors and writing the Gaussian index to its final slot.
+//
+// Because segments are contiguous in depth order and a warp walks its segment sequentially, every
+// tile's list comes out in depth order with ties in ascending Gaussian index -- exactly the order a
+// stable sort of (tile << 32 | depth bits) keys produces (the parity tests rebuild those keys and
+// compare them bit for bit).  R-sized traffic is ONE 4-byte write per instance (plus the table),
+// against 48 B/instance for emission + two radix passes and 152 B/instance for a 64-bit sort.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace dmgs {
+
+PlacePlan place_plan(int32_t P, int T)
+{
+    PlacePlan p;
+    memset(&p, 0, sizeof(p));
+    const size_t per_warp = (size_t)T * 4;
+    if (T < 1 || T > PLACE_MAX_TILES) return p;
+    // test hook: DMGS_TILE_PARTITION=radix forces the radix tile partition (sort.cu) for any image size
+    const char *force = getenv("DMGS_TILE_PARTITION");
+    if (force && strcmp(force, "radix") == 0) return p;
+    const size_t budget = 200 * 1024;  // shared memory per SM left to the counters
+    int wps = (int)(budget / per_warp);
+    if (wps > 32) wps = 32;
+    if (wps < 2) return p;
+    p.wpb = wps >= 4 ? 4 : wps >= 2 ? 2 : 1;
+    const int nseg_max = DMGS_NUM_SMS * (wps / p.wpb) * p.wpb;
+    const int64_t n = P > 0 ? P : 1;
+    int seg = (int)((n + nseg_max - 1) / nseg_max);
+    if (seg < 64) seg = 64;
+    seg = (seg + 31) / 32 * 32;
+    p.seg = seg;
+    p.nseg = (int)((n + seg - 1) / seg);
+    p.groups = p.nseg < PLACE_MAX_GROUPS ? p.nseg : PLACE_MAX_GROUPS;
+    p.rows_per_group = (p.nseg + p.groups - 1) / p.groups;
+    p.groups = (p.nseg + p.rows_per_group - 1) / p.rows_per_group;
+    p.smem = (size_t)p.wpb * per_warp;
+    p.ok = 1;
+    return p;
+}
+
+// ------------------------------------------------------------------------------ depth-ordered rectangles
+// srec[s] = {x0 | x1 << 16, y0 | y1 << 16, ceil(2^32 / width), Gaussian index} of the s-th Gaussian in
+// depth order: the walkers below read ONE coalesced 16-byte record per Gaussian instead of chasing
+// order[s] -> rect[g] through two dependent gathers per 32-Gaussian batch.
+__global__ void __launch_bounds__(256)
+sorted_rect_kernel(int P, const uint32_t *__restrict__ order, const uint2 *__restrict__ rect, uint4 *__restrict__ srec)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P) return;
+    const uint32_t g = order[s];
+    const uint2 rc = rect[g];
+    const uint32_t wd = (rc.x >> 16) - (rc.x & 0xffff);
+    const uint32_t magic = wd > 1 ? (uint32_t)((0x100000000ull + wd - 1) / wd) : 0u;
+    srec[s] = make_uint4(rc.x, rc.y, magic, g);
+}
+
+// ------------------------------------------------------------------------------ A: count
+// lane <-> Gaussian; order is irrelevant for counting, so lanes add their rectangles with shared atomics
+__global__ void __launch_bounds__(128)
+tile_count_kernel(int P, int T, int gx, int seg, int nseg, const uint4 *__restrict__ srec, uint32_t *__restrict__ table)
+{
+    extern __shared__ uint32_t s_cnt[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int sg = blockIdx.x * wpb + w;
+    if (sg >= nseg) return;
+    uint32_t *cnt = s_cnt + (size_t)w * T;
+    for (int t = lane; t < T; t += 32) cnt[t] = 0;
+    __syncwarp();
+    const int s0 = sg * seg, s1 = min(P, s0 + seg);
+    uint4 nxt = s0 + lane < s1 ? srec[s0 + lane] : make_uint4(0, 0, 0, 0);
+    for (int sb = s0; sb < s1; sb += 32) {
+        const uint4 rc = nxt;
+        const int sn = sb + 32 + lane;
+        nxt = sn < s1 ? srec[sn] : make_uint4(0, 0, 0, 0);  // prefetch the next batch
+        const int x0 = rc.x & 0xffff, x1 = rc.x >> 16, y0 = rc.y & 0xffff, y1 = rc.y >> 16;
+        for (int y = y0; y < y1; ++y) {
+            uint32_t *rowp = cnt + y * gx;
+            for (int x = x0; x < x1; ++x) atomicAdd(rowp + x, 1u);
+        }
+    }
+    __syncwarp();
+    uint32_t *row = table + (size_t)sg * T;
+    for (int t = lane; t < T; t += 32) row[t] = cnt[t];
+}
+
+// ------------------------------------------------------------------------------ C: place
+// One Gaussian per step, in depth order; lanes <-> the tiles of its rectangle (all distinct, so the
+// read-modify-write of the cursors needs no atomics and keeps the order).
+__global__ void __launch_bounds__(128)
+tile_place_kernel(int P, int T, int gx, int seg, int nseg, const uint4 *__restrict__ srec,
+                  const uint32_t *__restrict__ table, uint32_t *__restrict__ out_gidx)
+{
+    extern __shared__ uint32_t s_cur[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int sg = blockIdx.x * wpb + w;
+    if (sg >= nseg) return;
+    uint32_t *cur = s_cur + (size_t)w * T;
+    const uint32_t *row = table + (size_t)sg * T;
+    for (int t = lane; t < T; t += 32) cur[t] = row[t];
+    __syncwarp();
+    const int s0 = sg * seg, s1 = min(P, s0 + seg);
+    uint4 nxt = s0 + lane < s1 ? srec[s0 + lane] : make_uint4(0, 0, 0, 0);
+    for (int sb = s0; sb < s1; sb += 32) {
+        // lane <-> Gaussian: 32 depth-ordered records at once; the next batch is already in flight
+        const uint4 rc = nxt;
+        const int sn = sb + 32 + lane;
+        nxt = sn < s1 ? srec[sn] : make_uint4(0, 0, 0, 0);
+        const uint32_t x0 = rc.x & 0xffff, y0 = rc.y & 0xffff, wd = (rc.x >> 16) - x0;
+        const uint32_t n = wd * ((rc.y >> 16) - y0), tb = y0 * (uint32_t)gx + x0;
+        uint32_t m = __ballot_sync(0xffffffffu, n != 0);
+        while (m) {
+            const int i = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t ni = __shfl_sync(0xffffffffu, n, i), wi = __shfl_sync(0xffffffffu, wd, i);
+            const uint32_t tbase = __shfl_sync(0xffffffffu, tb, i);
+            const uint32_t mg = __shfl_sync(0xffffffffu, rc.z, i), gi = __shfl_sync(0xffffffffu, rc.w, i);
+            for (uint32_t k = lane; k < ni; k += 32) {
+                const uint32_t q = mg ? __umulhi(k, mg) : k;  // k / width (exact for k < 2^18)
+                const uint32_t t = tbase + q * (uint32_t)gx + (k - q * wi);
+                const uint32_t slot = cur[t];
+                cur[t] = slot + 1;
+                out_gidx[slot] = gi;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ B: column scan
+// Two-level exclusive scan down the columns of table[nseg][T]: rows are cut into <= 256 groups.
+// gsum[g][t] = sum of the rows of group g in column t
+__global__ void __launch_bounds__(128)
+col_sum_kernel(int T, int nseg, int rows_per_group, const uint32_t *__restrict__ table, uint32_t *__restrict__ gsum)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, g = blockIdx.y;
+    if (t >= T) return;
+    const int r0 = g * rows_per_group, r1 = min(nseg, r0 + rows_per_group);
+    uint32_t s = 0;
+#pragma unroll 4
+    for (int r = r0; r < r1; ++r) s += table[(size_t)r * T + t];
+    gsum[(size_t)g * T + t] = s;
+}
+
+// one warp per tile: exclusive scan of the tile's group sums (in place) and the tile total
+__global__ void __launch_bounds__(256)
+group_scan_kernel(int T, int groups, uint32_t *__restrict__ gsum, uint32_t *__restrict__ tile_total)
+{
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (t >= T) return;
+    constexpr int PER = PLACE_MAX_GROUPS / 32;
+    uint32_t v[PER], sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int g = lane * PER + i;
+        v[i] = g < groups ? gsum[(size_t)g * T + t] : 0u;
+        sum += v[i];
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    uint32_t run = incl - sum;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int g = lane * PER + i;
+        if (g < groups) gsum[(size_t)g * T + t] = run;
+        run += v[i];
+    }
+    if (lane == 31) tile_total[t] = incl;
+}
+
+// one block: exclusive scan of the tile totals (in place -> tile_start) and the tile ranges
+// (empty tiles keep (0,0), as the reference's zero-initialised ranges do)
+__global__ void __launch_bounds__(1024)
+tile_scan_kernel(int T, uint32_t *__restrict__ tile_start, uint2 *__restrict__ ranges)
+{
+    __shared__ uint32_t warp_sums[32];
+    const int per = (T + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int t0 = threadIdx.x * per, t1 = min(T, t0 + per);
+    uint32_t local = 0;
+    for (int t = t0; t < t1; ++t) local += tile_start[t];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t incl = local;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) warp_sums[w] = incl;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int k = 0; k < w; ++k) base += warp_sums[k];
+    uint32_t run = base + incl - local;
+    for (int t = t0; t < t1; ++t) {
+        const uint32_t tot = tile_start[t];
+        tile_start[t] = run;
+        ranges[t] = tot ? make_uint2(run, run + tot) : make_uint2(0u, 0u);
+        run += tot;
+    }
+}
+
+// table[r][t] <- tile_start[t] + (entries of tile t in the rows before r)
+__global__ void __launch_bounds__(128)
+col_apply_kernel(int T, int nseg, int rows_per_group, const uint32_t *__restrict__ gsum,
+                 const uint32_t *__restrict__ tile_start, uint32_t *table)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, g = blockIdx.y;
+    if (t >= T) return;
+    uint32_t run = tile_start[t] + gsum[(size_t)g * T + t];
+    const int r0 = g * rows_per_group, r1 = min(nseg, r0 + rows_per_group);
+    // batches of 8 rows: all loads issued before the dependent prefix / stores
+    for (int r = r0; r < r1; r += 8) {
+        uint32_t c[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) c[k] = r + k < r1 ? table[(size_t)(r + k) * T + t] : 0u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (r + k < r1) table[(size_t)(r + k) * T + t] = run;
+            run += c[k];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ inspection helper
+// sorted tile ids rebuilt from the ranges (the placement path never materialises them)
+__global__ void fill_tiles_kernel(int T, const uint2 *__restrict__ ranges, uint32_t *__restrict__ sorted_tiles)
+{
+    const int t = blockIdx.x;
+    const uint2 r = ranges[t];
+    for (uint32_t j = r.x + threadIdx.x; j < r.y; j += blockDim.x) sorted_tiles[j] = (uint32_t)t;
+}
+
+int launch_fill_tiles(int T, const uint2 *ranges, uint32_t *sorted_tiles, cudaStream_t s)
+{
+    if (T <= 0) return 0;
+    fill_tiles_kernel<<<T, 128, 0, s>>>(T, ranges, sorted_tiles);
+    DMGS_CUDA(cudaGetLastError());
+    count_launches(1);
+    return 0;
+}
+
+int launch_tile_placement(const PlacePlan &pl, int P, int T, int gx, const uint32_t *order, const uint2 *rect,
+                          uint4 *srec, uint32_t *table, uint32_t *gsum, uint32_t *tile_start, uint2 *ranges,
+                          uint32_t *out_gidx, cudaStream_t s)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        DMGS_CUDA(cudaFuncSetAttribute(tile_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        DMGS_CUDA(cudaFuncSetAttribute(tile_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        // the plan counts on ~200 KB of shared memory per SM: ask for the largest carve-out
+        DMGS_CUDA(cudaFuncSetAttribute(tile_count_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        DMGS_CUDA(cudaFuncSetAttribute(tile_place_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        attr_set = true;
+    }
+    const int threads = pl.wpb * 32;
+    const int blocks = (pl.nseg + pl.wpb - 1) / pl.wpb;
+    const dim3 cgrid((T + 127) / 128, pl.groups);
+    sorted_rect_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, order, rect, srec);
+    tile_count_kernel<<<blocks, threads, pl.smem, s>>>(P, T, gx, pl.seg, pl.nseg, srec, table);
+    col_sum_kernel<<<cgrid, 128, 0, s>>>(T, pl.nseg, pl.rows_per_group, table, gsum);
+    group_scan_kernel<<<(T + 7) / 8, 256, 0, s>>>(T, pl.groups, gsum, tile_start);
+    tile_scan_kernel<<<1, 1024, 0, s>>>(T, tile_start, ranges);
+    col_apply_kernel<<<cgrid, 128, 0, s>>>(T, pl.nseg, pl.rows_per_group, gsum, tile_start, table);
+    tile_place_kernel<<<blocks, threads, pl.smem, s>>>(P, T, gx, pl.seg, pl.nseg, srec, table, out_gidx);
+    DMGS_CUDA(cudaGetLastError());
+    count_launches(7);
+    return 0;
+}
+
+}  // namespace dmgs

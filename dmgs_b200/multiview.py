@@ -118,3 +118,44 @@ def accumulate_view(settings, inputs: Dict[str, Optional[torch.Tensor]], image_g
     rasterize_backward(state, dL.contiguous(), inputs["means3D"], g("shs"), g("scales"), g("rotations"),
                        g("cov3D_precomp"), g("colors_precomp") is not None, accumulate_into=acc)
     return loss, color, radii
+
+
+class StagedInputs:
+    """Double-buffered host -> device staging of a step's inputs on a side stream.
+
+    `host` holds PINNED tensors.  `prefetch(slot)` enqueues the copy of all tensors into device buffer
+    set `slot` on the copy stream; `acquire(slot)` makes the compute stream wait for that copy and
+    returns the device tensors; `release(slot)` marks the buffers free once the compute stream has
+    consumed them.  With two slots the copy of step i+1 overlaps the kernels of step i (PCIe and the
+    SMs are independent engines), so a training loop whose inputs arrive from the host every step is
+    not serialised behind the H2D transfer."""
+
+    def __init__(self, host: Dict[str, torch.Tensor], device, slots: int = 2):
+        self.host = host
+        self.dev = [{k: torch.empty(v.shape, dtype=v.dtype, device=device) for k, v in host.items()} for _ in range(slots)]
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.ready: List[Optional[torch.cuda.Event]] = [None] * slots
+        self.freed: List[Optional[torch.cuda.Event]] = [None] * slots
+        self.bytes_per_step = sum(v.numel() * v.element_size() for v in host.values())
+
+    def prefetch(self, slot: int):
+        with torch.cuda.stream(self.copy_stream):
+            if self.freed[slot] is not None:
+                self.copy_stream.wait_event(self.freed[slot])
+            for k, v in self.host.items():
+                self.dev[slot][k].copy_(v, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+            self.ready[slot] = ev
+
+    def acquire(self, slot: int) -> Dict[str, torch.Tensor]:
+        if self.ready[slot] is None:
+            self.prefetch(slot)
+        torch.cuda.current_stream().wait_event(self.ready[slot])
+        return self.dev[slot]
+
+    def release(self, slot: int):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.freed[slot] = ev
+        self.ready[slot] = None

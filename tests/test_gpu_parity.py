@@ -92,6 +92,19 @@ def test_forward_parity_c1_100k():
     assert_forward_parity(ref, color, radii, st, arrays)
 
 
+def test_forward_parity_radix_tile_partition(monkeypatch):
+    """Images above PLACE_MAX_TILES tiles use the radix tile partition instead of direct placement;
+    DMGS_TILE_PARTITION=radix forces that path at any size."""
+    monkeypatch.setenv("DMGS_TILE_PARTITION", "radix")
+    cam, cl = small_scene(P=3000, W=200, H=136, scale=0.05)
+    for mode in ("sh_scale_rot", "precomp"):
+        _, _, ref, color, radii, st, arrays = run_both(cam, cl, mode)
+        assert_forward_parity(ref, color, radii, st, arrays)
+    cam, cl = small_scene(P=400, W=333, H=250, scale=0.5)
+    _, _, ref, color, radii, st, arrays = run_both(cam, cl, "sh_scale_rot")
+    assert_forward_parity(ref, color, radii, st, arrays)
+
+
 def test_forward_parity_big_splats_and_ties():
     # large Gaussians (rectangles of hundreds of tiles -> warp-cooperative emission) and exact
     # duplicates (same tile, bit-identical depth -> order must be ascending Gaussian index)
