@@ -1,0 +1,213 @@
+// blend_bwd.cu -- back-to-front adjoint of the per-tile alpha blend; see blend.cu for
+// the tile / warp-rectangle layout and the culling scheme, which are shared.
+//
+// This translation unit is compiled WITH floating-point contraction (-fmad=true): the backward is
+// held to 1e-4 relative (BASELINE.json), not to bit parity, so the gradient arithmetic may fuse.
+// Everything that decides WHICH entries contribute (power, exp, alpha and the two tests) is written
+// with explicit __fmul_rn / __fmaf_rn operations, which are never contracted, so the contributor set
+// is bit-identical to the forward's.
+#include "blend_common.cuh"
+
+namespace dmgs {
+
+// ------------------------------------------------------------------------------ backward
+// Transposed butterfly: N per-lane values -> N totals over the warp.  At every step a lane keeps
+// one half of its values and hands the other half to its partner, so the payload halves with the
+// distance: 5+3+2+1+1 = 12 shuffles for N = 9.  The total of slot `tr_slot9(lane)` ends in v[0].
+template <int N, int OFF>
+__device__ __forceinline__ void tr_reduce(float *v, int lane)
+{
+    if constexpr (N == 1) {
+#pragma unroll
+        for (int o = OFF; o > 0; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+    } else {
+        constexpr int LO = (N + 1) / 2;
+        const bool up = lane & OFF;
+#pragma unroll
+        for (int i = 0; i < LO; ++i) {
+            const float hi = (LO + i < N) ? v[LO + i] : 0.0f;
+            const float send = up ? v[i] : hi;
+            const float keepv = up ? hi : v[i];
+            v[i] = keepv + __shfl_xor_sync(0xffffffffu, send, OFF);
+        }
+        tr_reduce<LO, OFF / 2>(v, lane);
+    }
+}
+// slot whose total lands in this lane's v[0] after tr_reduce<9,16> (-1: a padding slot)
+__device__ __forceinline__ int tr_slot9(int lane)
+{
+    int n = 9, base = 0, cnt = 9;
+#pragma unroll
+    for (int off = 16; off >= 2; off >>= 1) {
+        const int lo = (n + 1) / 2;
+        if (lane & off) { base += lo; cnt -= lo; } else { cnt = min(cnt, lo); }
+        n = lo;
+    }
+    return cnt >= 1 ? base : -1;
+}
+
+__global__ void __launch_bounds__(BLK, BWD_MIN_BLOCKS)
+blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ ranges,
+                 const uint32_t *__restrict__ gidx, const float4 *__restrict__ rec, const float4 *__restrict__ rgb4,
+                 const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
+                 const float *__restrict__ dL_dpix, float *__restrict__ grad_blend)
+{
+    __shared__ float4 s_ra[BLK];
+    __shared__ float4 s_rb[BLK];
+    __shared__ float4 s_rgb[BLK];
+    __shared__ float4 s_acc[BLK * 3];  // per staged entry: the 9 (+3 pad) gradient sums of this tile
+    __shared__ uint32_t s_id[BLK];
+    __shared__ int s_max;
+
+    const int lane = threadIdx.x & 31;
+    int px0, py0;
+    warp_rect(px0, py0);
+    const int px = px0 + (lane & 7), py = py0 + (lane >> 3);
+    const bool inside = px < a.W && py < a.H;
+    const float pxf = (float)px, pyf = (float)py;
+    const float rx0 = (float)px0, rx1 = (float)(px0 + 7), ry0 = (float)py0, ry1 = (float)(py0 + 3);
+    const uint2 rng = ranges[blockIdx.y * a.gx + blockIdx.x];
+    const size_t pix = (size_t)py * a.W + px, HW = (size_t)a.H * a.W;
+
+    const float T_final = inside ? final_T[pix] : 0.0f;
+    const int last = inside ? (int)n_contrib[pix] : 0;
+    float dp0 = 0, dp1 = 0, dp2 = 0;
+    if (inside) { dp0 = dL_dpix[pix]; dp1 = dL_dpix[HW + pix]; dp2 = dL_dpix[2 * HW + pix]; }
+    const float bgT = -T_final * dot3(a.bg[0], dp0, a.bg[1], dp1, a.bg[2], dp2);
+    const float ddelx_dx = 0.5f * (float)a.W, ddely_dy = 0.5f * (float)a.H;
+    const int slot = tr_slot9(lane);
+    const bool owner = slot >= 0 && !(lane & 1);
+    const uint32_t a_ra = smem_addr(s_ra), a_rb = smem_addr(s_rb), a_rgb = smem_addr(s_rgb);
+    const uint32_t a_acc = smem_addr(s_acc) + 4u * (uint32_t)(slot < 0 ? 0 : slot);
+
+    // only the first max(n_contrib) entries of the list matter: per tile for staging, per warp for work
+    if (threadIdx.x == 0) s_max = 0;
+    s_acc[threadIdx.x] = make_float4(0, 0, 0, 0);
+    s_acc[BLK + threadIdx.x] = make_float4(0, 0, 0, 0);
+    s_acc[2 * BLK + threadIdx.x] = make_float4(0, 0, 0, 0);
+    __syncthreads();
+    const int wmax = __reduce_max_sync(0xffffffffu, last);
+    if (lane == 0) atomicMax(&s_max, wmax);
+    __syncthreads();
+    const int count = s_max;
+    if (count == 0) return;
+
+    float T = T_final, acc0 = 0, acc1 = 0, acc2 = 0, lc0 = 0, lc1 = 0, lc2 = 0, last_alpha = 0;
+    const int rounds = (count + BLK - 1) / BLK;
+    for (int r = rounds - 1; r >= 0; --r) {
+        const int idx = r * BLK + threadIdx.x;
+        if (idx < count) {
+            const uint32_t g = gidx[rng.x + idx];
+            s_id[threadIdx.x] = g;
+            s_ra[threadIdx.x] = rec[2 * (size_t)g];
+            s_rb[threadIdx.x] = rec[2 * (size_t)g + 1];
+            s_rgb[threadIdx.x] = rgb4[g];
+        }
+        __syncthreads();
+        if (r * BLK < wmax) {  // else nothing in this round is a contributor for this warp
+            const int nb = min(BLK, min(count, wmax) - r * BLK);
+            for (int s0 = ((nb - 1) / 32) * 32; s0 >= 0; s0 -= 32) {
+                const int e = s0 + lane;
+                bool keep = false;
+                if (e < nb) {
+                    const float4 ra = lds128(a_ra + 16u * e), rb = lds128(a_rb + 16u * e);
+                    keep = !cull_rect(ra.x, ra.y, ra.z, ra.w, rb.x, rb.z, rx0, rx1, ry0, ry1);
+                }
+                uint32_t m = __ballot_sync(0xffffffffu, keep);
+                while (m) {
+                    const int jb = 31 - __clz(m);  // back to front
+                    m &= ~(1u << jb);
+                    const int j = s0 + jb;
+                    const int pos = r * BLK + j;  // 0-based list position
+                    float v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                    bool hit = false;
+                    if (pos < last) {
+                        const float4 ra = lds128(a_ra + 16u * j), rb = lds128(a_rb + 16u * j);
+                        const float dx = ra.x - pxf, dy = ra.y - pyf;
+                        // same power / exp / alpha arithmetic as the forward (explicit _rn operations, immune
+                        // to contraction): the contributor set is identical
+                        const float q = fma_(__fmul_rn(rb.x, dy), dy, __fmul_rn(__fmul_rn(ra.z, dx), dx));
+                        const float power = fma_(-__fmul_rn(ra.w, dx), dy, __fmul_rn(-0.5f, q));
+                        if (power <= 0.0f) {
+                            const float G = dmgs_exp(power);
+                            const float alpha = fminf(0.99f, __fmul_rn(rb.y, G));
+                            if (alpha >= 1.0f / 255.0f) {
+                                hit = true;
+                                // one refined reciprocal replaces two IEEE divisions by (1 - alpha) (no FCHK /
+                                // slow-path branches; operands are in [0.01, 1] so no special cases exist)
+                                const float oma = 1.0f - alpha;
+                                const float inv = rcp_nr(oma);
+                                const float t0 = T * inv;  // T / (1 - alpha), residual-corrected: the error must
+                                T = fma_(fma_(-t0, oma, T), inv, t0);  // not accumulate along the list
+                                const float w = alpha * T;
+                                const float4 c = lds128(a_rgb + 16u * j);
+                                const float om = 1.0f - last_alpha;
+                                acc0 = fma_(last_alpha, lc0, om * acc0);
+                                acc1 = fma_(last_alpha, lc1, om * acc1);
+                                acc2 = fma_(last_alpha, lc2, om * acc2);
+                                lc0 = c.x; lc1 = c.y; lc2 = c.z;
+                                float dL_dalpha = (c.x - acc0) * dp0;
+                                dL_dalpha = fma_(c.y - acc1, dp1, dL_dalpha);
+                                dL_dalpha = fma_(c.z - acc2, dp2, dL_dalpha);
+                                v[6] = w * dp0; v[7] = w * dp1; v[8] = w * dp2;
+                                last_alpha = alpha;
+                                dL_dalpha = fma_(bgT, inv, dL_dalpha * T);
+                                const float dL_dG = rb.y * dL_dalpha;
+                                const float gdx = G * dx, gdy = G * dy;
+                                const float dG_ddelx = fma_(-gdy, ra.w, -gdx * ra.z);
+                                const float dG_ddely = fma_(-gdx, ra.w, -gdy * rb.x);
+                                const float hg = -0.5f * dL_dG;
+                                v[0] = (dL_dG * dG_ddelx) * ddelx_dx;
+                                v[1] = (dL_dG * dG_ddely) * ddely_dy;
+                                v[2] = (hg * gdx) * dx;
+                                v[3] = (hg * gdx) * dy;
+                                v[4] = (hg * gdy) * dy;
+                                v[5] = G * dL_dalpha;
+                            }
+                        }
+                    }
+                    if (!__any_sync(0xffffffffu, hit)) continue;
+                    tr_reduce<9, 16>(v, lane);
+                    if (owner) reds_add(a_acc + 48u * j, v[0]);
+                }
+            }
+        }
+        __syncthreads();
+        // flush the round's tile-level sums: three 16-byte vector reductions per touched Gaussian
+        if (idx < count) {
+            const float4 g0 = s_acc[3 * threadIdx.x], g1 = s_acc[3 * threadIdx.x + 1], g2 = s_acc[3 * threadIdx.x + 2];
+            const bool nz = g0.x != 0.0f || g0.y != 0.0f || g0.z != 0.0f || g0.w != 0.0f || g1.x != 0.0f || g1.y != 0.0f ||
+                            g1.z != 0.0f || g1.w != 0.0f || g2.x != 0.0f;
+            if (nz) {
+                float *dst = grad_blend + 12 * (size_t)s_id[threadIdx.x];
+                red_global_v4(dst, g0);
+                red_global_v4(dst + 4, g1);
+                red_global_v4(dst + 8, g2);
+                s_acc[3 * threadIdx.x] = make_float4(0, 0, 0, 0);
+                s_acc[3 * threadIdx.x + 1] = make_float4(0, 0, 0, 0);
+                s_acc[3 * threadIdx.x + 2] = make_float4(0, 0, 0, 0);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+int launch_blend_bwd(const dmgs_params *prm, const void *geom, const GeomLayout &GL, const void *binning,
+                     const BinLayout &BL, const void *image, const ImgLayout &IL, const float *dL_dpix,
+                     float *grad_blend, cudaStream_t s)
+{
+    BlendArgs a;
+    a.W = prm->image_width; a.H = prm->image_height;
+    a.gx = (a.W + DMGS_TILE - 1) / DMGS_TILE; a.gy = (a.H + DMGS_TILE - 1) / DMGS_TILE;
+    for (int i = 0; i < 3; ++i) a.bg[i] = prm->bg[i];
+    if (a.W <= 0 || a.H <= 0) return 0;
+    blend_bwd_kernel<<<dim3(a.gx, a.gy), BLK, 0, s>>>(a, at<uint2>(binning, BL.ranges), at<uint32_t>(binning, BL.gidx),
+                                                      at<float4>(geom, GL.rec), at<float4>(geom, GL.rgb),
+                                                      at<float>(image, IL.final_T), at<uint32_t>(image, IL.n_contrib),
+                                                      dL_dpix, grad_blend);
+    DMGS_CUDA(cudaGetLastError());
+    count_launches(1);
+    return 0;
+}
+
+}  // namespace dmgs

@@ -152,10 +152,11 @@ __device__ __forceinline__ float affine3(const float *m, int r, float x, float y
 // exp(x): clamp to [-80, 80], Cody-Waite reduction by ln2, degree-6 Horner, exponent insert.
 __device__ __forceinline__ float dmgs_exp(float x)
 {
+    // explicit _rn operations: never contracted, whatever -fmad says for the translation unit
     x = fminf(fmaxf(x, -80.0f), 80.0f);
-    const float t = x * 1.44269502162933349609375f;
-    const float r = t + 12582912.0f;
-    const float jf = r - 12582912.0f;
+    const float t = __fmul_rn(x, 1.44269502162933349609375f);
+    const float r = __fadd_rn(t, 12582912.0f);
+    const float jf = __fadd_rn(r, -12582912.0f);
     const int j = __float_as_int(r) - 0x4B400000;
     float f = fma_(jf, -0.693145751953125f, x);
     f = fma_(jf, -1.42860682030941723212e-6f, f);

@@ -215,19 +215,40 @@ preprocess_fwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
         if (colors_precomp) {
             col = make_float4(colors_precomp[3 * i], colors_precomp[3 * i + 1], colors_precomp[3 * i + 2], 0.0f);
         } else {
-            float r[SHMODE ? SH_ROW_FLOATS : 1];
-            if (SHMODE) stage.read(r);
             const float dx = x - pr.cam[0], dy = y - pr.cam[1], dz = z - pr.cam[2];
             const float len = sqrtf(dot3(dx, dx, dy, dy, dz, dz));
             float bas[16];
             const int nb = sh_basis(pr.sh_degree, dx / len, dy / len, dz / len, bas);
-            float v[3];
+            float v[3] = {0.0f, 0.0f, 0.0f};
+            if (SHMODE) {
+                // stream the staged row (12 x LDS.128); per channel the terms arrive in increasing k,
+                // the accumulation order of the arithmetic contract
+                const float4 *row4 = reinterpret_cast<const float4 *>(stage.row);
+#pragma unroll
+                for (int j = 0; j < SH_ROW_FLOATS / 4; ++j) {
+                    const float4 q4 = row4[j];
+                    const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int f = 4 * j + c;
+                        const int k = SHMODE == 1 ? f / 3 : f % 16, ch = SHMODE == 1 ? f % 3 : f / 16;
+                        if (k == 0) v[ch] = bas[0] * qv[c];
+                        else if (k < nb) v[ch] = fma_(bas[k], qv[c], v[ch]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    float acc = bas[0] * sh_get<0>(shs, pr, nullptr, i, 0, ch);
+#pragma unroll
+                    for (int k = 1; k < 16; ++k)
+                        if (k < nb) acc = fma_(bas[k], sh_get<0>(shs, pr, nullptr, i, k, ch), acc);
+                    v[ch] = acc;
+                }
+            }
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-                float acc = bas[0] * sh_get<SHMODE>(shs, pr, r, i, 0, ch);
-#pragma unroll
-                for (int k = 1; k < 16; ++k)
-                    if (k < nb) acc = fma_(bas[k], sh_get<SHMODE>(shs, pr, r, i, k, ch), acc);
+                float acc = v[ch];
                 if (pr.sh_act == 0) {
                     acc = acc + 0.5f;
                     if (acc < 0.0f) clampbits |= (uint8_t)(1u << ch);
@@ -303,7 +324,7 @@ int launch_preprocess_fwd(const dmgs_params *prm, const float *means3D, const fl
 // grad_blend: per Gaussian 12 floats {dmean2D.x, dmean2D.y, dconic.a, dconic.b(half), dconic.c,
 // dopacity, dcolor.r, dcolor.g, dcolor.b, pad x3} accumulated by the blend backward.
 template <int SHMODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restrict__ means3D, const float *__restrict__ scales,
                       const float *__restrict__ rotations, const float *__restrict__ cov3D_precomp,
                       const float *__restrict__ shs, const int32_t *__restrict__ radii,
@@ -417,13 +438,7 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
     // ---- SH backward: dL/dsh rows and the view-direction term of dL/dmean
     if (SHMODE) stage.wait();  // warp-uniform
     if (do_sh) {
-        float r[SHMODE ? SH_ROW_FLOATS : 1];
-        if (SHMODE) {
-#pragma unroll
-            for (int k = 0; k < SH_ROW_FLOATS; ++k) r[k] = 0.0f;
-        }
         if (vis) {
-            if (SHMODE) stage.read(r);
             const float ox = x - pr.cam[0], oy = y - pr.cam[1], oz = z - pr.cam[2];
             const float s2 = dot3(ox, ox, oy, oy, oz, oz);
             const float len = sqrtf(s2);
@@ -433,72 +448,90 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
             const uint8_t cb = clamped[i];
             const float4 rgbv = rgb4[i];
             const float sg[3] = {rgbv.x, rgbv.y, rgbv.z};
-            float ddx = 0, ddy = 0, ddz = 0;
-            const float xx = dxn * dxn, yy = dyn * dyn, zz = dzn * dzn, xy_ = dxn * dyn, yz = dyn * dzn, xz = dxn * dzn;
+            float g[3];
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-                float g = dcol[ch];
-                if (pr.sh_act == 0) g = (cb >> ch) & 1 ? 0.0f : g;
-                else g = g * (sg[ch] * (1.0f - sg[ch]));
-                float sv[16];
+                if (pr.sh_act == 0) g[ch] = (cb >> ch) & 1 ? 0.0f : dcol[ch];
+                else g[ch] = dcol[ch] * (sg[ch] * (1.0f - sg[ch]));
+            }
+            // h[k] = sum_ch sh[k][ch] * g[ch]: the view-direction gradient is linear in it, so the basis
+            // Jacobian below is applied once instead of once per channel
+            float h[16];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    if (SHMODE) {
-                        const int ri = SHMODE == 1 ? k * 3 + ch : ch * 16 + k;
-                        sv[k] = k < nb ? r[ri] : 0.0f;
-                        r[ri] = k < nb ? bas[k] * g : 0.0f;
-                    } else {
+            for (int k = 0; k < 16; ++k) h[k] = 0.0f;
+            if (SHMODE) {
+                // stream the staged row in place: read 4 coefficients, write their 4 gradients back
+                float4 *row4 = reinterpret_cast<float4 *>(stage.row);
+#pragma unroll
+                for (int j = 0; j < SH_ROW_FLOATS / 4; ++j) {
+                    const float4 q4 = row4[j];
+                    const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
+                    float ov[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int f = 4 * j + c;
+                        const int k = SHMODE == 1 ? f / 3 : f % 16, ch = SHMODE == 1 ? f % 3 : f / 16;
+                        const bool on = k < nb;
+                        h[k] = on ? fma_(qv[c], g[ch], h[k]) : h[k];
+                        ov[c] = on ? bas[k] * g[ch] : 0.0f;
+                    }
+                    row4[j] = make_float4(ov[0], ov[1], ov[2], ov[3]);
+                }
+            } else {
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
                         const size_t idx = pr.sh_layout == 0 ? ((size_t)i * M + k) * 3 + ch : ((size_t)i * 3 + ch) * M + k;
                         if (k < nb) {
-                            sv[k] = __ldg(shs + idx);
-                            dL_dshs[idx] = accumulate ? dL_dshs[idx] + bas[k] * g : bas[k] * g;
-                        } else {
-                            sv[k] = 0.0f;
-                            if (k < M && !accumulate) dL_dshs[idx] = 0.0f;
+                            h[k] = fma_(__ldg(shs + idx), g[ch], h[k]);
+                            dL_dshs[idx] = accumulate ? dL_dshs[idx] + bas[k] * g[ch] : bas[k] * g[ch];
+                        } else if (k < M && !accumulate) {
+                            dL_dshs[idx] = 0.0f;
                         }
                     }
-                }
-                if (!SHMODE) {
                     for (int k = 16; k < M && !accumulate; ++k) {
                         const size_t idx = pr.sh_layout == 0 ? ((size_t)i * M + k) * 3 + ch : ((size_t)i * 3 + ch) * M + k;
                         dL_dshs[idx] = 0.0f;
                     }
                 }
-                if (pr.sh_degree > 0) {
-                    float gx_ = -SH_C1 * sv[3], gy_ = -SH_C1 * sv[1], gz_ = SH_C1 * sv[2];
-                    if (pr.sh_degree > 1) {
-                        gx_ += SH_C2_0 * dyn * sv[4] + SH_C2_2 * 2.0f * -dxn * sv[6] + SH_C2_3 * dzn * sv[7] + SH_C2_4 * 2.0f * dxn * sv[8];
-                        gy_ += SH_C2_0 * dxn * sv[4] + SH_C2_1 * dzn * sv[5] + SH_C2_2 * 2.0f * -dyn * sv[6] + SH_C2_4 * 2.0f * -dyn * sv[8];
-                        gz_ += SH_C2_1 * dyn * sv[5] + SH_C2_2 * 2.0f * 2.0f * dzn * sv[6] + SH_C2_3 * dxn * sv[7];
-                        if (pr.sh_degree > 2) {
-                            gx_ += SH_C3_0 * sv[9] * 3.0f * 2.0f * xy_ + SH_C3_1 * sv[10] * yz + SH_C3_2 * sv[11] * -2.0f * xy_ +
-                                   SH_C3_3 * sv[12] * -3.0f * 2.0f * xz + SH_C3_4 * sv[13] * (-3.0f * xx + 4.0f * zz - yy) +
-                                   SH_C3_5 * sv[14] * 2.0f * xz + SH_C3_6 * sv[15] * 3.0f * (xx - yy);
-                            gy_ += SH_C3_0 * sv[9] * 3.0f * (xx - yy) + SH_C3_1 * sv[10] * xz +
-                                   SH_C3_2 * sv[11] * (-3.0f * yy + 4.0f * zz - xx) + SH_C3_3 * sv[12] * -3.0f * 2.0f * yz +
-                                   SH_C3_4 * sv[13] * -2.0f * xy_ + SH_C3_5 * sv[14] * -2.0f * yz + SH_C3_6 * sv[15] * -3.0f * 2.0f * xy_;
-                            gz_ += SH_C3_1 * sv[10] * xy_ + SH_C3_2 * sv[11] * 4.0f * 2.0f * yz +
-                                   SH_C3_3 * sv[12] * 3.0f * (2.0f * zz - xx - yy) + SH_C3_4 * sv[13] * 4.0f * 2.0f * xz +
-                                   SH_C3_5 * sv[14] * (xx - yy);
-                        }
-                    }
-                    ddx = fma_(gx_, g, ddx);
-                    ddy = fma_(gy_, g, ddy);
-                    ddz = fma_(gz_, g, ddz);
-                }
             }
             if (pr.sh_degree > 0) {
+                const float xx = dxn * dxn, yy = dyn * dyn, zz = dzn * dzn, xy_ = dxn * dyn, yz = dyn * dzn, xz = dxn * dzn;
+                float ddx = -SH_C1 * h[3], ddy = -SH_C1 * h[1], ddz = SH_C1 * h[2];
+                if (pr.sh_degree > 1) {
+                    ddx += SH_C2_0 * dyn * h[4] + SH_C2_2 * 2.0f * -dxn * h[6] + SH_C2_3 * dzn * h[7] + SH_C2_4 * 2.0f * dxn * h[8];
+                    ddy += SH_C2_0 * dxn * h[4] + SH_C2_1 * dzn * h[5] + SH_C2_2 * 2.0f * -dyn * h[6] + SH_C2_4 * 2.0f * -dyn * h[8];
+                    ddz += SH_C2_1 * dyn * h[5] + SH_C2_2 * 2.0f * 2.0f * dzn * h[6] + SH_C2_3 * dxn * h[7];
+                    if (pr.sh_degree > 2) {
+                        ddx += SH_C3_0 * h[9] * 3.0f * 2.0f * xy_ + SH_C3_1 * h[10] * yz + SH_C3_2 * h[11] * -2.0f * xy_ +
+                               SH_C3_3 * h[12] * -3.0f * 2.0f * xz + SH_C3_4 * h[13] * (-3.0f * xx + 4.0f * zz - yy) +
+                               SH_C3_5 * h[14] * 2.0f * xz + SH_C3_6 * h[15] * 3.0f * (xx - yy);
+                        ddy += SH_C3_0 * h[9] * 3.0f * (xx - yy) + SH_C3_1 * h[10] * xz +
+                               SH_C3_2 * h[11] * (-3.0f * yy + 4.0f * zz - xx) + SH_C3_3 * h[12] * -3.0f * 2.0f * yz +
+                               SH_C3_4 * h[13] * -2.0f * xy_ + SH_C3_5 * h[14] * -2.0f * yz + SH_C3_6 * h[15] * -3.0f * 2.0f * xy_;
+                        ddz += SH_C3_1 * h[10] * xy_ + SH_C3_2 * h[11] * 4.0f * 2.0f * yz +
+                               SH_C3_3 * h[12] * 3.0f * (2.0f * zz - xx - yy) + SH_C3_4 * h[13] * 4.0f * 2.0f * xz +
+                               SH_C3_5 * h[14] * (xx - yy);
+                    }
+                }
                 const float inv3 = 1.0f / sqrtf(s2 * s2 * s2);
                 gm[0] += ((s2 - ox * ox) * ddx - oy * ox * ddy - oz * ox * ddz) * inv3;
                 gm[1] += (-ox * oy * ddx + (s2 - oy * oy) * ddy - oz * oy * ddz) * inv3;
                 gm[2] += (-ox * oz * ddx - oy * oz * ddy + (s2 - oz * oz) * ddz) * inv3;
             }
-        } else if (!SHMODE && inb && !accumulate) {
-            for (int k = 0; k < 3 * M; ++k) dL_dshs[(size_t)i * 3 * M + k] = 0.0f;
+        } else if (inb && !accumulate) {
+            if (SHMODE) {  // culled Gaussian: a row of zeros
+                float4 *row4 = reinterpret_cast<float4 *>(stage.row);
+#pragma unroll
+                for (int j = 0; j < SH_ROW_FLOATS / 4; ++j) row4[j] = make_float4(0, 0, 0, 0);
+            } else {
+                for (int k = 0; k < 3 * M; ++k) dL_dshs[(size_t)i * 3 * M + k] = 0.0f;
+            }
         }
         if (SHMODE) {
             // store: every in-range row (zeros for culled Gaussians); accumulate: only rows with a gradient
-            if (inb && (vis || !accumulate)) stage.write_out(r, dL_dshs + (size_t)i * SH_ROW_FLOATS, accumulate != 0);
+            if (inb && (vis || !accumulate)) stage.flush_row(dL_dshs + (size_t)i * SH_ROW_FLOATS, accumulate != 0);
         }
     }
 

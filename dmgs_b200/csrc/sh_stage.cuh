@@ -105,6 +105,14 @@ struct ShStage {
         else bulk_store(dst, smem_u32(row), SH_ROW_BYTES);
         bulk_commit();
     }
+    // same, for a row that was already built in place in shared memory
+    __device__ __forceinline__ void flush_row(float *dst, bool accumulate)
+    {
+        fence_proxy_async();
+        if (accumulate) bulk_reduce_add_f32(dst, smem_u32(row), SH_ROW_BYTES);
+        else bulk_store(dst, smem_u32(row), SH_ROW_BYTES);
+        bulk_commit();
+    }
     __device__ __forceinline__ void flush() { bulk_wait_read_all(); }
 };
 
