@@ -108,18 +108,23 @@ int dmgs_preprocess_forward(const dmgs_params *prm, const float *means3D, const 
     // it on the fly; the radix tile partition also needs the per-Gaussian offsets (scan below)
     const int T = ((prm->image_width + DMGS_TILE - 1) / DMGS_TILE) * ((prm->image_height + DMGS_TILE - 1) / DMGS_TILE);
     const bool placed = place_plan(P, T).ok != 0;
-    if (placed) DMGS_CUDA(cudaMemsetAsync(num_rendered, 0, sizeof(uint32_t), s));
+    uint32_t *stat = placed ? at<uint32_t>(geom, L.stat) : nullptr;
+    if (placed) {
+        DMGS_CUDA(cudaMemsetAsync(num_rendered, 0, sizeof(uint32_t), s));
+        DMGS_CUDA(cudaMemsetAsync(stat, 0, 16, s));
+    }
     rc = launch_preprocess_fwd(prm, means3D, scales, rotations, cov3D_precomp, opacities, shs, colors_precomp, radii,
-                               geom, L, placed ? num_rendered : nullptr, s);
+                               geom, L, placed ? num_rendered : nullptr, stat, s);
     if (rc) return rc;
     if ((rc = check_stage(prm, s, "preprocess"))) return rc;
-    // stable depth sort of the Gaussians: keys_a/order -> (4 passes) -> keys_a/order
+    // stable depth sort of the Gaussians: 8-bit LSD passes over (keys_a, order) <-> (keys_b, vals_b).
+    // On the placement path the passes are adaptive (digits in which no two live keys differ are
+    // skipped on the device, typically the top byte); otherwise all four run and the result is in A.
     uint32_t *ka = at<uint32_t>(geom, L.keys_a), *kb = at<uint32_t>(geom, L.keys_b);
     uint32_t *va = at<uint32_t>(geom, L.order), *vb = at<uint32_t>(geom, L.vals_b);
     uint32_t *hist = at<uint32_t>(geom, L.hist), *tmp = at<uint32_t>(geom, L.scan_tmp);
     for (int pass = 0; pass < 4; ++pass) {
-        rc = (pass & 1) ? radix_pass(kb, vb, ka, va, P, 8 * pass, 8, hist, tmp, s)
-                        : radix_pass(ka, va, kb, vb, P, 8 * pass, 8, hist, tmp, s);
+        rc = radix_pass(ka, va, kb, vb, P, pass, 8 * pass, 8, hist, stat, s);
         if (rc) return rc;
     }
     if ((rc = check_stage(prm, s, "depth sort"))) return rc;
@@ -144,7 +149,8 @@ int dmgs_bin_forward(const dmgs_params *prm, const void *geom, int64_t R, void *
     if (pl.ok) {
         // direct placement from the depth-sorted Gaussian order (place.cu); ranges fall out of the scan
         if (R > 0 && P > 0) {
-            rc = launch_tile_placement(pl, P, T, gx, at<uint32_t>(geom, GL.order), at<uint2>(geom, GL.rect),
+            rc = launch_tile_placement(pl, P, T, gx, at<uint32_t>(geom, GL.order), at<uint32_t>(geom, GL.vals_b),
+                                       at<uint32_t>(geom, GL.stat), at<uint2>(geom, GL.rect),
                                        at<uint4>(binning, BL.srec), at<uint32_t>(binning, BL.table),
                                        at<uint32_t>(binning, BL.gsum), at<uint32_t>(binning, BL.tile_start),
                                        at<uint2>(binning, BL.ranges), at<uint32_t>(binning, BL.gidx), s);
@@ -168,14 +174,13 @@ int dmgs_bin_forward(const dmgs_params *prm, const void *geom, int64_t R, void *
                                    at<uint32_t>(geom, GL.tiles), at<uint2>(geom, GL.rect), gx, ek, ev, s);
         if (rc) return rc;
         if ((rc = check_stage(prm, s, "emit instances"))) return rc;
-        uint32_t *ck = ek, *cv = ev;
+        // pass p reads A when p is even: make A the buffer the instances were emitted into
+        uint32_t *A_k = ek, *A_v = ev, *B_k = (ek == ta) ? tb : ta, *B_v = (ev == ga) ? gb : ga;
         int shift = 0;
         for (int pass = 0; pass < npass; ++pass) {
-            uint32_t *ok = (ck == ta) ? tb : ta, *ov = (cv == ga) ? gb : ga;
-            rc = radix_pass(ck, cv, ok, ov, R, shift, nbits[pass], hist, tmp, s);
+            rc = radix_pass(A_k, A_v, B_k, B_v, R, pass, shift, nbits[pass], hist, nullptr, s);
             if (rc) return rc;
             shift += nbits[pass];
-            ck = ok; cv = ov;
         }
         if ((rc = check_stage(prm, s, "tile partition"))) return rc;
     }

@@ -42,7 +42,7 @@ static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a
 
 struct GeomLayout {
     size_t depths, rec, rgb, clamped, cov3D, tiles, rect, order, offsets;  // inspection arrays
-    size_t keys_a, keys_b, vals_b, hist, scan_tmp, total;
+    size_t keys_a, keys_b, vals_b, hist, scan_tmp, stat, total;
     int sort_blocks;
 };
 struct BinLayout {
@@ -89,6 +89,7 @@ static inline GeomLayout geom_layout(int32_t P)
     L.hist = o;    o += align_up(hist_n * 4);
     size_t big = hist_n > n ? hist_n : n;
     L.scan_tmp = o; o += scan_tmp_bytes(big);
+    L.stat = o;    o += 256;  // {max of ~key, max of key over the live depth keys, -, -}
     L.total = o;
     return L;
 }

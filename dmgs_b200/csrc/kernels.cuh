@@ -10,7 +10,7 @@ DevParams make_dev_params(const dmgs_params *p);
 int launch_preprocess_fwd(const dmgs_params *prm, const float *means3D, const float *scales, const float *rotations,
                           const float *cov3D_precomp, const float *opacities, const float *shs,
                           const float *colors_precomp, int32_t *radii, void *geom, const GeomLayout &L,
-                          uint32_t *total_instances, cudaStream_t s);
+                          uint32_t *total_instances, uint32_t *key_stat, cudaStream_t s);
 int launch_preprocess_bwd(const dmgs_params *prm, const float *means3D, const float *scales, const float *rotations,
                           const float *cov3D_precomp, const float *shs, const int32_t *radii, const void *geom,
                           const GeomLayout &L, const float *grad_blend, float *dL_dmeans3D, float *dL_dmeans2D,
@@ -20,9 +20,11 @@ int launch_mark_visible(int P, const float *means3D, const float *view_dev, uint
 int launch_exp_array(const float *x, float *y, int64_t n, cudaStream_t s);
 
 // sort.cu
-// Stable LSD radix pass over (key,value) pairs on `bits` bits starting at `shift`.
-int radix_pass(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out, int64_t n,
-               int shift, int bits, uint32_t *hist, uint32_t *scan_tmp, cudaStream_t s);
+// Stable LSD radix pass number `pass` over (key,value) pairs on `bits` bits starting at `shift`; buffers
+// alternate A -> B -> A ...  `stat` (device, optional): {OR of keys, OR of ~keys} enables the adaptive
+// depth sort that skips digits which do not vary (sort.cu).
+int radix_pass(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b, int64_t n, int pass, int shift,
+               int bits, uint32_t *hist, const uint32_t *stat, cudaStream_t s);
 // out[i] = sum_{j<i} in[gather ? gather[j] : j]; *total = sum of all (may be NULL)
 int exclusive_scan_u32(const uint32_t *in, const uint32_t *gather, uint32_t *out, int64_t n, uint32_t *total,
                        uint32_t *scan_tmp, cudaStream_t s);
@@ -33,7 +35,8 @@ int launch_sorted_keys(int64_t R, const uint32_t *sorted_tiles, const uint32_t *
                        uint64_t *keys_out, cudaStream_t s);
 
 // place.cu
-int launch_tile_placement(const PlacePlan &pl, int P, int T, int gx, const uint32_t *order, const uint2 *rect,
+int launch_tile_placement(const PlacePlan &pl, int P, int T, int gx, const uint32_t *order_a, const uint32_t *order_b,
+                          const uint32_t *stat, const uint2 *rect,
                           uint4 *srec, uint32_t *table, uint32_t *gsum, uint32_t *tile_start, uint2 *ranges,
                           uint32_t *out_gidx, cudaStream_t s);
 int launch_fill_tiles(int T, const uint2 *ranges, uint32_t *sorted_tiles, cudaStream_t s);

@@ -63,11 +63,18 @@ PlacePlan place_plan(int32_t P, int T)
 // depth order: the walkers below read ONE coalesced 16-byte record per Gaussian instead of chasing
 // order[s] -> rect[g] through two dependent gathers per 32-Gaussian batch.
 __global__ void __launch_bounds__(256)
-sorted_rect_kernel(int P, const uint32_t *__restrict__ order, const uint2 *__restrict__ rect, uint4 *__restrict__ srec)
+sorted_rect_kernel(int P, const uint32_t *__restrict__ order_a, const uint32_t *__restrict__ order_b,
+                   const uint32_t *__restrict__ stat, const uint2 *__restrict__ rect, uint4 *__restrict__ srec)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= P) return;
-    const uint32_t g = order[s];
+    // the adaptive depth sort leaves its result in A or B depending on how many passes ran
+    const uint32_t kmin = ~stat[0], kmax = stat[1];
+    const uint32_t range = kmax >= kmin ? kmax - kmin : 0u;
+    int ran = kmax >= kmin ? 1 : 0;  // pass 0 always runs when there is a live key
+#pragma unroll
+    for (int q = 1; q < 4; ++q) ran += (range >> (8 * q)) != 0;
+    const uint32_t g = (ran & 1) ? order_b[s] : order_a[s];
     const uint2 rc = rect[g];
     const uint32_t wd = (rc.x >> 16) - (rc.x & 0xffff);
     const uint32_t magic = wd > 1 ? (uint32_t)((0x100000000ull + wd - 1) / wd) : 0u;
@@ -261,7 +268,8 @@ int launch_fill_tiles(int T, const uint2 *ranges, uint32_t *sorted_tiles, cudaSt
     return 0;
 }
 
-int launch_tile_placement(const PlacePlan &pl, int P, int T, int gx, const uint32_t *order, const uint2 *rect,
+int launch_tile_placement(const PlacePlan &pl, int P, int T, int gx, const uint32_t *order_a, const uint32_t *order_b,
+                          const uint32_t *stat, const uint2 *rect,
                           uint4 *srec, uint32_t *table, uint32_t *gsum, uint32_t *tile_start, uint2 *ranges,
                           uint32_t *out_gidx, cudaStream_t s)
 {
@@ -277,7 +285,7 @@ int launch_tile_placement(const PlacePlan &pl, int P, int T, int gx, const uint3
     const int threads = pl.wpb * 32;
     const int blocks = (pl.nseg + pl.wpb - 1) / pl.wpb;
     const dim3 cgrid((T + 127) / 128, pl.groups);
-    sorted_rect_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, order, rect, srec);
+    sorted_rect_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, order_a, order_b, stat, rect, srec);
     tile_count_kernel<<<blocks, threads, pl.smem, s>>>(P, T, gx, pl.seg, pl.nseg, srec, table);
     col_sum_kernel<<<cgrid, 128, 0, s>>>(T, pl.nseg, pl.rows_per_group, table, gsum);
     group_scan_kernel<<<(T + 7) / 8, 256, 0, s>>>(T, pl.groups, gsum, tile_start);

@@ -132,7 +132,7 @@ preprocess_fwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
                       float *__restrict__ depths, float4 *__restrict__ rec, float4 *__restrict__ rgb4,
                       uint8_t *__restrict__ clamped, float *__restrict__ cov3D, uint32_t *__restrict__ tiles,
                       uint2 *__restrict__ rect, uint32_t *__restrict__ sort_key, uint32_t *__restrict__ sort_val,
-                      uint32_t *__restrict__ total_instances)
+                      uint32_t *__restrict__ total_instances, uint32_t *__restrict__ key_stat)
 {
     extern __shared__ __align__(16) unsigned char dsm[];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -266,6 +266,16 @@ preprocess_fwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
         const uint32_t wsum = __reduce_add_sync(0xffffffffu, ntiles);
         if ((threadIdx.x & 31) == 0 && wsum) atomicAdd(total_instances, wsum);
     }
+    // range of the live depth keys (adaptive depth sort, sort.cu): {max of ~key, max of key}, both
+    // zero-initialised.  Culled Gaussians never reach a tile list, so where the sort puts them is irrelevant.
+    if (key_stat) {
+        const uint32_t k0 = __reduce_max_sync(0xffffffffu, ntiles ? ~key : 0u);
+        const uint32_t k1 = __reduce_max_sync(0xffffffffu, ntiles ? key : 0u);
+        if ((threadIdx.x & 31) == 0 && k1) {
+            atomicMax(key_stat, k0);
+            atomicMax(key_stat + 1, k1);
+        }
+    }
     if (!inb) return;
     radii[i] = rad;
     depths[i] = depth;
@@ -293,7 +303,7 @@ static int sh_mode(const dmgs_params *prm, const float *shs)
 int launch_preprocess_fwd(const dmgs_params *prm, const float *means3D, const float *scales, const float *rotations,
                           const float *cov3D_precomp, const float *opacities, const float *shs,
                           const float *colors_precomp, int32_t *radii, void *geom, const GeomLayout &L,
-                          uint32_t *total_instances, cudaStream_t s)
+                          uint32_t *total_instances, uint32_t *key_stat, cudaStream_t s)
 {
     const int P = prm->P;
     if (P <= 0) return 0;
@@ -309,7 +319,7 @@ int launch_preprocess_fwd(const dmgs_params *prm, const float *means3D, const fl
     dp, means3D, scales, rotations, cov3D_precomp, opacities, shs, colors_precomp, radii, at<float>(geom, L.depths), \
         at<float4>(geom, L.rec), at<float4>(geom, L.rgb), at<uint8_t>(geom, L.clamped), at<float>(geom, L.cov3D),    \
         at<uint32_t>(geom, L.tiles), at<uint2>(geom, L.rect), at<uint32_t>(geom, L.keys_a), at<uint32_t>(geom, L.order), \
-        total_instances
+        total_instances, key_stat
     const int grid = (P + 255) / 256;
     if (mode == 1) preprocess_fwd_kernel<1><<<grid, 256, SH_STAGE_SMEM, s>>>(DMGS_FWD_ARGS);
     else if (mode == 2) preprocess_fwd_kernel<2><<<grid, 256, SH_STAGE_SMEM, s>>>(DMGS_FWD_ARGS);

@@ -131,11 +131,42 @@ constexpr int RP_WARPS = RP_THREADS / 32;
 #define SCATTER_MIN_BLOCKS 4
 #endif
 
+// Adaptive passes: `stat` (optional) holds {max of ~key, max of key} over the live keys, i.e. their
+// minimum and maximum.  The passes sort on (key - min), whose significant bits are those of
+// (max - min): a pass over a digit above them has nothing to do, its kernels exit at once, and every
+// kernel finds its input in buffer A or B from the number of passes that did run before it.
+struct PassSel {
+    bool active;
+    int src;        // 0: (keys_a, vals_a) -> (keys_b, vals_b); 1: the other way round
+    uint32_t kmin;  // subtracted from every key before the digit is taken
+};
+__device__ __forceinline__ PassSel pass_select(const uint32_t *__restrict__ stat, int pass, int shift)
+{
+    PassSel r;
+    if (!stat) {
+        r.active = true;
+        r.src = pass & 1;
+        r.kmin = 0;
+        return r;
+    }
+    const uint32_t kmin = ~stat[0], kmax = stat[1];
+    const uint32_t range = kmax >= kmin ? kmax - kmin : 0u;  // no live key: nothing to sort
+    r.active = (range >> shift) != 0 || (pass == 0 && kmax >= kmin);
+    r.src = pass & 1;  // 8-bit digits from bit 0: the active passes are a prefix 0..k-1 of the sequence
+    r.kmin = kmin;
+    return r;
+}
+
 template <int RP_ROUNDS>
 __global__ void __launch_bounds__(RP_THREADS)
-radix_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift, int bins, int nblocks,
-                  uint32_t *__restrict__ hist)
+radix_hist_kernel(const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ keys_b, int64_t n, int shift,
+                  int bins, int nblocks, uint32_t *__restrict__ hist, const uint32_t *__restrict__ stat, int pass,
+                  int bits)
 {
+    (void)bits;
+    const PassSel ps = pass_select(stat, pass, shift);
+    if (!ps.active) return;
+    const uint32_t *__restrict__ keys = ps.src ? keys_b : keys_a;
     __shared__ uint32_t h[SORT_MAX_BINS];
     for (int d = threadIdx.x; d < bins; d += RP_THREADS) h[d] = 0;
     constexpr int ITEMS = RP_ROUNDS * RP_THREADS;
@@ -151,7 +182,7 @@ radix_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift, int b
 #pragma unroll
     for (int r = 0; r < RP_ROUNDS; ++r) {
         const int64_t i = base + (int64_t)r * RP_THREADS + threadIdx.x;
-        if (i < n) atomicAdd(&h[(k[r] >> shift) & mask], 1u);
+        if (i < n) atomicAdd(&h[((k[r] - ps.kmin) >> shift) & mask], 1u);
     }
     __syncthreads();
     for (int d = threadIdx.x; d < bins; d += RP_THREADS) hist[(size_t)d * nblocks + blockIdx.x] = h[d];
@@ -172,10 +203,14 @@ __device__ __forceinline__ uint32_t digit_peers(uint32_t d, uint32_t act)
 
 template <int BITS, int RP_ROUNDS>
 __global__ void __launch_bounds__(RP_THREADS, SCATTER_MIN_BLOCKS)
-radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
-                     uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n, int shift,
-                     int nblocks, const uint32_t *__restrict__ row_prefix, const uint32_t *__restrict__ bin_total)
+radix_scatter_kernel(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b, int64_t n, int shift,
+                     int nblocks, const uint32_t *__restrict__ row_prefix, const uint32_t *__restrict__ bin_total,
+                     const uint32_t *__restrict__ stat, int pass)
 {
+    const PassSel ps = pass_select(stat, pass, shift);
+    if (!ps.active) return;
+    const uint32_t *__restrict__ keys_in = ps.src ? keys_b : keys_a, *__restrict__ vals_in = ps.src ? vals_b : vals_a;
+    uint32_t *__restrict__ keys_out = ps.src ? keys_a : keys_b, *__restrict__ vals_out = ps.src ? vals_a : vals_b;
     constexpr int BINS = 1 << BITS;
     constexpr int ITEMS = RP_ROUNDS * RP_THREADS;
     __shared__ uint32_t wh[RP_WARPS][BINS];
@@ -209,7 +244,7 @@ radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
     for (int r = 0; r < RP_ROUNDS; ++r) {
         const bool valid = wbase + r * 32 < n;
         const uint32_t act = __ballot_sync(0xffffffffu, valid);
-        const uint32_t d = (key[r] >> shift) & mask;
+        const uint32_t d = ((key[r] - ps.kmin) >> shift) & mask;
         const uint32_t peers = digit_peers<BITS>(d, act);
         uint32_t old = 0;
         if (valid && (peers & lt) == 0) old = atomicAdd(&wh[w][d], (uint32_t)__popc(peers));
@@ -244,7 +279,7 @@ radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
 #pragma unroll
     for (int r = 0; r < RP_ROUNDS; ++r) {
         if (wbase + r * 32 < n) {
-            const uint32_t d = (key[r] >> shift) & mask;
+            const uint32_t d = ((key[r] - ps.kmin) >> shift) & mask;
             const uint32_t pos = bin_local[d] + wh[w][d] + rank[r];
             skeys[pos] = key[r];
             svals[pos] = val[r];
@@ -256,7 +291,7 @@ radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
 #pragma unroll 4
     for (int j = threadIdx.x; j < count; j += RP_THREADS) {
         const uint32_t k = skeys[j];
-        const uint32_t d = (k >> shift) & mask;
+        const uint32_t d = ((k - ps.kmin) >> shift) & mask;
         const uint32_t out = bin_global[d] + ((uint32_t)j - bin_local[d]);
         keys_out[out] = k;
         vals_out[out] = svals[j];
@@ -265,8 +300,11 @@ radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
 
 // one block per digit: exclusive scan of the digit's table row (over blocks) + the row total
 __global__ void __launch_bounds__(256)
-radix_rowscan_kernel(uint32_t *__restrict__ hist, int nblocks, uint32_t *__restrict__ bin_total)
+radix_rowscan_kernel(uint32_t *__restrict__ hist, int nblocks, uint32_t *__restrict__ bin_total,
+                     const uint32_t *__restrict__ stat, int pass, int shift, int bits)
 {
+    (void)bits;
+    if (!pass_select(stat, pass, shift).active) return;
     uint32_t *row = hist + (size_t)blockIdx.x * nblocks;
     uint32_t carry = 0;
     for (int b0 = 0; b0 < nblocks; b0 += 256 * 4) {
@@ -284,17 +322,23 @@ radix_rowscan_kernel(uint32_t *__restrict__ hist, int nblocks, uint32_t *__restr
 }
 
 template <int BITS>
-static void launch_scatter(int rounds, const uint32_t *ki, const uint32_t *vi, uint32_t *ko, uint32_t *vo, int64_t n,
-                           int shift, int nblocks, const uint32_t *hist, const uint32_t *bin_total, cudaStream_t s)
+static void launch_scatter(int rounds, uint32_t *ka, uint32_t *va, uint32_t *kb, uint32_t *vb, int64_t n, int shift,
+                           int nblocks, const uint32_t *hist, const uint32_t *bin_total, const uint32_t *stat, int pass,
+                           cudaStream_t s)
 {
-    if (rounds == 4) radix_scatter_kernel<BITS, 4><<<nblocks, RP_THREADS, 0, s>>>(ki, vi, ko, vo, n, shift, nblocks, hist, bin_total);
-    else radix_scatter_kernel<BITS, 8><<<nblocks, RP_THREADS, 0, s>>>(ki, vi, ko, vo, n, shift, nblocks, hist, bin_total);
+    if (rounds == 4)
+        radix_scatter_kernel<BITS, 4><<<nblocks, RP_THREADS, 0, s>>>(ka, va, kb, vb, n, shift, nblocks, hist, bin_total, stat, pass);
+    else
+        radix_scatter_kernel<BITS, 8><<<nblocks, RP_THREADS, 0, s>>>(ka, va, kb, vb, n, shift, nblocks, hist, bin_total, stat, pass);
 }
 
-int radix_pass(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out, int64_t n,
-               int shift, int bits, uint32_t *hist, uint32_t *scan_tmp, cudaStream_t s)
+// One stable LSD pass on `bits` bits starting at `shift`.  Without `stat`, pass p reads (keys_a, vals_a)
+// when p is even and (keys_b, vals_b) when odd and writes the other pair.  With `stat` (adaptive depth
+// sort, 8-bit digits) passes over digits that do not vary are skipped on the device and the buffers
+// alternate over the passes that did run.
+int radix_pass(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b, int64_t n, int pass, int shift,
+               int bits, uint32_t *hist, const uint32_t *stat, cudaStream_t s)
 {
-    (void)scan_tmp;
     if (n <= 0) return 0;
     if (bits < 1 || bits > 8) { set_error("radix_pass: bits=%d unsupported", bits); return -8; }
     const int bins = 1 << bits;
@@ -303,18 +347,18 @@ int radix_pass(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_
     const int items = rounds * RP_THREADS;
     const int nblocks = (int)((n + items - 1) / items);
     uint32_t *bin_total = hist + (size_t)SORT_MAX_BINS * nblocks;  // 256 spare entries behind the table
-    if (rounds == 4) radix_hist_kernel<4><<<nblocks, RP_THREADS, 0, s>>>(keys_in, n, shift, bins, nblocks, hist);
-    else radix_hist_kernel<8><<<nblocks, RP_THREADS, 0, s>>>(keys_in, n, shift, bins, nblocks, hist);
-    radix_rowscan_kernel<<<bins, 256, 0, s>>>(hist, nblocks, bin_total);
+    if (rounds == 4) radix_hist_kernel<4><<<nblocks, RP_THREADS, 0, s>>>(keys_a, keys_b, n, shift, bins, nblocks, hist, stat, pass, bits);
+    else radix_hist_kernel<8><<<nblocks, RP_THREADS, 0, s>>>(keys_a, keys_b, n, shift, bins, nblocks, hist, stat, pass, bits);
+    radix_rowscan_kernel<<<bins, 256, 0, s>>>(hist, nblocks, bin_total, stat, pass, shift, bits);
     switch (bits) {
-    case 1: launch_scatter<1>(rounds, keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
-    case 2: launch_scatter<2>(rounds, keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
-    case 3: launch_scatter<3>(rounds, keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
-    case 4: launch_scatter<4>(rounds, keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
-    case 5: launch_scatter<5>(rounds, keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
-    case 6: launch_scatter<6>(rounds, keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
-    case 7: launch_scatter<7>(rounds, keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
-    default: launch_scatter<8>(rounds, keys_in, vals_in, keys_out, vals_out, n, shift, nblocks, hist, bin_total, s); break;
+    case 1: launch_scatter<1>(rounds, keys_a, vals_a, keys_b, vals_b, n, shift, nblocks, hist, bin_total, stat, pass, s); break;
+    case 2: launch_scatter<2>(rounds, keys_a, vals_a, keys_b, vals_b, n, shift, nblocks, hist, bin_total, stat, pass, s); break;
+    case 3: launch_scatter<3>(rounds, keys_a, vals_a, keys_b, vals_b, n, shift, nblocks, hist, bin_total, stat, pass, s); break;
+    case 4: launch_scatter<4>(rounds, keys_a, vals_a, keys_b, vals_b, n, shift, nblocks, hist, bin_total, stat, pass, s); break;
+    case 5: launch_scatter<5>(rounds, keys_a, vals_a, keys_b, vals_b, n, shift, nblocks, hist, bin_total, stat, pass, s); break;
+    case 6: launch_scatter<6>(rounds, keys_a, vals_a, keys_b, vals_b, n, shift, nblocks, hist, bin_total, stat, pass, s); break;
+    case 7: launch_scatter<7>(rounds, keys_a, vals_a, keys_b, vals_b, n, shift, nblocks, hist, bin_total, stat, pass, s); break;
+    default: launch_scatter<8>(rounds, keys_a, vals_a, keys_b, vals_b, n, shift, nblocks, hist, bin_total, stat, pass, s); break;
     }
     DMGS_CUDA(cudaGetLastError());
     count_launches(3);
