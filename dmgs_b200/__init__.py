@@ -1,4 +1,4 @@
 """dmgs_b200 -- B200-native rasteriser + mesh binding for DMGS."""
-from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer  # noqa: F401
+from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, check_async, configure  # noqa: F401
 
-__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer"]
+__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "configure", "check_async"]

@@ -33,6 +33,7 @@ _SIGS = {
     "dmgs_backward_scratch_bytes": (C.c_size_t, [_i32]),
     "dmgs_preprocess_forward": (C.c_int, [C.POINTER(DmgsParams)] + [_vp] * 11),
     "dmgs_bin_forward": (C.c_int, [C.POINTER(DmgsParams), _vp, _i64, _vp, _vp]),
+    "dmgs_bin_forward_async": (C.c_int, [C.POINTER(DmgsParams), _vp, _i64, _vp, _vp, _vp]),
     "dmgs_blend_forward": (C.c_int, [C.POINTER(DmgsParams), _vp, _vp, _i64, _vp, _vp, _vp]),
     "dmgs_backward": (C.c_int, [C.POINTER(DmgsParams)] + [_vp] * 9 + [_i64] + [_vp] * 11),
     "dmgs_blend_backward": (C.c_int, [C.POINTER(DmgsParams), _vp, _vp, _vp, _i64, _vp, _vp, _vp]),

@@ -134,7 +134,8 @@ int dmgs_preprocess_forward(const dmgs_params *prm, const float *means3D, const 
     return check_stage(prm, s, "tile scan");
 }
 
-int dmgs_bin_forward(const dmgs_params *prm, const void *geom, int64_t R, void *binning, void *stream)
+static int bin_forward_impl(const dmgs_params *prm, const void *geom, int64_t R, void *binning, uint32_t *overflow,
+                            bool async, void *stream)
 {
     int rc = validate(prm);
     if (rc) return rc;
@@ -153,12 +154,18 @@ int dmgs_bin_forward(const dmgs_params *prm, const void *geom, int64_t R, void *
                                        at<uint32_t>(geom, GL.stat), at<uint2>(geom, GL.rect),
                                        at<uint4>(binning, BL.srec), at<uint32_t>(binning, BL.table),
                                        at<uint32_t>(binning, BL.gsum), at<uint32_t>(binning, BL.tile_start),
-                                       at<uint2>(binning, BL.ranges), at<uint32_t>(binning, BL.gidx), s);
+                                       at<uint2>(binning, BL.ranges), at<uint32_t>(binning, BL.gidx), R, overflow, s);
             if (rc) return rc;
         } else {
             DMGS_CUDA(cudaMemsetAsync(at<uint2>(binning, BL.ranges), 0, sizeof(uint2) * (size_t)T, s));
+            if (overflow) DMGS_CUDA(cudaMemsetAsync(overflow, 0, sizeof(uint32_t), s));
         }
         return check_stage(prm, s, "tile placement");
+    }
+    if (async) {
+        set_error("dmgs_bin_forward_async needs the direct-placement path (<= %d tiles); read num_rendered back "
+                  "and call dmgs_bin_forward", PLACE_MAX_TILES);
+        return -9;
     }
     uint32_t *ta = at<uint32_t>(binning, BL.tiles), *tb = at<uint32_t>(binning, BL.tiles_b);
     uint32_t *ga = at<uint32_t>(binning, BL.gidx), *gb = at<uint32_t>(binning, BL.gidx_b);
@@ -187,6 +194,19 @@ int dmgs_bin_forward(const dmgs_params *prm, const void *geom, int64_t R, void *
     rc = launch_tile_ranges(R, ta, at<uint2>(binning, BL.ranges), T, s);
     if (rc) return rc;
     return check_stage(prm, s, "tile ranges");
+}
+
+int dmgs_bin_forward(const dmgs_params *prm, const void *geom, int64_t R, void *binning, void *stream)
+{
+    return bin_forward_impl(prm, geom, R, binning, nullptr, false, stream);
+}
+
+int dmgs_bin_forward_async(const dmgs_params *prm, const void *geom, int64_t capacity, void *binning,
+                           uint32_t *overflow, void *stream)
+{
+    if (!overflow) { set_error("overflow pointer is NULL"); return -6; }
+    if (capacity < 1) { set_error("capacity must be positive"); return -7; }
+    return bin_forward_impl(prm, geom, capacity, binning, overflow, true, stream);
 }
 
 int dmgs_blend_forward(const dmgs_params *prm, const void *geom, const void *binning, int64_t R, float *out_color,

@@ -17,7 +17,6 @@
 #define DMGS_TILE 16
 #define DMGS_NEAR 0.2f
 #define DMGS_NUM_SMS 148        /* B200 */
-#define PLACE_MAX_GROUPS 256     /* row groups of the placement table scan */
 #define PLACE_MAX_TILES 16384   /* direct tile placement (place.cu) up to this many tiles, radix partition above */
 
 namespace dmgs {

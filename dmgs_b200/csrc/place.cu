@@ -9,10 +9,10 @@
 //   A  tile_count_kernel   the depth-ordered Gaussians are cut into `nseg` contiguous segments, one
 //                          per warp; each warp counts the tiles its Gaussians touch in its own
 //                          shared-memory counters and writes one row of table[nseg][T];
-//   B  col_sum / group_scan / tile_scan / col_apply
-//                          column-wise exclusive scan of the table (two-level over row groups) and
-//                          the exclusive scan of the tile totals: table[s][t] becomes the position of
-//                          segment s's first entry in tile t's list, and ranges[t] falls out for free;
+//   B  group_scan / tile_scan
+//                          exclusive scan of the per-CTA sums down every tile column and of the tile
+//                          totals: together with the rows of the table they give every segment its first
+//                          slot in every tile's list, and ranges[t] falls out for free;
 //   C  tile_place_kernel   each warp re-walks its segment IN ORDER, one Gaussian per step with lanes
 //                          over the tiles of its rectangle (distinct tiles, so no conflicts), bumping
 //                          its shared-memory cursors and writing the Gaussian index to its final slot.
@@ -50,9 +50,8 @@ PlacePlan place_plan(int32_t P, int T)
     seg = (seg + 31) / 32 * 32;
     p.seg = seg;
     p.nseg = (int)((n + seg - 1) / seg);
-    p.groups = p.nseg < PLACE_MAX_GROUPS ? p.nseg : PLACE_MAX_GROUPS;
-    p.rows_per_group = (p.nseg + p.groups - 1) / p.groups;
-    p.groups = (p.nseg + p.rows_per_group - 1) / p.rows_per_group;
+    p.rows_per_group = p.wpb;  // one group of table rows per CTA of the count / place kernels
+    p.groups = (p.nseg + p.wpb - 1) / p.wpb;
     p.smem = (size_t)p.wpb * per_warp;
     p.ok = 1;
     return p;
@@ -82,49 +81,152 @@ sorted_rect_kernel(int P, const uint32_t *__restrict__ order_a, const uint32_t *
 }
 
 // ------------------------------------------------------------------------------ A: count
-// lane <-> Gaussian; order is irrelevant for counting, so lanes add their rectangles with shared atomics
+// lane <-> Gaussian; order is irrelevant for counting, so lanes add their rectangles with shared
+// atomics.  Each warp writes its row of table[nseg][T]; the CTA also writes the sum of its rows to
+// gsum[cta][T], the coarse level of the column scan.
 __global__ void __launch_bounds__(128)
-tile_count_kernel(int P, int T, int gx, int seg, int nseg, const uint4 *__restrict__ srec, uint32_t *__restrict__ table)
+tile_count_kernel(int P, int T, int gx, int seg, int nseg, const uint4 *__restrict__ srec, uint32_t *__restrict__ table,
+                  uint32_t *__restrict__ gsum)
 {
     extern __shared__ uint32_t s_cnt[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int sg = blockIdx.x * wpb + w;
-    if (sg >= nseg) return;
     uint32_t *cnt = s_cnt + (size_t)w * T;
     for (int t = lane; t < T; t += 32) cnt[t] = 0;
     __syncwarp();
-    const int s0 = sg * seg, s1 = min(P, s0 + seg);
-    uint4 nxt = s0 + lane < s1 ? srec[s0 + lane] : make_uint4(0, 0, 0, 0);
-    for (int sb = s0; sb < s1; sb += 32) {
-        const uint4 rc = nxt;
-        const int sn = sb + 32 + lane;
-        nxt = sn < s1 ? srec[sn] : make_uint4(0, 0, 0, 0);  // prefetch the next batch
-        const int x0 = rc.x & 0xffff, x1 = rc.x >> 16, y0 = rc.y & 0xffff, y1 = rc.y >> 16;
-        for (int y = y0; y < y1; ++y) {
-            uint32_t *rowp = cnt + y * gx;
-            for (int x = x0; x < x1; ++x) atomicAdd(rowp + x, 1u);
+    if (sg < nseg) {
+        const int s0 = sg * seg, s1 = min(P, s0 + seg);
+        uint4 nxt = s0 + lane < s1 ? srec[s0 + lane] : make_uint4(0, 0, 0, 0);
+        for (int sb = s0; sb < s1; sb += 32) {
+            const uint4 rc = nxt;
+            const int sn = sb + 32 + lane;
+            nxt = sn < s1 ? srec[sn] : make_uint4(0, 0, 0, 0);  // prefetch the next batch
+            const int x0 = rc.x & 0xffff, x1 = rc.x >> 16, y0 = rc.y & 0xffff, y1 = rc.y >> 16;
+            for (int y = y0; y < y1; ++y) {
+                uint32_t *rowp = cnt + y * gx;
+                for (int x = x0; x < x1; ++x) atomicAdd(rowp + x, 1u);
+            }
         }
+        __syncwarp();
+        uint32_t *row = table + (size_t)sg * T;
+        for (int t = lane; t < T; t += 32) row[t] = cnt[t];
     }
-    __syncwarp();
-    uint32_t *row = table + (size_t)sg * T;
-    for (int t = lane; t < T; t += 32) row[t] = cnt[t];
+    __syncthreads();
+    uint32_t *grow = gsum + (size_t)blockIdx.x * T;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        uint32_t sum = 0;
+        for (int k = 0; k < wpb; ++k) sum += s_cnt[(size_t)k * T + t];
+        grow[t] = sum;
+    }
+}
+
+// ------------------------------------------------------------------------------ B: column scan
+// one warp per tile: exclusive scan of the tile's CTA sums down the column (in place) and the tile total
+__global__ void __launch_bounds__(256)
+group_scan_kernel(int T, int groups, uint32_t *__restrict__ gsum, uint32_t *__restrict__ tile_total)
+{
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (t >= T) return;
+    uint32_t carry = 0;
+    for (int g0 = 0; g0 < groups; g0 += 128) {
+        uint32_t v[4], sum = 0;  // lane owns 4 consecutive groups of this 128-group chunk
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int g = g0 + lane * 4 + i;
+            v[i] = g < groups ? gsum[(size_t)g * T + t] : 0u;
+            sum += v[i];
+        }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        uint32_t run = carry + incl - sum;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int g = g0 + lane * 4 + i;
+            if (g < groups) gsum[(size_t)g * T + t] = run;
+            run += v[i];
+        }
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) tile_total[t] = carry;
+}
+
+// one block: exclusive scan of the tile totals (in place -> tile_start) and the tile ranges
+// (empty tiles keep (0,0), as the reference's zero-initialised ranges do)
+// capacity / overflow: the instance list holds `capacity` entries; if the total exceeds it nothing can be
+// placed: every range stays (0,0), *overflow receives the total (0 otherwise) and the place kernel exits.
+__global__ void __launch_bounds__(1024)
+tile_scan_kernel(int T, uint32_t *__restrict__ tile_start, uint2 *__restrict__ ranges, uint32_t capacity,
+                 uint32_t *__restrict__ overflow)
+{
+    __shared__ uint32_t warp_sums[32];
+    const int per = (T + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int t0 = threadIdx.x * per, t1 = min(T, t0 + per);
+    uint32_t local = 0;
+    for (int t = t0; t < t1; ++t) local += tile_start[t];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t incl = local;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (threadIdx.x < 32) warp_sums[threadIdx.x] = 0;
+    __syncthreads();
+    if (lane == 31) warp_sums[w] = incl;
+    __syncthreads();
+    uint32_t base = 0, total = 0;
+    for (int k = 0; k < 32; ++k) {
+        if (k < w) base += warp_sums[k];
+        total += warp_sums[k];
+    }
+    const bool fits = total <= capacity;
+    if (threadIdx.x == 0 && overflow) *overflow = fits ? 0u : total;
+    uint32_t run = base + incl - local;
+    for (int t = t0; t < t1; ++t) {
+        const uint32_t tot = tile_start[t];
+        tile_start[t] = run;
+        ranges[t] = (tot && fits) ? make_uint2(run, run + tot) : make_uint2(0u, 0u);
+        run += tot;
+    }
 }
 
 // ------------------------------------------------------------------------------ C: place
-// One Gaussian per step, in depth order; lanes <-> the tiles of its rectangle (all distinct, so the
-// read-modify-write of the cursors needs no atomics and keeps the order).
+// The CTA first turns its rows of counts into cursors (tile start + CTAs before + warps before), then
+// every warp walks its segment: one Gaussian per step, in depth order; lanes <-> the tiles of its
+// rectangle (all distinct, so the read-modify-write of the cursors needs no atomics and keeps the order).
 __global__ void __launch_bounds__(128)
 tile_place_kernel(int P, int T, int gx, int seg, int nseg, const uint4 *__restrict__ srec,
-                  const uint32_t *__restrict__ table, uint32_t *__restrict__ out_gidx)
+                  const uint32_t *__restrict__ table, const uint32_t *__restrict__ gsum,
+                  const uint32_t *__restrict__ tile_start, const uint32_t *__restrict__ overflow,
+                  uint32_t *__restrict__ out_gidx)
 {
     extern __shared__ uint32_t s_cur[];
+    if (overflow && *overflow) return;  // the list does not fit its buffer: nothing is placed (uniform)
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int sg = blockIdx.x * wpb + w;
-    if (sg >= nseg) return;
     uint32_t *cur = s_cur + (size_t)w * T;
-    const uint32_t *row = table + (size_t)sg * T;
-    for (int t = lane; t < T; t += 32) cur[t] = row[t];
-    __syncwarp();
+    if (sg < nseg) {
+        const uint32_t *row = table + (size_t)sg * T;
+        for (int t = lane; t < T; t += 32) cur[t] = row[t];
+    } else {
+        for (int t = lane; t < T; t += 32) cur[t] = 0;
+    }
+    __syncthreads();
+    const uint32_t *grow = gsum + (size_t)blockIdx.x * T;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        uint32_t run = tile_start[t] + grow[t];
+        for (int k = 0; k < wpb; ++k) {
+            const uint32_t c = s_cur[(size_t)k * T + t];
+            s_cur[(size_t)k * T + t] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    if (sg >= nseg) return;
     const int s0 = sg * seg, s1 = min(P, s0 + seg);
     uint4 nxt = s0 + lane < s1 ? srec[s0 + lane] : make_uint4(0, 0, 0, 0);
     for (int sb = s0; sb < s1; sb += 32) {
@@ -153,103 +255,6 @@ tile_place_kernel(int P, int T, int gx, int seg, int nseg, const uint4 *__restri
     }
 }
 
-// ------------------------------------------------------------------------------ B: column scan
-// Two-level exclusive scan down the columns of table[nseg][T]: rows are cut into <= 256 groups.
-// gsum[g][t] = sum of the rows of group g in column t
-__global__ void __launch_bounds__(128)
-col_sum_kernel(int T, int nseg, int rows_per_group, const uint32_t *__restrict__ table, uint32_t *__restrict__ gsum)
-{
-    const int t = blockIdx.x * blockDim.x + threadIdx.x, g = blockIdx.y;
-    if (t >= T) return;
-    const int r0 = g * rows_per_group, r1 = min(nseg, r0 + rows_per_group);
-    uint32_t s = 0;
-#pragma unroll 4
-    for (int r = r0; r < r1; ++r) s += table[(size_t)r * T + t];
-    gsum[(size_t)g * T + t] = s;
-}
-
-// one warp per tile: exclusive scan of the tile's group sums (in place) and the tile total
-__global__ void __launch_bounds__(256)
-group_scan_kernel(int T, int groups, uint32_t *__restrict__ gsum, uint32_t *__restrict__ tile_total)
-{
-    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (t >= T) return;
-    constexpr int PER = PLACE_MAX_GROUPS / 32;
-    uint32_t v[PER], sum = 0;
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        const int g = lane * PER + i;
-        v[i] = g < groups ? gsum[(size_t)g * T + t] : 0u;
-        sum += v[i];
-    }
-    uint32_t incl = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += o;
-    }
-    uint32_t run = incl - sum;
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        const int g = lane * PER + i;
-        if (g < groups) gsum[(size_t)g * T + t] = run;
-        run += v[i];
-    }
-    if (lane == 31) tile_total[t] = incl;
-}
-
-// one block: exclusive scan of the tile totals (in place -> tile_start) and the tile ranges
-// (empty tiles keep (0,0), as the reference's zero-initialised ranges do)
-__global__ void __launch_bounds__(1024)
-tile_scan_kernel(int T, uint32_t *__restrict__ tile_start, uint2 *__restrict__ ranges)
-{
-    __shared__ uint32_t warp_sums[32];
-    const int per = (T + (int)blockDim.x - 1) / (int)blockDim.x;
-    const int t0 = threadIdx.x * per, t1 = min(T, t0 + per);
-    uint32_t local = 0;
-    for (int t = t0; t < t1; ++t) local += tile_start[t];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    uint32_t incl = local;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += v;
-    }
-    if (lane == 31) warp_sums[w] = incl;
-    __syncthreads();
-    uint32_t base = 0;
-    for (int k = 0; k < w; ++k) base += warp_sums[k];
-    uint32_t run = base + incl - local;
-    for (int t = t0; t < t1; ++t) {
-        const uint32_t tot = tile_start[t];
-        tile_start[t] = run;
-        ranges[t] = tot ? make_uint2(run, run + tot) : make_uint2(0u, 0u);
-        run += tot;
-    }
-}
-
-// table[r][t] <- tile_start[t] + (entries of tile t in the rows before r)
-__global__ void __launch_bounds__(128)
-col_apply_kernel(int T, int nseg, int rows_per_group, const uint32_t *__restrict__ gsum,
-                 const uint32_t *__restrict__ tile_start, uint32_t *table)
-{
-    const int t = blockIdx.x * blockDim.x + threadIdx.x, g = blockIdx.y;
-    if (t >= T) return;
-    uint32_t run = tile_start[t] + gsum[(size_t)g * T + t];
-    const int r0 = g * rows_per_group, r1 = min(nseg, r0 + rows_per_group);
-    // batches of 8 rows: all loads issued before the dependent prefix / stores
-    for (int r = r0; r < r1; r += 8) {
-        uint32_t c[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) c[k] = r + k < r1 ? table[(size_t)(r + k) * T + t] : 0u;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (r + k < r1) table[(size_t)(r + k) * T + t] = run;
-            run += c[k];
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------ inspection helper
 // sorted tile ids rebuilt from the ranges (the placement path never materialises them)
 __global__ void fill_tiles_kernel(int T, const uint2 *__restrict__ ranges, uint32_t *__restrict__ sorted_tiles)
@@ -271,7 +276,7 @@ int launch_fill_tiles(int T, const uint2 *ranges, uint32_t *sorted_tiles, cudaSt
 int launch_tile_placement(const PlacePlan &pl, int P, int T, int gx, const uint32_t *order_a, const uint32_t *order_b,
                           const uint32_t *stat, const uint2 *rect,
                           uint4 *srec, uint32_t *table, uint32_t *gsum, uint32_t *tile_start, uint2 *ranges,
-                          uint32_t *out_gidx, cudaStream_t s)
+                          uint32_t *out_gidx, int64_t capacity, uint32_t *overflow, cudaStream_t s)
 {
     static bool attr_set = false;
     if (!attr_set) {
@@ -283,17 +288,14 @@ int launch_tile_placement(const PlacePlan &pl, int P, int T, int gx, const uint3
         attr_set = true;
     }
     const int threads = pl.wpb * 32;
-    const int blocks = (pl.nseg + pl.wpb - 1) / pl.wpb;
-    const dim3 cgrid((T + 127) / 128, pl.groups);
+    const int blocks = pl.groups;
     sorted_rect_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, order_a, order_b, stat, rect, srec);
-    tile_count_kernel<<<blocks, threads, pl.smem, s>>>(P, T, gx, pl.seg, pl.nseg, srec, table);
-    col_sum_kernel<<<cgrid, 128, 0, s>>>(T, pl.nseg, pl.rows_per_group, table, gsum);
+    tile_count_kernel<<<blocks, threads, pl.smem, s>>>(P, T, gx, pl.seg, pl.nseg, srec, table, gsum);
     group_scan_kernel<<<(T + 7) / 8, 256, 0, s>>>(T, pl.groups, gsum, tile_start);
-    tile_scan_kernel<<<1, 1024, 0, s>>>(T, tile_start, ranges);
-    col_apply_kernel<<<cgrid, 128, 0, s>>>(T, pl.nseg, pl.rows_per_group, gsum, tile_start, table);
-    tile_place_kernel<<<blocks, threads, pl.smem, s>>>(P, T, gx, pl.seg, pl.nseg, srec, table, out_gidx);
+    tile_scan_kernel<<<1, 1024, 0, s>>>(T, tile_start, ranges, (uint32_t)capacity, overflow);
+    tile_place_kernel<<<blocks, threads, pl.smem, s>>>(P, T, gx, pl.seg, pl.nseg, srec, table, gsum, tile_start, overflow, out_gidx);
     DMGS_CUDA(cudaGetLastError());
-    count_launches(7);
+    count_launches(5);
     return 0;
 }
 

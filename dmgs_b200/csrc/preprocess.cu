@@ -261,19 +261,26 @@ preprocess_fwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
             col = make_float4(v[0], v[1], v[2], 0.0f);
         }
     }
-    // number of (Gaussian, tile) instances: one fire-and-forget reduction per warp
+    // per block: number of (Gaussian, tile) instances, and the range of the live depth keys as
+    // {max of ~key, max of key} (adaptive depth sort, sort.cu; both zero-initialised).  Culled Gaussians
+    // never reach a tile list, so where the sort puts them is irrelevant.
     if (total_instances) {
+        __shared__ uint32_t s_red[3];
+        if (threadIdx.x < 3) s_red[threadIdx.x] = 0;
+        __syncthreads();
         const uint32_t wsum = __reduce_add_sync(0xffffffffu, ntiles);
-        if ((threadIdx.x & 31) == 0 && wsum) atomicAdd(total_instances, wsum);
-    }
-    // range of the live depth keys (adaptive depth sort, sort.cu): {max of ~key, max of key}, both
-    // zero-initialised.  Culled Gaussians never reach a tile list, so where the sort puts them is irrelevant.
-    if (key_stat) {
         const uint32_t k0 = __reduce_max_sync(0xffffffffu, ntiles ? ~key : 0u);
         const uint32_t k1 = __reduce_max_sync(0xffffffffu, ntiles ? key : 0u);
-        if ((threadIdx.x & 31) == 0 && k1) {
-            atomicMax(key_stat, k0);
-            atomicMax(key_stat + 1, k1);
+        if ((threadIdx.x & 31) == 0 && wsum) {
+            atomicAdd(&s_red[0], wsum);
+            atomicMax(&s_red[1], k0);
+            atomicMax(&s_red[2], k1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && s_red[0]) {
+            atomicAdd(total_instances, s_red[0]);
+            atomicMax(key_stat, s_red[1]);
+            atomicMax(key_stat + 1, s_red[2]);
         }
     }
     if (!inb) return;

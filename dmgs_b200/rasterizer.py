@@ -7,6 +7,12 @@ Extensions that keep the drop-in intact (all optional, default = upstream behavi
     lets DMGS's python ``eval_sh`` + ``sigmoid`` (gaussian_renderer/__init__.py:74-78, :166-170) run
     inside preprocess: pass ``shs=features`` instead of ``colors_precomp``.
   * ``rasterizer.last`` keeps the state buffers of the last forward for inspection (tests).
+  * ``configure(async_binning=True)`` removes the one host synchronisation of the forward (the
+    read-back of the instance count that sizes the binning buffer, which upstream also performs):
+    the buffer is sized from the counts seen so far for the same (P, W, H) plus slack, the count
+    stays on the device, and ``check_async()`` -- called at the caller's next natural sync point,
+    e.g. right after ``loss.item()`` -- reports whether any frame since the last check overflowed
+    its buffer (such a frame rendered as background with zero gradients and must be repeated).
 """
 from __future__ import annotations
 
@@ -36,6 +42,37 @@ class GaussianRasterizationSettings(NamedTuple):
 
 
 _HOST_CACHE: dict = {}
+
+# ---- optional sync-free binning (see the module docstring) ------------------------------------------
+_ASYNC = {"on": False, "slack": 1.25, "capacity": {}, "pending": []}
+
+
+def configure(async_binning: Optional[bool] = None, capacity_slack: Optional[float] = None):
+    """async_binning: size the binning buffer from earlier frames instead of reading the instance
+    count back (default False = upstream behaviour).  capacity_slack: head-room factor (default 1.25)."""
+    if async_binning is not None:
+        _ASYNC["on"] = bool(async_binning)
+    if capacity_slack is not None:
+        _ASYNC["slack"] = float(capacity_slack)
+    if not _ASYNC["on"]:
+        _ASYNC["pending"].clear()
+
+
+def check_async() -> bool:
+    """True if every async-binned frame since the last call fitted its buffer.  Synchronises (one
+    small device->host copy).  On overflow the capacity for that shape is raised and False is
+    returned: the caller repeats the step."""
+    pend, _ASYNC["pending"] = _ASYNC["pending"], []
+    if not pend:
+        return True
+    flags = torch.cat([f for _, f, _ in pend]).cpu().tolist()
+    counts = torch.cat([n for _, _, n in pend]).cpu().tolist()
+    ok = True
+    for (key, _, _), need, count in zip(pend, flags, counts):
+        cap = _ASYNC["capacity"].get(key, 0)
+        _ASYNC["capacity"][key] = max(cap, int(max(need, count) * _ASYNC["slack"]) + 4096)
+        ok = ok and need == 0
+    return ok
 
 
 def _host_values(tensors):
@@ -99,9 +136,18 @@ def _stream():
 class RasterState:
     """Caller-owned state of one forward (the geom / binning / image byte buffers)."""
 
-    def __init__(self, prm, geom, binning, image, num_rendered, radii):
+    def __init__(self, prm, geom, binning, image, num_rendered, radii, count_dev=None):
         self.prm, self.geom, self.binning, self.image = prm, geom, binning, image
-        self.num_rendered, self.radii = num_rendered, radii
+        # layout_R sizes the binning layout in every later C call: the instance count on the synchronous
+        # path, the buffer capacity on the async path (where the real count stays on the device)
+        self.layout_R, self.radii, self._count_dev = num_rendered, radii, count_dev
+        self._count = None if count_dev is not None else num_rendered
+
+    @property
+    def num_rendered(self) -> int:
+        if self._count is None:
+            self._count = int(self._count_dev.item())
+        return self._count
 
     # typed views for the parity tests -------------------------------------------------
     def _view(self, buf, off, dtype, shape):
@@ -126,7 +172,7 @@ class RasterState:
         R, W, H = self.num_rendered, self.prm.image_width, self.prm.image_height
         T = ((W + 15) // 16) * ((H + 15) // 16)
         o = (C.c_int64 * 3)()
-        L.lib().dmgs_binning_layout(self.prm.P, R, W, H, o)
+        L.lib().dmgs_binning_layout(self.prm.P, self.layout_R, W, H, o)
         v = self._view
         return {"tiles": v(self.binning, o[0], torch.int32, (R,)), "gidx": v(self.binning, o[1], torch.int32, (R,)),
                 "ranges": v(self.binning, o[2], torch.int32, (T, 2))}
@@ -142,6 +188,8 @@ class RasterState:
     def sorted_keys(self):
         R = self.num_rendered
         keys = torch.empty(max(R, 1), dtype=torch.int64, device=self.geom.device)
+        if self.layout_R != R:
+            raise RuntimeError("sorted_keys() is an inspection helper of the synchronous path")
         L.check(L.lib().dmgs_sorted_keys(L.ptr(self.geom), L.ptr(self.binning), self.prm.P, R, self.prm.image_width,
                                          self.prm.image_height, L.ptr(keys), _stream()), "dmgs_sorted_keys")
         return keys[:R]
@@ -171,16 +219,35 @@ def rasterize_forward(settings, means3D, opacities, shs, colors_precomp, scales,
                                         L.ptr(radii), L.ptr(geom), L.ptr(nr), stream), "dmgs_preprocess_forward")
     if stage_hook is not None:
         stage_hook("preprocess_sort_scan")
-    R = int(nr.item())  # the one host read-back of the forward (upstream does the same after its scan)
-    binning = torch.empty(lib.dmgs_binning_bytes(P, R, W, H), dtype=torch.uint8, device=dev)
-    L.check(lib.dmgs_bin_forward(C.byref(prm), L.ptr(geom), R, L.ptr(binning), stream), "dmgs_bin_forward")
+    key = (dev.index, P, W, H)
+    cap = _ASYNC["capacity"].get(key) if _ASYNC["on"] else None
+    count_dev = None
+    if cap is not None:
+        # sync-free: buffer sized from earlier frames of this shape; the count stays on the device
+        R = int(cap)
+        binning = torch.empty(lib.dmgs_binning_bytes(P, R, W, H), dtype=torch.uint8, device=dev)
+        flag = torch.empty(1, dtype=torch.int32, device=dev)
+        rc = lib.dmgs_bin_forward_async(C.byref(prm), L.ptr(geom), R, L.ptr(binning), L.ptr(flag), stream)
+        if rc == -9:  # image too large for the placement path: synchronous from now on
+            _ASYNC["capacity"].pop(key, None)
+            cap = None
+        else:
+            L.check(rc, "dmgs_bin_forward_async")
+            _ASYNC["pending"].append((key, flag, nr))
+            count_dev = nr
+    if cap is None:
+        R = int(nr.item())  # the one host read-back of the forward (upstream does the same after its scan)
+        if _ASYNC["on"]:
+            _ASYNC["capacity"][key] = max(_ASYNC["capacity"].get(key, 0), int(R * _ASYNC["slack"]) + 4096)
+        binning = torch.empty(lib.dmgs_binning_bytes(P, R, W, H), dtype=torch.uint8, device=dev)
+        L.check(lib.dmgs_bin_forward(C.byref(prm), L.ptr(geom), R, L.ptr(binning), stream), "dmgs_bin_forward")
     if stage_hook is not None:
         stage_hook("binning")
     L.check(lib.dmgs_blend_forward(C.byref(prm), L.ptr(geom), L.ptr(binning), R, L.ptr(color), L.ptr(image), stream),
             "dmgs_blend_forward")
     if stage_hook is not None:
         stage_hook("blend_fwd")
-    return color, radii, RasterState(prm, geom, binning, image, R, radii)
+    return color, radii, RasterState(prm, geom, binning, image, R, radii, count_dev)
 
 
 def rasterize_backward(state: RasterState, grad_color, means3D, shs, scales, rotations, cov3D_precomp,
@@ -207,7 +274,7 @@ def rasterize_backward(state: RasterState, grad_color, means3D, shs, scales, rot
     scratch = torch.empty(lib.dmgs_backward_scratch_bytes(P), dtype=torch.uint8, device=dev)
     stream = _stream()
     L.check(lib.dmgs_blend_backward(C.byref(prm), L.ptr(state.geom), L.ptr(state.binning), L.ptr(state.image),
-                                    state.num_rendered, L.ptr(grad_color), L.ptr(scratch), stream),
+                                    state.layout_R, L.ptr(grad_color), L.ptr(scratch), stream),
             "dmgs_blend_backward")
     if stage_hook is not None:
         stage_hook("blend_bwd")

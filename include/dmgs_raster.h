@@ -56,9 +56,10 @@ size_t dmgs_binning_bytes(int32_t P, int64_t num_rendered, int32_t W, int32_t H)
 size_t dmgs_image_bytes(int32_t W, int32_t H);
 
 /* ---- forward, stage 1: replaces preprocessCUDA + InclusiveSum ----------
- * Per-Gaussian EWA projection / SH colour / tile rectangle, a stable depth sort of the
- * Gaussians, and the prefix sum of tiles touched in depth order.  Writes radii[P] (int32) and
- * the number of (Gaussian, tile) instances to *num_rendered (device uint32). */
+ * Per-Gaussian EWA projection / SH colour / tile rectangle and a stable depth sort of the
+ * Gaussians (adaptive: only the digits in which the live depth keys differ are sorted).
+ * Writes radii[P] (int32) and the number of (Gaussian, tile) instances to *num_rendered
+ * (device uint32). */
 int dmgs_preprocess_forward(const dmgs_params *prm, const float *means3D, const float *scales,
                             const float *rotations, const float *cov3D_precomp, const float *opacities,
                             const float *shs, const float *colors_precomp, int32_t *radii, void *geom,
@@ -66,8 +67,20 @@ int dmgs_preprocess_forward(const dmgs_params *prm, const float *means3D, const 
 
 /* ---- forward, stage 2: replaces duplicateWithKeys + SortPairs + identifyTileRanges (K3-K5) --
  * num_rendered is the value stage 1 produced (read back by the caller, as the upstream host
- * code does).  Produces the tile-major, depth-ordered instance list and per-tile ranges. */
+ * code does).  Produces the tile-major, depth-ordered instance list and per-tile ranges: by
+ * direct placement from the depth-sorted Gaussian order for images of up to 16384 tiles, by a
+ * stable radix partition of the emitted instances above that (or with DMGS_TILE_PARTITION=radix
+ * in the environment). */
 int dmgs_bin_forward(const dmgs_params *prm, const void *geom, int64_t num_rendered, void *binning, void *stream);
+/* Same without the host read-back (no counterpart upstream): the binning buffer is sized for
+ * `capacity` instances (dmgs_binning_bytes(P, capacity, W, H)) and `capacity` takes the place of
+ * num_rendered in every later call on this state.  The real count stays on the device; if it
+ * exceeds the capacity nothing is placed, every tile range is (0,0) (the frame renders as
+ * background and its gradients are zero) and *overflow (device uint32) receives the count needed,
+ * 0 otherwise.  The caller checks the flag at its next synchronisation point and repeats the frame
+ * with a larger buffer.  Direct-placement path only (-9 for images above 16384 tiles). */
+int dmgs_bin_forward_async(const dmgs_params *prm, const void *geom, int64_t capacity, void *binning,
+                           uint32_t *overflow, void *stream);
 
 /* ---- forward, stage 3: replaces renderCUDA forward (K6). out_color is [3,H,W]. */
 int dmgs_blend_forward(const dmgs_params *prm, const void *geom, const void *binning, int64_t num_rendered,
@@ -119,9 +132,11 @@ int dmgs_bind_backward(int64_t F, int32_t k, const float *verts, const int64_t *
 /* ---- inspection (parity tests): byte offsets of the named arrays inside the state buffers.
  * geom:    [0] depths f32[P]  [1] rec f32[P][8]={x,y,conA,conB,conC,opacity,cut,_}  [2] rgb f32[P][4]
  *          [3] clamped u8[P] (bit ch)  [4] cov3D f32[P][6]  [5] tiles_touched u32[P]
- *          [6] rect u16[P][4]={x0,x1,y0,y1}  [7] depth-sorted Gaussian index u32[P]
- *          [8] instance offsets (exclusive scan in depth order) u32[P]
- * binning: [0] sorted tile ids u32[R]  [1] sorted Gaussian indices u32[R]  [2] ranges u32[T][2]
+ *          [6] rect u16[P][4]={x0,x1,y0,y1}  [7] sort buffer A of Gaussian indices u32[P] (the
+ *          depth order after an even number of executed passes)  [8] instance offsets (exclusive
+ *          scan in depth order; radix tile partition only) u32[P]
+ * binning: [0] sorted tile ids u32[R] (materialised by dmgs_sorted_keys on the placement path)
+ *          [1] sorted Gaussian indices u32[R]  [2] ranges u32[T][2]
  * image:   [0] final_T f32[H*W]  [1] n_contrib u32[H*W]                                        */
 int dmgs_geom_layout(int32_t P, int64_t *offsets9);
 int dmgs_binning_layout(int32_t P, int64_t num_rendered, int32_t W, int32_t H, int64_t *offsets3);

@@ -108,3 +108,49 @@ def test_multiview_accumulate_equals_sum_of_views():
     for name in ("means3D", "opacities", "scales", "rotations", "shs"):
         a, b = buf.views[name].cpu().numpy(), t[name].grad.cpu().numpy()
         grad_close(a.reshape(P, -1), b.reshape(P, -1), rtol=2e-4, name=name)
+
+
+def test_async_binning_matches_sync_and_reports_overflow():
+    """configure(async_binning=True): same image / gradients without the host read-back; a frame whose
+    instance list outgrows the remembered capacity renders as background, check_async() reports it,
+    and the repeated frame is right."""
+    import dmgs_b200
+    from dmgs_b200 import GaussianRasterizer
+    from dmgs_b200 import rasterizer as RZ
+    from gpu_util import settings_for
+    P, W, H = 4000, 192, 128
+    cl = S.random_cloud(P, seed=11, extent=1.0, log_scale_mean=math.log(0.04))
+    d = {k: v.cuda() for k, v in cl.items()}
+    cam = S.nerf_synthetic_camera(2, W, H)
+    rs = settings_for(cam, (0.3, 0.2, 0.1))
+
+    def run(scales):
+        t = {k: v.clone().requires_grad_() for k, v in d.items()}
+        ras = GaussianRasterizer(rs)
+        img, radii = ras(means3D=t["means3D"], means2D=torch.zeros_like(t["means3D"]), shs=t["shs"],
+                         opacities=t["opacities"], scales=scales, rotations=t["rotations"])
+        img.square().sum().backward()
+        return img.detach(), t["means3D"].grad.clone(), ras.last
+
+    ref_img, ref_g, _ = run(d["scales"])
+    big_img, _, _ = run(d["scales"] * 3.0)
+    try:
+        dmgs_b200.configure(async_binning=True, capacity_slack=1.25)
+        RZ._ASYNC["capacity"].clear()
+        img0, g0, st0 = run(d["scales"])  # first frame of this shape: synchronous, learns the capacity
+        assert st0._count_dev is None and dmgs_b200.check_async()
+        img1, g1, st1 = run(d["scales"])  # sync-free
+        assert st1._count_dev is not None and st1.layout_R > st1.num_rendered
+        assert dmgs_b200.check_async()
+        assert torch.equal(img1, ref_img) and torch.equal(img0, ref_img)
+        grad_close(g1.cpu().numpy(), ref_g.cpu().numpy(), rtol=2e-4, name="means3D")
+        # 3x larger splats: the instance list no longer fits
+        img2, g2, st2 = run(d["scales"] * 3.0)
+        assert not dmgs_b200.check_async()
+        bgimg = torch.tensor([0.3, 0.2, 0.1], device="cuda").view(3, 1, 1).expand_as(img2)
+        assert torch.equal(img2, bgimg) and g2.abs().sum() == 0
+        img3, _, st3 = run(d["scales"] * 3.0)  # repeated with the raised capacity
+        assert dmgs_b200.check_async()
+        assert torch.equal(img3, big_img)
+    finally:
+        dmgs_b200.configure(async_binning=False)
