@@ -92,7 +92,7 @@ blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
     const int count = s_max;
     if (count == 0) return;
 
-    float T = T_final, acc0 = 0, acc1 = 0, acc2 = 0, lc0 = 0, lc1 = 0, lc2 = 0, last_alpha = 0;
+    float T = T_final, behind = 0, last_cd = 0, last_alpha = 0;
     const int rounds = (count + BLK - 1) / BLK;
     for (int r = rounds - 1; r >= 0; --r) {
         const int idx = r * BLK + threadIdx.x;
@@ -119,11 +119,13 @@ blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
                     m &= ~(1u << jb);
                     const int j = s0 + jb;
                     const int pos = r * BLK + j;  // 0-based list position
-                    float v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                    // per-pixel work stops at cg = G * dL/dalpha and w = alpha * T; lanes that do not
+                    // contribute keep both at zero, so the products below need no other masking
+                    float cg = 0.0f, w = 0.0f;
                     bool hit = false;
+                    const float4 ra = lds128(a_ra + 16u * j), rb = lds128(a_rb + 16u * j);
+                    const float dx = ra.x - pxf, dy = ra.y - pyf;
                     if (pos < last) {
-                        const float4 ra = lds128(a_ra + 16u * j), rb = lds128(a_rb + 16u * j);
-                        const float dx = ra.x - pxf, dy = ra.y - pyf;
                         // same power / exp / alpha arithmetic as the forward (explicit _rn operations, immune
                         // to contraction): the contributor set is identical
                         const float q = fma_(__fmul_rn(rb.x, dy), dy, __fmul_rn(__fmul_rn(ra.z, dx), dx));
@@ -139,34 +141,22 @@ blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
                                 const float inv = rcp_nr(oma);
                                 const float t0 = T * inv;  // T / (1 - alpha), residual-corrected: the error must
                                 T = fma_(fma_(-t0, oma, T), inv, t0);  // not accumulate along the list
-                                const float w = alpha * T;
+                                w = alpha * T;
                                 const float4 c = lds128(a_rgb + 16u * j);
-                                const float om = 1.0f - last_alpha;
-                                acc0 = fma_(last_alpha, lc0, om * acc0);
-                                acc1 = fma_(last_alpha, lc1, om * acc1);
-                                acc2 = fma_(last_alpha, lc2, om * acc2);
-                                lc0 = c.x; lc1 = c.y; lc2 = c.z;
-                                float dL_dalpha = (c.x - acc0) * dp0;
-                                dL_dalpha = fma_(c.y - acc1, dp1, dL_dalpha);
-                                dL_dalpha = fma_(c.z - acc2, dp2, dL_dalpha);
-                                v[6] = w * dp0; v[7] = w * dp1; v[8] = w * dp2;
+                                // colour behind this entry enters only through its dot product with dL/dpixel
+                                const float cd = fma_(c.z, dp2, fma_(c.y, dp1, c.x * dp0));
+                                behind = fma_(last_alpha, last_cd, (1.0f - last_alpha) * behind);
+                                last_cd = cd;
                                 last_alpha = alpha;
-                                dL_dalpha = fma_(bgT, inv, dL_dalpha * T);
-                                const float dL_dG = rb.y * dL_dalpha;
-                                const float gdx = G * dx, gdy = G * dy;
-                                const float dG_ddelx = fma_(-gdy, ra.w, -gdx * ra.z);
-                                const float dG_ddely = fma_(-gdx, ra.w, -gdy * rb.x);
-                                const float hg = -0.5f * dL_dG;
-                                v[0] = (dL_dG * dG_ddelx) * ddelx_dx;
-                                v[1] = (dL_dG * dG_ddely) * ddely_dy;
-                                v[2] = (hg * gdx) * dx;
-                                v[3] = (hg * gdx) * dy;
-                                v[4] = (hg * gdy) * dy;
-                                v[5] = G * dL_dalpha;
+                                cg = G * fma_(bgT, inv, (cd - behind) * T);
                             }
                         }
                     }
                     if (!__any_sync(0xffffffffu, hit)) continue;
+                    // moments of cg about the Gaussian's centre (the flush below turns the tile's sums into
+                    // dL/dmean2D and dL/dconic) and the colour gradient
+                    const float cgx = cg * dx, cgy = cg * dy;
+                    float v[9] = {cgx, cgy, cgx * dx, cgx * dy, cgy * dy, cg, w * dp0, w * dp1, w * dp2};
                     tr_reduce<9, 16>(v, lane);
                     if (owner) reds_add(a_acc + 48u * j, v[0]);
                 }
@@ -175,10 +165,18 @@ blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
         __syncthreads();
         // flush the round's tile-level sums: three 16-byte vector reductions per touched Gaussian
         if (idx < count) {
-            const float4 g0 = s_acc[3 * threadIdx.x], g1 = s_acc[3 * threadIdx.x + 1], g2 = s_acc[3 * threadIdx.x + 2];
+            float4 g0 = s_acc[3 * threadIdx.x], g1 = s_acc[3 * threadIdx.x + 1];
+            const float4 g2 = s_acc[3 * threadIdx.x + 2];
             const bool nz = g0.x != 0.0f || g0.y != 0.0f || g0.z != 0.0f || g0.w != 0.0f || g1.x != 0.0f || g1.y != 0.0f ||
                             g1.z != 0.0f || g1.w != 0.0f || g2.x != 0.0f;
             if (nz) {
+                // moments -> gradients: dG/ddelta = -G (A dx + B dy, B dx + C dy), dG/dconic = -0.5 G (dx^2, dx dy, dy^2)
+                const float4 ra = s_ra[threadIdx.x], rb = s_rb[threadIdx.x];
+                const float opx = -rb.y * ddelx_dx, opy = -rb.y * ddely_dy, oph = -0.5f * rb.y;
+                const float mx = g0.x, my = g0.y;
+                g0.x = opx * fma_(ra.w, my, ra.z * mx);
+                g0.y = opy * fma_(rb.x, my, ra.w * mx);
+                g0.z *= oph; g0.w *= oph; g1.x *= oph;
                 float *dst = grad_blend + 12 * (size_t)s_id[threadIdx.x];
                 red_global_v4(dst, g0);
                 red_global_v4(dst + 4, g1);

@@ -18,7 +18,12 @@ struct BlendArgs {
 // Shared-memory reads in the inner loops go through explicit 32-bit shared addresses: with C++
 // indexing nvcc rebuilds the cluster-window base (S2UR SR_CgaCtaId + ULEA) inside the hot loop,
 // ~12 instructions and a scoreboard stall per entry (profiles/r1a).
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t smem_addr(const void *p)
+{
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p), r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(a));  // volatile: the value is kept in a register, never rematerialised
+    return r;
+}
 __device__ __forceinline__ float4 lds128(uint32_t a)
 {
     float4 v;
@@ -60,14 +65,15 @@ __device__ __forceinline__ bool cull_rect(float gx, float gy, float A, float B, 
     if (dx != 0.0f || dy != 0.0f) {
         qmin = 3.0e38f;
         if (dx != 0.0f) {  // vertical edge x = cx: minimise over y in [y0, y1]
-            const float ys = gy + (B * dx) / C;  // stationary point of q along the edge
+            const float ys = gy + __fdividef(B * dx, C);  // stationary point of q along the edge (an approximate
+            // quotient moves the evaluation point by < 1e-3 px: q changes by < C * 1e-6, inside the margin below)
             const float dyc = gy - fminf(fmaxf(ys, y0), y1);
             const float t0 = A * dx * dx, t1 = 2.0f * B * dx * dyc, t2 = C * dyc * dyc;
             qmin = t0 + t1 + t2;
             mag = t0 + fabsf(t1) + t2;
         }
         if (dy != 0.0f) {  // horizontal edge y = cy
-            const float xs = gx + (B * dy) / A;
+            const float xs = gx + __fdividef(B * dy, A);
             const float dxc = gx - fminf(fmaxf(xs, x0), x1);
             const float t0 = A * dxc * dxc, t1 = 2.0f * B * dxc * dy, t2 = C * dy * dy;
             const float q2 = t0 + t1 + t2;
