@@ -110,6 +110,30 @@ def test_multiview_accumulate_equals_sum_of_views():
         grad_close(a.reshape(P, -1), b.reshape(P, -1), rtol=2e-4, name=name)
 
 
+def test_view_streams_equal_single_stream():
+    """Views of a step on two CUDA streams (one accumulator each) give the single-stream sum."""
+    from dmgs_b200 import multiview as MV
+    from gpu_util import settings_for
+    P, W, H, NV = 5000, 160, 120, 5
+    cl = S.random_cloud(P, seed=9, extent=1.0, log_scale_mean=math.log(0.05))
+    d = {k: v.cuda() for k, v in cl.items()}
+    sets = [settings_for(S.nerf_synthetic_camera(v, W, H), (0, 0, 0)) for v in range(NV)]
+    dLs = [torch.randn(3, H, W, generator=torch.Generator().manual_seed(v)).cuda() for v in range(NV)]
+    inputs = dict(means3D=d["means3D"], opacities=d["opacities"], shs=d["shs"], scales=d["scales"], rotations=d["rotations"])
+    out = []
+    for n in (1, 2):
+        vs = MV.ViewStreams(P, MV.RASTER_WIDTHS_SH, torch.device("cuda"), n=n)
+        for _ in range(2):  # twice: begin() must reset every accumulator
+            vs.begin()
+            for v in range(NV):
+                vs.run(v, lambda acc, v=v: MV.accumulate_view(sets[v], inputs, lambda img: (None, dLs[v]), acc))
+            buf = vs.finish()
+        torch.cuda.synchronize()
+        out.append({k: x.cpu().numpy().copy() for k, x in buf.views.items()})
+    for name in out[0]:
+        grad_close(out[1][name].reshape(P, -1), out[0][name].reshape(P, -1), rtol=2e-4, name=name)
+
+
 def test_async_binning_matches_sync_and_reports_overflow():
     """configure(async_binning=True): same image / gradients without the host read-back; a frame whose
     instance list outgrows the remembered capacity renders as background, check_async() reports it,
