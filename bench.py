@@ -313,7 +313,7 @@ def run_ours(args):
         staged.release(slot)
         return host_loss
 
-    Ke = max(2, K // 2)
+    Ke = max(3, K)  # the first step's copy is exposed (pipeline fill), later copies hide behind the previous step
     for i in range(2):
         e2e_step(i, last=(i == 1))
     torch.cuda.synchronize()

@@ -23,6 +23,13 @@ class DmgsParams(C.Structure):
                 ("campos", C.c_float * 3)]
 
 
+class AdamSegment(C.Structure):
+    """struct dmgs_adam_segment (include/dmgs_raster.h)."""
+
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("n", C.c_int64), ("lr", C.c_double), ("lr_hi", C.c_double), ("period", C.c_int32), ("split", C.c_int32)]
+
+
 _lib = None
 
 _vp, _i32, _i64, _f = C.c_void_p, C.c_int32, C.c_int64, C.c_float
@@ -42,6 +49,12 @@ _SIGS = {
     "dmgs_mark_visible": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp]),
     "dmgs_bind_forward": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _f, _f, _vp, _i32, _vp, _vp, _vp, _vp]),
     "dmgs_bind_backward": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _f, _f, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dmgs_l1_ssim_scratch_bytes": (C.c_size_t, [_i32, _i32, _i32]),
+    "dmgs_l1_ssim_forward": (C.c_int, [_i32, _i32, _i32, C.POINTER(_f), _vp, _vp, _vp, _vp, _vp]),
+    "dmgs_l1_ssim_backward": (C.c_int, [_i32, _i32, _i32, C.POINTER(_f), _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dmgs_frustum_scratch_bytes": (C.c_size_t, [_i64]),
+    "dmgs_in_frustum": (C.c_int, [_i64, C.POINTER(_f), _f, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dmgs_adam_step": (C.c_int, [_i32, C.POINTER(AdamSegment), C.c_double, C.c_double, C.c_double, _i64, _f, _i32, _vp]),
     "dmgs_geom_layout": (C.c_int, [_i32, C.POINTER(_i64)]),
     "dmgs_binning_layout": (C.c_int, [_i32, _i64, _i32, _i32, C.POINTER(_i64)]),
     "dmgs_image_layout": (C.c_int, [_i32, _i32, C.POINTER(_i64)]),

@@ -305,6 +305,49 @@ int dmgs_bind_backward(int64_t F, int32_t k, const float *verts, const int64_t *
                            dg, (cudaStream_t)stream);
 }
 
+// ---- rows next to the path -------------------------------------------------
+size_t dmgs_l1_ssim_scratch_bytes(int32_t planes, int32_t H, int32_t W)
+{
+    return loss_scratch_bytes(planes > 0 ? planes : 1, H > 0 ? H : 1, W > 0 ? W : 1);
+}
+
+int dmgs_l1_ssim_forward(int32_t planes, int32_t H, int32_t W, const float *window11_host, const float *img,
+                         const float *gt, void *scratch, float *out_means, void *stream)
+{
+    if (planes <= 0 || H <= 0 || W <= 0 || planes > 65535) { set_error("l1_ssim: bad shape [%d,%d,%d]", planes, H, W); return -10; }
+    if (!window11_host || !img || !gt || !scratch || !out_means) { set_error("l1_ssim: NULL pointer"); return -6; }
+    return launch_l1_ssim_fwd(planes, H, W, window11_host, img, gt, scratch, out_means, (cudaStream_t)stream);
+}
+
+int dmgs_l1_ssim_backward(int32_t planes, int32_t H, int32_t W, const float *window11_host, const float *img,
+                          const float *gt, const void *scratch, const float *upstream, float *grad, void *stream)
+{
+    if (planes <= 0 || H <= 0 || W <= 0 || planes > 65535) { set_error("l1_ssim: bad shape [%d,%d,%d]", planes, H, W); return -10; }
+    if (!window11_host || !img || !gt || !scratch || !upstream || !grad) { set_error("l1_ssim: NULL pointer"); return -6; }
+    return launch_l1_ssim_bwd(planes, H, W, window11_host, img, gt, scratch, upstream, grad, (cudaStream_t)stream);
+}
+
+size_t dmgs_frustum_scratch_bytes(int64_t N) { return frustum_scratch_bytes(N > 0 ? N : 1); }
+
+int dmgs_in_frustum(int64_t N, const float *proj16_host, float cube_len, int32_t has_cube, int32_t piece_id,
+                    int32_t n_piece, const float *pts, const int64_t *faces, uint8_t *mask, int64_t *faces_out,
+                    int32_t *index_out, int32_t *count_out, void *scratch, void *stream)
+{
+    if (N < 0 || N >= ((int64_t)1 << 31)) { set_error("in_frustum: N out of range"); return -10; }
+    if (!proj16_host || (N > 0 && (!pts || !mask))) { set_error("in_frustum: NULL pointer"); return -6; }
+    if (count_out && !scratch) { set_error("in_frustum: compaction needs the scratch buffer"); return -6; }
+    if (faces_out && !faces) { set_error("in_frustum: faces_out needs faces"); return -6; }
+    return launch_frustum(N, proj16_host, cube_len, has_cube, piece_id, n_piece, pts, faces, mask, faces_out, index_out,
+                          count_out, scratch, (cudaStream_t)stream);
+}
+
+int dmgs_adam_step(int32_t nseg, const dmgs_adam_segment *segments_host, double beta1, double beta2, double eps,
+                   int64_t step, float grad_scale, int32_t zero_grad, void *stream)
+{
+    if (!segments_host) { set_error("adam: NULL segments"); return -6; }
+    return launch_adam(nseg, segments_host, beta1, beta2, eps, step, grad_scale, zero_grad, (cudaStream_t)stream);
+}
+
 int dmgs_sorted_keys(const void *geom, const void *binning, int32_t P, int64_t R, int32_t W, int32_t H,
                      uint64_t *keys_out, void *stream)
 {

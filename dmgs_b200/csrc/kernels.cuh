@@ -48,6 +48,23 @@ int launch_blend_bwd(const dmgs_params *prm, const void *geom, const GeomLayout 
                      const BinLayout &BL, const void *image, const ImgLayout &IL, const float *dL_dpix,
                      float *grad_blend, cudaStream_t s);
 
+// loss.cu
+size_t loss_scratch_bytes(int planes, int H, int W);
+int launch_l1_ssim_fwd(int planes, int H, int W, const float *window11, const float *img, const float *gt,
+                       void *scratch, float *out_means, cudaStream_t s);
+int launch_l1_ssim_bwd(int planes, int H, int W, const float *window11, const float *img, const float *gt,
+                       const void *scratch, const float *upstream, float *grad, cudaStream_t s);
+
+// frustum.cu
+size_t frustum_scratch_bytes(int64_t N);
+int launch_frustum(int64_t N, const float *proj16_host, float cube_len, int has_cube, int piece_id, int n_piece,
+                   const float *pts, const int64_t *faces, uint8_t *mask, int64_t *faces_out, int32_t *index_out,
+                   int32_t *count_out, void *scratch, cudaStream_t s);
+
+// adam.cu
+int launch_adam(int nseg, const dmgs_adam_segment *segs, double beta1, double beta2, double eps, int64_t step,
+                float grad_scale, int zero_grad, cudaStream_t s);
+
 // binding.cu
 int launch_bind_fwd(int64_t F, int k, const float *verts, const int64_t *faces, const float *bc, float rad_base,
                     float thin_z, const float *g, int adaptive, float *xyz, float *cov6, float *rot_t2w, cudaStream_t s);

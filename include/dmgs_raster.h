@@ -129,6 +129,53 @@ int dmgs_bind_backward(int64_t F, int32_t k, const float *verts, const int64_t *
                        float rad_base, float thin_z, const float *g, int32_t adaptive, const float *dL_dxyz,
                        const float *dL_dcov6, const float *dL_drot, float *dverts, float *dg, void *stream);
 
+/* ==== rows next to the path ========================================== */
+
+/* ---- fused L1 + SSIM image loss (utils/loss_utils.py:17-18 l1_loss, :35-63 ssim/_ssim; caller
+ *      train_geo_stage2.py:115-116).  img, gt: [planes,H,W] fp32 (planes = batch x channels);
+ * window11_host: the 11 normalised Gaussian taps (loss_utils.py:23-25, sigma 1.5) as HOST floats.
+ * forward: out_means[planes][2] = {mean |img-gt|, mean ssim_map} per plane; fills `scratch`
+ * (dmgs_l1_ssim_scratch_bytes) with the derivative fields the backward convolves.
+ * backward: upstream[planes][2] (DEVICE) = dLoss/d(l1 mean), dLoss/d(ssim mean) per plane, already
+ * divided by H*W; grad [planes,H,W] is overwritten.                                          */
+size_t dmgs_l1_ssim_scratch_bytes(int32_t planes, int32_t H, int32_t W);
+int dmgs_l1_ssim_forward(int32_t planes, int32_t H, int32_t W, const float *window11_host, const float *img,
+                         const float *gt, void *scratch, float *out_means, void *stream);
+int dmgs_l1_ssim_backward(int32_t planes, int32_t H, int32_t W, const float *window11_host, const float *img,
+                          const float *gt, const void *scratch, const float *upstream, float *grad, void *stream);
+
+/* ---- view-frustum test + ordered compaction of the visible faces
+ *      (in_frustum: scene/gaussian_geo_model_finetune.py:33-48, COLMAP variant
+ *      scene/gaussian_geo_model_mlp_flex_colmap.py:32-76; use at finetune.py:405-409).
+ * proj16_host: the [4,4] full_proj_transform, row-major, HOST floats (points are right-multiplied).
+ * has_cube / cube_len / piece_id / n_piece: the COLMAP variant's arguments (has_cube = 0, piece_id = -1
+ * for the stage-3 variant).  faces == NULL: `pts` [N,3] are the query points themselves; otherwise
+ * the query points are the centroids verts[faces].mean(1) of the N int64 faces over pts = verts.
+ * mask: uint8 [N] (torch.bool layout).  Compaction (optional, count_out != NULL): count_out (DEVICE
+ * int32) = number of visible items, faces_out [count,3] = faces[mask] (needs faces), index_out
+ * [count] = their indices (either may be NULL); scratch: dmgs_frustum_scratch_bytes(N).       */
+size_t dmgs_frustum_scratch_bytes(int64_t N);
+int dmgs_in_frustum(int64_t N, const float *proj16_host, float cube_len, int32_t has_cube, int32_t piece_id,
+                    int32_t n_piece, const float *pts, const int64_t *faces, uint8_t *mask, int64_t *faces_out,
+                    int32_t *index_out, int32_t *count_out, void *scratch, void *stream);
+
+/* ---- fused multi-tensor Adam step (torch.optim.Adam(l, lr=0.0, eps=1e-15) with one group per tensor:
+ *      scene/gaussian_geo_model_finetune.py:526-537, step at train_geo_stage3.py:164-166).
+ * One launch updates up to DMGS_ADAM_MAX_SEGMENTS tensors; all arrays fp32, 16-byte aligned.
+ * Elements with (i % period) >= split use lr_hi (period == 0: lr for every element) -- e.g. the
+ * [P,16,3] SH tensor whose DC and rest coefficients have different learning rates.
+ * grad is read as grad * grad_scale (view averaging) and set to zero afterwards when zero_grad != 0.
+ * step counts from 1 (torch's state['step'] after the increment).                             */
+#define DMGS_ADAM_MAX_SEGMENTS 8
+typedef struct dmgs_adam_segment {
+    float *param, *grad, *exp_avg, *exp_avg_sq;
+    int64_t n;
+    double lr, lr_hi;
+    int32_t period, split;
+} dmgs_adam_segment;
+int dmgs_adam_step(int32_t nseg, const dmgs_adam_segment *segments_host, double beta1, double beta2, double eps,
+                   int64_t step, float grad_scale, int32_t zero_grad, void *stream);
+
 /* ---- inspection (parity tests): byte offsets of the named arrays inside the state buffers.
  * geom:    [0] depths f32[P]  [1] rec f32[P][8]={x,y,conA,conB,conC,opacity,cut,_}  [2] rgb f32[P][4]
  *          [3] clamped u8[P] (bit ch)  [4] cov3D f32[P][6]  [5] tiles_touched u32[P]
