@@ -35,48 +35,56 @@ struct AdamArgs {
     int zero_grad;
 };
 
+__device__ __forceinline__ void adam_update(const AdamArgs &a, const AdamSeg &sg, long long i, int k, float &p, float g,
+                                            float &m, float &v, uint32_t ph)
+{
+    const float gk = g * a.grad_scale;
+    m = fma_(a.one_minus_b1, gk - m, m);
+    v = fma_(a.one_minus_b2 * gk, gk, v * a.b2);
+    const float denom = sqrtf(v) / a.sqrt_bc2 + a.eps;
+    const float st = (sg.period > 0 && (ph + k) % (uint32_t)sg.period >= (uint32_t)sg.split) ? sg.step_hi : sg.step_lo;
+    p = p - st * (m / denom);
+}
+
 __global__ void __launch_bounds__(256, 4)
 adam_kernel(const __grid_constant__ AdamArgs a)
 {
-    // blockIdx.y = segment; every thread handles 4 consecutive elements (arrays are 16-byte aligned:
-    // FlatGradBuffer fields are)
+    // blockIdx.y = segment; every thread handles two float4 groups per iteration, all eight 16-byte loads
+    // issued before the first store (arrays are 16-byte aligned: FlatGradBuffer fields are)
     const AdamSeg &sg = a.seg[blockIdx.y];
-    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < sg.n;
-         i += (long long)gridDim.x * blockDim.x * 4) {
-        const int cnt = (int)min((long long)4, sg.n - i);
-        float p[4], g[4], m[4], v[4];
+    const long long n4 = sg.n >> 2, stride = (long long)gridDim.x * blockDim.x;
+    float4 *P = reinterpret_cast<float4 *>(sg.p), *G = reinterpret_cast<float4 *>(sg.g);
+    float4 *M = reinterpret_cast<float4 *>(sg.m), *V = reinterpret_cast<float4 *>(sg.v);
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += 2 * stride) {
+        const long long q1 = q + stride;
+        const bool two = q1 < n4;
+        float4 p0 = P[q], g0 = G[q], m0 = M[q], v0 = V[q], p1, g1, m1, v1;
+        if (two) { p1 = P[q1]; g1 = G[q1]; m1 = M[q1]; v1 = V[q1]; }
+        const uint32_t ph0 = sg.period > 0 ? (uint32_t)((unsigned long long)(4 * q) % (unsigned)sg.period) : 0u;
+        adam_update(a, sg, 4 * q, 0, p0.x, g0.x, m0.x, v0.x, ph0);
+        adam_update(a, sg, 4 * q, 1, p0.y, g0.y, m0.y, v0.y, ph0);
+        adam_update(a, sg, 4 * q, 2, p0.z, g0.z, m0.z, v0.z, ph0);
+        adam_update(a, sg, 4 * q, 3, p0.w, g0.w, m0.w, v0.w, ph0);
+        P[q] = p0; M[q] = m0; V[q] = v0;
+        if (a.zero_grad) G[q] = make_float4(0, 0, 0, 0);
+        if (two) {
+            const uint32_t ph1 = sg.period > 0 ? (uint32_t)((unsigned long long)(4 * q1) % (unsigned)sg.period) : 0u;
+            adam_update(a, sg, 4 * q1, 0, p1.x, g1.x, m1.x, v1.x, ph1);
+            adam_update(a, sg, 4 * q1, 1, p1.y, g1.y, m1.y, v1.y, ph1);
+            adam_update(a, sg, 4 * q1, 2, p1.z, g1.z, m1.z, v1.z, ph1);
+            adam_update(a, sg, 4 * q1, 3, p1.w, g1.w, m1.w, v1.w, ph1);
+            P[q1] = p1; M[q1] = m1; V[q1] = v1;
+            if (a.zero_grad) G[q1] = make_float4(0, 0, 0, 0);
+        }
+    }
+    // the last n % 4 elements
+    if (blockIdx.x == 0 && threadIdx.x < (sg.n & 3)) {
+        const long long i = (n4 << 2) + threadIdx.x;
         const uint32_t ph = sg.period > 0 ? (uint32_t)((unsigned long long)i % (unsigned)sg.period) : 0u;
-        if (cnt == 4) {
-            const float4 P4 = *reinterpret_cast<const float4 *>(sg.p + i), G4 = *reinterpret_cast<const float4 *>(sg.g + i);
-            const float4 M4 = *reinterpret_cast<const float4 *>(sg.m + i), V4 = *reinterpret_cast<const float4 *>(sg.v + i);
-            p[0] = P4.x; p[1] = P4.y; p[2] = P4.z; p[3] = P4.w;
-            g[0] = G4.x; g[1] = G4.y; g[2] = G4.z; g[3] = G4.w;
-            m[0] = M4.x; m[1] = M4.y; m[2] = M4.z; m[3] = M4.w;
-            v[0] = V4.x; v[1] = V4.y; v[2] = V4.z; v[3] = V4.w;
-        } else {
-            for (int k = 0; k < cnt; ++k) { p[k] = sg.p[i + k]; g[k] = sg.g[i + k]; m[k] = sg.m[i + k]; v[k] = sg.v[i + k]; }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (k >= cnt) break;
-            const float gk = g[k] * a.grad_scale;
-            m[k] = fma_(a.one_minus_b1, gk - m[k], m[k]);
-            v[k] = fma_(a.one_minus_b2 * gk, gk, v[k] * a.b2);
-            const float denom = sqrtf(v[k]) / a.sqrt_bc2 + a.eps;
-            const float st = (sg.period > 0 && (ph + k) % (uint32_t)sg.period >= (uint32_t)sg.split) ? sg.step_hi : sg.step_lo;
-            p[k] = p[k] - st * (m[k] / denom);
-        }
-        if (cnt == 4) {
-            *reinterpret_cast<float4 *>(sg.p + i) = make_float4(p[0], p[1], p[2], p[3]);
-            *reinterpret_cast<float4 *>(sg.m + i) = make_float4(m[0], m[1], m[2], m[3]);
-            *reinterpret_cast<float4 *>(sg.v + i) = make_float4(v[0], v[1], v[2], v[3]);
-            if (a.zero_grad) *reinterpret_cast<float4 *>(sg.g + i) = make_float4(0, 0, 0, 0);
-        } else {
-            for (int k = 0; k < cnt; ++k) {
-                sg.p[i + k] = p[k]; sg.m[i + k] = m[k]; sg.v[i + k] = v[k];
-                if (a.zero_grad) sg.g[i + k] = 0.0f;
-            }
-        }
+        float p = sg.p[i], m = sg.m[i], v = sg.v[i];
+        adam_update(a, sg, i, 0, p, sg.g[i], m, v, ph);
+        sg.p[i] = p; sg.m[i] = m; sg.v[i] = v;
+        if (a.zero_grad) sg.g[i] = 0.0f;
     }
 }
 

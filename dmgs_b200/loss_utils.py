@@ -103,3 +103,37 @@ def l1_ssim_loss(image, gt, lambda_dssim: float = 0.2):
     """(1 - lambda) * l1_loss + lambda * (1 - ssim)  (train_geo_stage2.py:115-116)."""
     m = l1_ssim_means(image, gt).mean(0)
     return (1.0 - lambda_dssim) * m[0] + lambda_dssim * (1.0 - m[1])
+
+
+_UP = {}
+
+
+def l1_ssim_loss_and_grad(image, gt, lambda_dssim: float = 0.2, need_loss: bool = True):
+    """(loss, dloss/dimage) of ``l1_ssim_loss`` without the autograd round trip: three kernel launches
+    (forward, the fixed-order reduction, backward).  This is the ``image_grad`` callback of the
+    view-batched training step (multiview.accumulate_view).  loss is None when need_loss is False."""
+    if image.device.type != "cuda":
+        raise RuntimeError("dmgs_b200 loss needs CUDA tensors; there is no CPU path")
+    B, Cn, H, W = _planes(image)
+    planes = B * Cn
+    x, y = image.detach().float().contiguous(), gt.detach().float().contiguous()
+    lib, dev = L.lib(), image.device
+    scratch = torch.empty(lib.dmgs_l1_ssim_scratch_bytes(planes, H, W), dtype=torch.uint8, device=dev)
+    means = torch.empty(planes, 2, dtype=torch.float32, device=dev)
+    key = (dev.index, planes, H, W, float(lambda_dssim))
+    up = _UP.get(key)
+    if up is None:  # d loss / d (per-plane means), divided by the pixel count: constants of the shape
+        up = torch.tensor([(1.0 - lambda_dssim) / planes / (H * W), -lambda_dssim / planes / (H * W)],
+                          dtype=torch.float32).repeat(planes, 1).to(dev)
+        _UP[key] = up
+    grad = torch.empty_like(x)
+    st = _stream()
+    L.check(lib.dmgs_l1_ssim_forward(planes, H, W, _window11(), L.ptr(x), L.ptr(y), L.ptr(scratch), L.ptr(means), st),
+            "dmgs_l1_ssim_forward")
+    L.check(lib.dmgs_l1_ssim_backward(planes, H, W, _window11(), L.ptr(x), L.ptr(y), L.ptr(scratch), L.ptr(up), L.ptr(grad),
+                                      st), "dmgs_l1_ssim_backward")
+    loss = None
+    if need_loss:
+        m = means.mean(0)
+        loss = (1.0 - lambda_dssim) * m[0] + lambda_dssim * (1.0 - m[1])
+    return loss, grad

@@ -32,6 +32,8 @@ def test_loss_matches_reference_golden(tag):
     got = img.grad.cpu().numpy()
     assert np.linalg.norm(got - ref) <= 1e-4 * np.linalg.norm(ref)  # gradients: 1e-4 relative
     assert np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max()
+    l2, g2 = LU.l1_ssim_loss_and_grad(img.detach(), gt, 0.2)  # the no-autograd path gives the same numbers
+    assert abs(l2.item() - loss.item()) <= 1e-7 and torch.allclose(g2, img.grad, rtol=1e-6, atol=1e-12)
     # separate pieces: the L1 gradient is exact (sign / N, zero on exact ties)
     img.grad = None
     LU.l1_loss(img, gt).backward()
