@@ -53,38 +53,78 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock and throttle reasons sampled every ~10 ms (NVML, in-process thread) while the timed region
+    runs; falls back to `nvidia-smi -lms` when NVML cannot be loaded."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake"}
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.rows, self.proc, self.h, self.stop_flag, self.thread = index, [], None, None, False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((mhz, rs))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def start(self):
+        if self.h is not None:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            threading.Thread(target=self._read_smi, daemon=True).start()
         except OSError:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _read_smi(self):
+        for ln in self.proc.stdout:
+            c = [x.strip() for x in ln.split(",")]
+            if c and c[0].replace(".", "").isdigit():
+                bits = sum(b for b, col in ((0x8, 2), (0x40, 3), (0x20, 4), (0x4, 5)) if len(c) > col and c[col] == "Active")
+                self.max_mhz = float(c[1]) if len(c) > 1 and c[1].replace(".", "").isdigit() else None
+                self.rows.append((float(c[0]), bits))
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k] == "Active" for r in self.rows)]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+        if self.h is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+        elif self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
+        sm = sorted(r[0] for r in self.rows)
+        bits = 0
+        for _, b in self.rows:
+            bits |= b
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": getattr(self, "max_mhz", None),
+                "reasons": [n for b, n in self.REASONS.items() if bits & b], "samples": len(sm),
+                "source": "nvml, 10 ms period" if self.h is not None else "nvidia-smi -lms 100"}
 
 
 def oracle_frame(O, pr, cl_np, dL):
