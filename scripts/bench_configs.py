@@ -1,0 +1,118 @@
+"""Supplementary measurements of the other BASELINE.json configurations (bench.py's line stays H0):
+  c2   stage-2 training step on a mesh-bound cloud (~300 k Gaussians, 800x800): binding -> render_dyn with
+       fused sigmoid-SH -> fused L1+SSIM -> backward -> binding backward -> fused Adam, per-stage CUDA-event times
+  c5   forward-only render sweep, 100 k .. 6 M Gaussians at 800x800 and 1920x1080 (torch.no_grad)
+One JSON line per measurement.  python scripts/bench_configs.py [c2] [c5]"""
+import json, math, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import dmgs_b200
+from dmgs_b200 import GaussianRasterizationSettings, loss_utils as LU, synthetic as S
+from dmgs_b200.binding import bind_faces
+from dmgs_b200.optim import FusedAdam
+from dmgs_b200.rasterizer import rasterize_backward, rasterize_forward
+
+dev = torch.device("cuda", 0)
+which = set(sys.argv[1:]) or {"c2", "c5"}
+dmgs_b200.configure(async_binning=True)
+
+
+def settings(cam, bg, deg=3):
+    return GaussianRasterizationSettings(cam.image_height, cam.image_width, math.tan(cam.FoVx / 2), math.tan(cam.FoVy / 2),
+                                         bg, 1.0, cam.world_view_transform.to(dev), cam.full_proj_transform.to(dev), deg,
+                                         cam.camera_center.to(dev), False, False)
+
+
+def ev():
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+if "c2" in which:
+    m = S.mesh_bound_inputs(50_000, 6, seed=1)
+    verts = m["verts"].to(dev).requires_grad_()
+    faces, bc = m["faces"].to(dev), m["bc"].to(dev)
+    feats = m["features"].to(dev).requires_grad_()
+    sf = torch.tensor([m["scale_factor"]], device=dev, requires_grad=True)
+    P = faces.shape[0] * m["k"]
+    op = torch.full((P, 1), 0.9999, device=dev)
+    W = H = 800
+    cams = [S.nerf_synthetic_camera(i, W, H) for i in range(8)]
+    bg = torch.ones(3, device=dev)
+    sets = [settings(c, bg) for c in cams]
+    gts = [torch.rand(3, H, W, generator=torch.Generator().manual_seed(i)).to(dev) for i in range(8)]
+    opt = FusedAdam([{"params": [verts.detach()], "lr": 1e-5, "name": "verts"},
+                     {"params": [feats.detach()], "lr": 2.5e-3, "name": "features"},
+                     {"params": [sf.detach()], "lr": 1e-3, "name": "scale_factor"}], lr=0.0, eps=1e-15)
+    names = ["bind_fwd", "render_fwd", "loss_fwd_bwd", "render_bwd", "bind_bwd", "adam"]
+    acc = {n: 0.0 for n in names}
+
+    def step(i, rec):
+        v = verts.detach().requires_grad_()
+        s = sf.detach().requires_grad_()
+        e = [ev()]
+        xyz, cov = bind_faces(v, faces, bc, m["rad_base"], m["spatial_lr_scale"] * 1e-6, s, 2.0)
+        e.append(ev())
+        color, radii, st = rasterize_forward(sets[i % 8], xyz.detach(), op, feats.detach(), None, None, None, cov.detach(),
+                                             sh_layout=1, sh_activation=1)
+        e.append(ev())
+        _, dL = LU.l1_ssim_loss_and_grad(color, gts[i % 8], 0.2, need_loss=False)
+        e.append(ev())
+        g = rasterize_backward(st, dL, xyz.detach(), feats.detach(), None, None, cov.detach(), False)
+        e.append(ev())
+        torch.autograd.backward([xyz, cov], [g[0], g[7]])
+        e.append(ev())
+        opt.step(grads={"verts": v.grad, "features": g[2], "scale_factor": s.grad})
+        e.append(ev())
+        if rec:
+            torch.cuda.synchronize()
+            for n, a, b in zip(names, e[:-1], e[1:]):
+                acc[n] += a.elapsed_time(b)
+        return st
+
+    for i in range(5):
+        step(i, False)
+    dmgs_b200.check_async()
+    torch.cuda.synchronize()
+    N = 24
+    t0 = ev()
+    for i in range(N):
+        st = step(i, False)
+    t1 = ev()
+    torch.cuda.synchronize()
+    total = t0.elapsed_time(t1) / N
+    for i in range(N):
+        step(i, True)
+    ok = dmgs_b200.check_async()
+    print(json.dumps({"config": "c2: stage-2 training step, mesh-bound (F=%d, k=6, P=%d), 800x800, fused sigmoid-SH, "
+                                "cov3D_precomp from the face frame, L1+SSIM loss, Adam" % (faces.shape[0], P),
+                      "ms_per_step": round(total, 4), "steps_per_s": round(1e3 / total, 1),
+                      "stage_ms": {n: round(acc[n] / N, 4) for n in names}, "R": st.num_rendered, "binning_fit": ok,
+                      "note": "stage times from a second pass with events + sync per step; ms_per_step is the free-running loop"}),
+          flush=True)
+
+if "c5" in which:
+    with torch.no_grad():
+        for (W, H) in [(800, 800), (1920, 1080)]:
+            cam = S.nerf_synthetic_camera(0, W, H)
+            rs = settings(cam, torch.zeros(3, device=dev))
+            for P in [100_000, 300_000, 1_000_000, 3_000_000, 6_000_000]:
+                cl = {k: v.to(dev) for k, v in S.random_cloud(P, seed=0, extent=1.3, log_scale_mean=math.log(0.01)).items()}
+                run = lambda: rasterize_forward(rs, cl["means3D"], cl["opacities"], cl["shs"], None, cl["scales"],
+                                                cl["rotations"], None)
+                for _ in range(4):
+                    st = run()[2]
+                dmgs_b200.check_async()
+                torch.cuda.synchronize()
+                n = 20
+                a = ev()
+                for _ in range(n):
+                    st = run()[2]
+                b = ev()
+                torch.cuda.synchronize()
+                ms = a.elapsed_time(b) / n
+                ok = dmgs_b200.check_async()
+                print(json.dumps({"config": f"c5: forward-only, {P} Gaussians SH-3, {W}x{H}", "ms_per_frame": round(ms, 4),
+                                  "frames_per_s": round(1e3 / ms, 1), "R": st.num_rendered, "binning_fit": ok}), flush=True)
+                del cl

@@ -52,3 +52,21 @@ def resident(n=5):
 
 h2d_only(); resident(); h2d_only()
 dmgs_b200.check_async()
+
+# ---- host-side enqueue time vs device time of the autograd path, and a cProfile of the host side
+import cProfile, pstats, io
+bufs = staged.acquire(0)
+def enqueue_only():
+    t = {k: bufs[k].detach().requires_grad_() for k in names}
+    for j in range(8):
+        m2d = torch.zeros_like(t["means3D"], requires_grad=True)
+        img, _ = GaussianRasterizer(sets[j])(means3D=t["means3D"], means2D=m2d, shs=t["shs"], opacities=t["opacities"],
+                                             scales=t["scales"], rotations=t["rotations"])
+        (img * dLs[j]).sum().backward()
+for _ in range(2): enqueue_only()
+torch.cuda.synchronize()
+t0 = time.perf_counter(); enqueue_only(); t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
+print(f"autograd path, 8 views: host enqueue {1e3*(t1-t0):.2f} ms, until device idle {1e3*(t2-t0):.2f} ms")
+pr = cProfile.Profile(); pr.enable(); enqueue_only(); pr.disable(); torch.cuda.synchronize()
+s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(28); print(s.getvalue()[:6000])
+dmgs_b200.check_async()
