@@ -219,8 +219,18 @@ def run_ours(args):
     dLs = [torch.randn(3, H, W, generator=gen).to(dev) for _ in range(min(n_views, 8))]
     # flat per-Gaussian gradient buffer (62 floats per Gaussian): the all-reduce payload
     # views of a step run round-robin on N_STREAMS CUDA streams (MV.ViewStreams), one accumulator each
-    vs = MV.ViewStreams(P, MV.RASTER_WIDTHS_SH, dev, n=N_STREAMS)
+    # N > 1: the summed buffer lives in symmetric memory and is exchanged over NVLink peer memory
+    # (dmgs_allreduce_peer; DMGS_BENCH_ALLREDUCE=nccl forces torch.distributed.all_reduce)
+    use_peer = world > 1 and os.environ.get("DMGS_BENCH_ALLREDUCE", "peer") != "nccl"
+    vs = MV.ViewStreams(P, MV.RASTER_WIDTHS_SH, dev, n=N_STREAMS, peer_group=dist.group.WORLD if use_peer else None)
     flat = vs.buf.flat
+    if world == 1:
+        allreduce_kind = "none (single GPU)"
+    elif vs.peer is not None:
+        mm = vs.peer.multicast_ptr and world >= vs.peer.MULTICAST_MIN_WORLD
+        allreduce_kind = "NVLink peer memory, " + ("NVSwitch multimem.ld_reduce/st" if mm else "P2P loads/stores")
+    else:
+        allreduce_kind = "NCCL all-reduce" + (f" (peer memory unavailable: {vs.peer_error})" if vs.peer_error else "")
     stage_ms, ev_log = {}, []
 
     def hook_factory(events):
@@ -265,7 +275,7 @@ def run_ours(args):
                 vs.run(j, lambda acc, j=j, v=v: one_view(j, v, False, acc))
             vs.finish()
         if world > 1:
-            dist.all_reduce(flat)
+            vs.all_reduce_()
         if not dmgs_b200.check_async():  # a frame overflowed its binning buffer: the step does not count
             stats["redone"] += 1
             if record:
@@ -371,7 +381,7 @@ def run_ours(args):
                 settings[v], inputs, lambda img: ((img * dl).sum(), dl), acc)[0]))
         vs.finish()
         if world > 1:
-            dist.all_reduce(flat)
+            vs.all_reduce_()
         host_loss = float(torch.stack(losses).sum().cpu())  # device -> host read of the step's result
         if not dmgs_b200.check_async():
             staged.ready[slot] = torch.cuda.Event()
@@ -433,7 +443,8 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": f"{args.workload.upper()}: {P} random Gaussians SH-3, {W}x{H}, shs+scales+rotations, fwd+bwd",
                    "views_per_rank_per_step": VIEWS_PER_RANK, "parallelism": f"views x{world} (replicated Gaussians, "
-                   "NCCL all-reduce of the flat gradient buffer once per step)" if world > 1 else "single GPU",
+                   "one all-reduce of the flat gradient buffer per step)" if world > 1 else "single GPU",
+                   "all_reduce": allreduce_kind,
                    "avg_instances_R": Ravg, "view_streams": N_STREAMS,
                    "stage_timing": "2 single-stream steps right after the timed region, CUDA events between stages",
                    "binning": "host read-back of the instance count every frame" if args.sync_binning else

@@ -348,6 +348,13 @@ int dmgs_adam_step(int32_t nseg, const dmgs_adam_segment *segments_host, double 
     return launch_adam(nseg, segments_host, beta1, beta2, eps, step, grad_scale, zero_grad, (cudaStream_t)stream);
 }
 
+int dmgs_allreduce_peer(int64_t n, int32_t world, int32_t rank, const void *const *peer_ptrs_host, void *multicast_ptr,
+                        float scale, void *stream)
+{
+    if (!peer_ptrs_host && !multicast_ptr) { set_error("allreduce_peer: no peer pointers"); return -6; }
+    return launch_allreduce_peer(n, world, rank, peer_ptrs_host, multicast_ptr, scale, (cudaStream_t)stream);
+}
+
 int dmgs_sorted_keys(const void *geom, const void *binning, int32_t P, int64_t R, int32_t W, int32_t H,
                      uint64_t *keys_out, void *stream)
 {

@@ -65,6 +65,10 @@ int launch_frustum(int64_t N, const float *proj16_host, float cube_len, int has_
 int launch_adam(int nseg, const dmgs_adam_segment *segs, double beta1, double beta2, double eps, int64_t step,
                 float grad_scale, int zero_grad, cudaStream_t s);
 
+// peer.cu
+int launch_allreduce_peer(int64_t n, int world, int rank, const void *const *peer_ptrs_host, void *multicast_ptr,
+                          float scale, cudaStream_t s);
+
 // binding.cu
 int launch_bind_fwd(int64_t F, int k, const float *verts, const int64_t *faces, const float *bc, float rad_base,
                     float thin_z, const float *g, int adaptive, float *xyz, float *cov6, float *rot_t2w, cudaStream_t s);

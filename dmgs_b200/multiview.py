@@ -41,7 +41,9 @@ class FlatGradBuffer:
     [P, ...] views.  The views are what `rasterize_backward(..., accumulate_into=views)` adds to and
     the flat tensor is the single all-reduce payload of a step."""
 
-    def __init__(self, P: int, widths: Dict[str, Tuple[int, ...]], device, dtype=torch.float32):
+    def __init__(self, P: int, widths: Dict[str, Tuple[int, ...]], device, dtype=torch.float32, allocate=None):
+        """allocate(numel) -> 1-D fp32 tensor: where the flat buffer lives (default: torch.zeros; the
+        peer-memory all-reduce passes a symmetric-memory allocator)."""
         self.P, self.widths = int(P), dict(widths)
         n = 0
         self.offsets: Dict[str, Tuple[int, int]] = {}
@@ -53,7 +55,8 @@ class FlatGradBuffer:
             n = (n + 3) // 4 * 4
             self.offsets[name] = (n, self.P * w)
             n += self.P * w
-        self.flat = torch.zeros(n, dtype=dtype, device=device)
+        n = (n + 3) // 4 * 4  # whole 16-byte groups: vector kernels (Adam, peer all-reduce) need no tail
+        self.flat = torch.zeros(n, dtype=dtype, device=device) if allocate is None else allocate(n)
         self.views = {name: self.flat[o:o + m].view(self.P, *self.widths[name]) for name, (o, m) in self.offsets.items()}
 
     def zero_(self):
@@ -103,6 +106,60 @@ class ViewParallel:
         return loss
 
 
+class PeerAllReduce:
+    """Sum of a flat fp32 buffer over the ranks of one box through NVLink peer memory, in place
+    (libdmgs_raster.so: dmgs_allreduce_peer) -- the gradient exchange of the view-partitioned step
+    without NCCL: rank r reduces slice r of every rank's buffer and writes the (scaled) sum back to
+    slice r of every rank's buffer; on NVSwitch systems with multicast the addition happens inside the
+    switch (multimem.ld_reduce / multimem.st).
+
+    The buffer lives in torch symmetric memory (`allocate` hands it to FlatGradBuffer); construction is
+    a collective (rendezvous).  `all_reduce_()` enqueues barrier -> kernel -> barrier on the current
+    stream; nothing synchronises with the host."""
+
+    MULTICAST_MIN_WORLD = 5  # measured on B200 x8 (profiles/r1_s6_allreduce.jsonl): P2P wins at 2 and 4 ranks, multimem at 8
+
+    def __init__(self, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self._symm, self.device = symm, device
+        self.group = group if group is not None else dist.group.WORLD
+        self.flat = self.hdl = None
+
+    def allocate(self, numel: int) -> torch.Tensor:
+        if self.flat is not None:
+            raise RuntimeError("PeerAllReduce serves one buffer")
+        self.flat = self._symm.empty(int(numel), dtype=torch.float32, device=self.device)
+        self.flat.zero_()
+        self.hdl = self._symm.rendezvous(self.flat, self.group)
+        self.world, self.rank = int(self.hdl.world_size), int(self.hdl.rank)
+        import ctypes as C
+        peers = [self.flat if k == self.rank else self.hdl.get_buffer(k, (int(numel),), torch.float32) for k in range(self.world)]
+        self._peers = peers  # keep the mappings alive
+        self._ptrs = (C.c_void_p * self.world)(*[p.data_ptr() for p in peers])
+        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+        if mc:
+            base = int(self.hdl.buffer_ptrs[self.rank])
+            mc += self.flat.data_ptr() - base  # the tensor's offset inside the symmetric allocation
+        self.multicast_ptr = mc
+        return self.flat
+
+    def all_reduce_(self, scale: float = 1.0, use_multicast: Optional[bool] = None):
+        """use_multicast: None = automatic (in-switch reduction from MULTICAST_MIN_WORLD ranks up: with few
+        ranks the peer loads/stores move as few bytes per link and were measured faster, see
+        profiles/), True / False force a path."""
+        import ctypes as C
+        from . import _lib as L
+        if use_multicast is None:
+            use_multicast = self.world >= self.MULTICAST_MIN_WORLD
+        mc = C.c_void_p(self.multicast_ptr) if (use_multicast and self.multicast_ptr) else None
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        self.hdl.barrier(channel=0)  # every rank's accumulator is complete
+        L.check(L.lib().dmgs_allreduce_peer(self.flat.numel(), self.world, self.rank, self._ptrs, mc, float(scale), st),
+                "dmgs_allreduce_peer")
+        self.hdl.barrier(channel=1)  # every slice has been delivered to every rank
+        return self.flat
+
+
 class ViewStreams:
     """Renders the local views of a step on `n` CUDA streams, round-robin, each stream accumulating into
     its own FlatGradBuffer; `finish()` joins the streams and sums the buffers into the first one.
@@ -114,10 +171,29 @@ class ViewStreams:
     per-Gaussian accumulators are read-modify-written without atomics by the per-Gaussian backward
     (one thread owns one row), hence one buffer per stream rather than one shared buffer."""
 
-    def __init__(self, P: int, widths: Dict[str, Tuple[int, ...]], device, n: int = 2):
+    def __init__(self, P: int, widths: Dict[str, Tuple[int, ...]], device, n: int = 2, peer_group=None):
+        """peer_group: a process group of ranks on ONE box -> the summed buffer lives in symmetric memory
+        and `all_reduce_()` exchanges it over NVLink peer memory (falls back to NCCL if symmetric memory
+        cannot be set up); None -> `all_reduce_()` is torch.distributed.all_reduce."""
         if n < 1:
             raise ValueError("need at least one stream")
-        self.bufs = [FlatGradBuffer(P, widths, device) for _ in range(n)]
+        self.peer, self.peer_error, self.group = None, None, peer_group
+        alloc = None
+        if peer_group is not None and dist.get_world_size(peer_group) > 1:
+            try:
+                self.peer = PeerAllReduce(device, peer_group)
+                probe = self.peer.allocate  # rendezvous happens on first allocation (collective)
+                alloc = probe
+            except Exception as e:  # symmetric memory unavailable: NCCL path
+                self.peer, self.peer_error = None, f"{type(e).__name__}: {e}"
+        try:
+            first = FlatGradBuffer(P, widths, device, allocate=alloc)
+        except Exception as e:
+            if alloc is None:
+                raise
+            self.peer, self.peer_error = None, f"{type(e).__name__}: {e}"
+            first = FlatGradBuffer(P, widths, device)
+        self.bufs = [first] + [FlatGradBuffer(P, widths, device) for _ in range(n - 1)]
         self.streams = [torch.cuda.Stream(device=device) for _ in range(n)] if n > 1 else [None]
         self.device = device
 
@@ -152,6 +228,18 @@ class ViewStreams:
                 cur.wait_stream(st)
         for b in self.bufs[1:]:
             self.bufs[0].flat.add_(b.flat)
+        return self.bufs[0]
+
+    def all_reduce_(self, scale: float = 1.0) -> FlatGradBuffer:
+        """Sums the (already stream-summed) buffer over the ranks, in place, on the current stream."""
+        if self.peer is not None:
+            self.peer.all_reduce_(scale)
+        elif dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(self.bufs[0].flat, op=dist.ReduceOp.SUM, group=self.group)
+            if scale != 1.0:
+                self.bufs[0].flat.mul_(scale)
+        elif scale != 1.0:
+            self.bufs[0].flat.mul_(scale)
         return self.bufs[0]
 
 

@@ -176,6 +176,19 @@ typedef struct dmgs_adam_segment {
 int dmgs_adam_step(int32_t nseg, const dmgs_adam_segment *segments_host, double beta1, double beta2, double eps,
                    int64_t step, float grad_scale, int32_t zero_grad, void *stream);
 
+/* ---- all-reduce (sum) of a flat fp32 buffer over NVLink peer memory (view-partitioned training step:
+ *      the per-Gaussian gradient exchange; replaces ncclAllReduce on one box).
+ * Every rank passes the same-sized buffer of n floats (n % 4 == 0, 16-byte aligned), mapped into every
+ * peer's address space (CUDA IPC / symmetric memory): peer_ptrs_host[k] = rank k's buffer as seen from
+ * THIS process (HOST array of `world` device pointers, own buffer at index `rank`).  multicast_ptr, when
+ * not NULL, is the NVSwitch multicast mapping of the same buffers: the reduction then happens in the
+ * switch (multimem.ld_reduce / multimem.st).  Rank r reduces slice r of everybody's buffer and writes
+ * the scaled sum back to slice r of everybody's buffer, in place.  The caller must place a device-side
+ * barrier across the ranks before the call (all buffers complete) and after it (all slices delivered). */
+#define DMGS_MAX_PEERS 8
+int dmgs_allreduce_peer(int64_t n, int32_t world, int32_t rank, const void *const *peer_ptrs_host, void *multicast_ptr,
+                        float scale, void *stream);
+
 /* ---- inspection (parity tests): byte offsets of the named arrays inside the state buffers.
  * geom:    [0] depths f32[P]  [1] rec f32[P][8]={x,y,conA,conB,conC,opacity,cut,_}  [2] rgb f32[P][4]
  *          [3] clamped u8[P] (bit ch)  [4] cov3D f32[P][6]  [5] tiles_touched u32[P]
