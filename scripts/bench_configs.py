@@ -85,6 +85,15 @@ if "c2" in which:
     for i in range(N):
         step(i, True)
     ok = dmgs_b200.check_async()
+    if os.environ.get("DMGS_HOST_PROFILE"):
+        import cProfile, pstats, io
+        torch.cuda.synchronize()
+        pr = cProfile.Profile(); pr.enable()
+        for i in range(N):
+            step(i, False)
+        pr.disable(); torch.cuda.synchronize()
+        sio = io.StringIO(); pstats.Stats(pr, stream=sio).sort_stats("tottime").print_stats(30)
+        print(sio.getvalue()[:7000], file=sys.stderr)
     print(json.dumps({"config": "c2: stage-2 training step, mesh-bound (F=%d, k=6, P=%d), 800x800, fused sigmoid-SH, "
                                 "cov3D_precomp from the face frame, L1+SSIM loss, Adam" % (faces.shape[0], P),
                       "ms_per_step": round(total, 4), "steps_per_s": round(1e3 / total, 1),
