@@ -5,7 +5,8 @@ Host-side mirror of the binding interface of the reference's stage-2/3 models:
                              barycentric means, affine cov3D_L) + :370-385 (get_covariance_dyn);
                              the COLMAP variant (…_mlp_flex_colmap.py:494-512) is ``scale_factor=None``.
   * ``bind_frame``        <- scene/gaussian_geo_model_finetune.py:414-421 (rot_t2w + means, all with grad)
-  * ``stage3_scales_rotations`` / ``stage3_covariance`` <- …_finetune.py:446-482, :501-516
+  * ``stage3_scales_rotations`` / ``stage3_covariance`` <- …_finetune.py:446-482, :501-516 (fused:
+                             dmgs_stage3_forward/backward)
   * ``renew_gaussian``    <- the gs_info dict of mlp_flex.py:321-334 that render_dyn consumes.
 Gradients follow the reference's autograd exactly: cov3D_L is a constant (built under no_grad,
 mlp_flex.py:285), gradients reach ``verts`` through the face frame and the barycentric means and
@@ -93,61 +94,64 @@ def renew_gaussian(verts, faces, bc, rad_base, spatial_lr_scale, scale_factor, f
 
 
 # ------------------------------------------------------------------------------ stage 3
-def matrix_to_quaternion(matrix: torch.Tensor) -> torch.Tensor:
-    """Rotation matrices [N,3,3] -> quaternions (w,x,y,z) with non-negative... largest-denominator
-    branch selection, the semantics of pytorch3d.transforms.matrix_to_quaternion that
-    finetune.py:461 calls (restated; pytorch3d is not a dependency)."""
-    m = matrix
-    m00, m01, m02 = m[:, 0, 0], m[:, 0, 1], m[:, 0, 2]
-    m10, m11, m12 = m[:, 1, 0], m[:, 1, 1], m[:, 1, 2]
-    m20, m21, m22 = m[:, 2, 0], m[:, 2, 1], m[:, 2, 2]
-    pos_sqrt = lambda x: torch.where(x > 0, torch.sqrt(torch.clamp_min(x, 1e-30)), torch.zeros_like(x))
-    q_abs = torch.stack([pos_sqrt(1.0 + m00 + m11 + m22), pos_sqrt(1.0 + m00 - m11 - m22),
-                         pos_sqrt(1.0 - m00 + m11 - m22), pos_sqrt(1.0 - m00 - m11 + m22)], dim=-1)
-    cand = torch.stack([
-        torch.stack([q_abs[:, 0] ** 2, m21 - m12, m02 - m20, m10 - m01], dim=-1),
-        torch.stack([m21 - m12, q_abs[:, 1] ** 2, m10 + m01, m02 + m20], dim=-1),
-        torch.stack([m02 - m20, m10 + m01, q_abs[:, 2] ** 2, m12 + m21], dim=-1),
-        torch.stack([m10 - m01, m20 + m02, m21 + m12, q_abs[:, 3] ** 2], dim=-1)], dim=-2)
-    cand = cand / (2.0 * q_abs[:, :, None].clamp_min(0.1))
-    best = q_abs.argmax(dim=-1)
-    return cand[torch.arange(m.shape[0], device=m.device), best]
+class _Stage3(torch.autograd.Function):
+    """(rot_t2w [F,3,3], scaling2d [P,2], rotation2d [P,2]) -> scales / quaternions / cov6 on the device
+    (libdmgs_raster.so: dmgs_stage3_forward / dmgs_stage3_backward)."""
 
+    @staticmethod
+    def forward(ctx, rot_t2w, scaling2d, rotation2d, thin_z, want):
+        if rot_t2w.device.type != "cuda":
+            raise RuntimeError("dmgs_b200 binding needs CUDA tensors; there is no CPU path")
+        rot = rot_t2w.detach().float().contiguous()
+        s2 = scaling2d.detach().float().contiguous()
+        r2 = rotation2d.detach().float().contiguous()
+        F, P = int(rot.shape[0]), int(s2.shape[0])
+        if F == 0 or P % max(F, 1) != 0 or r2.shape[0] != P:
+            if P != 0 or F != 0:
+                raise ValueError(f"stage 3: {P} Gaussians over {F} faces")
+        k = P // F if F else 1
+        dev = rot.device
+        scales = torch.empty(P, 3, dtype=torch.float32, device=dev) if "scales" in want else None
+        quats = torch.empty(P, 4, dtype=torch.float32, device=dev) if "quats" in want else None
+        cov6 = torch.empty(P, 6, dtype=torch.float32, device=dev) if "cov6" in want else None
+        L.check(L.lib().dmgs_stage3_forward(F, k, L.ptr(rot), L.ptr(r2), L.ptr(s2), float(thin_z), L.ptr(scales),
+                                            L.ptr(quats), L.ptr(cov6), _stream()), "dmgs_stage3_forward")
+        ctx.save_for_backward(rot, s2, r2)
+        ctx.meta = (F, k, float(thin_z), want)
+        return tuple(t for t in (scales, quats, cov6) if t is not None)
 
-def stage3_rot_matrix(rot_t2w, rotation2d):
-    """R = rot_t2w[f] @ [[a,-b,0],[b,a,0],[0,0,1]], (a,b) = normalize(_rotation) (finetune.py:465-482)."""
-    F = rot_t2w.shape[0]
-    c = torch.nn.functional.normalize(rotation2d, dim=1)
-    a, b = c[:, 0], c[:, 1]
-    z, o = torch.zeros_like(a), torch.ones_like(a)
-    Rt = torch.stack([a, -b, z, b, a, z, z, z, o], dim=1).view(F, -1, 3, 3)
-    return torch.matmul(rot_t2w.view(F, 1, 3, 3), Rt).view(-1, 3, 3)
+    @staticmethod
+    def backward(ctx, *grads):
+        rot, s2, r2 = ctx.saved_tensors
+        F, k, thin_z, want = ctx.meta
+        it = iter(grads)
+        fix = lambda t: None if t is None else t.float().contiguous()
+        g_s = fix(next(it)) if "scales" in want else None
+        g_q = fix(next(it)) if "quats" in want else None
+        g_c = fix(next(it)) if "cov6" in want else None
+        d_rot, d_r2, d_s2 = torch.empty_like(rot), torch.empty_like(r2), torch.empty_like(s2)
+        L.check(L.lib().dmgs_stage3_backward(F, k, L.ptr(rot), L.ptr(r2), L.ptr(s2), thin_z, L.ptr(g_s), L.ptr(g_q),
+                                             L.ptr(g_c), L.ptr(d_rot), L.ptr(d_r2), L.ptr(d_s2), _stream()),
+                "dmgs_stage3_backward")
+        return d_rot, d_s2, d_r2, None, None
 
 
 def stage3_scales_rotations(rot_t2w, scaling2d, rotation2d, thin_z_scale):
-    """-> (scales [P,3], rotations [P,4] unit (w,x,y,z)) as finetune.py:446-463 hands to render()."""
-    s = torch.cat([torch.exp(scaling2d), torch.full((scaling2d.shape[0], 1), float(thin_z_scale),
-                                                    device=scaling2d.device)], dim=1)
-    q = matrix_to_quaternion(stage3_rot_matrix(rot_t2w, rotation2d))
-    return s, torch.nn.functional.normalize(q)
+    """-> (scales [P,3], rotations [P,4] unit (w,x,y,z)) as finetune.py:446-463 hands to render():
+    get_scaling, and get_rotation = normalize(matrix_to_quaternion(get_rot_matrix()))."""
+    return _Stage3.apply(rot_t2w, scaling2d, rotation2d, thin_z_scale, ("scales", "quats"))
 
 
 def stage3_covariance(rot_t2w, scaling2d, rotation2d, thin_z_scale):
     """Sigma = (R S)(R S)^T stripped to 6 (finetune.py:501-516)."""
-    s = torch.cat([torch.exp(scaling2d), torch.full((scaling2d.shape[0], 1), float(thin_z_scale),
-                                                    device=scaling2d.device)], dim=1)
-    Lm = stage3_rot_matrix(rot_t2w, rotation2d) * s[:, None, :]
-    Sg = Lm @ Lm.transpose(1, 2)
-    return torch.stack([Sg[:, 0, 0], Sg[:, 0, 1], Sg[:, 0, 2], Sg[:, 1, 1], Sg[:, 1, 2], Sg[:, 2, 2]], dim=1)
+    return _Stage3.apply(rot_t2w, scaling2d, rotation2d, thin_z_scale, ("cov6",))[0]
 
 
 def in_frustum(full_proj_transform, points):
-    """Face-centroid frustum mask of finetune.py:33-48 (|ndc| < 1.05 and w > 0)."""
-    p = points @ full_proj_transform[:3, :] + full_proj_transform[3:, :]
-    w = p[:, 3:] + 1e-6
-    ndc = p[:, :3] / w
-    return (ndc.abs() < 1.05).all(dim=-1) & (w.squeeze(-1) > 0)
+    """Face-centroid frustum mask of finetune.py:33-48 (|ndc| < 1.05 and w > 0); see dmgs_b200.frustum."""
+    from .frustum import in_frustum as _f
+    return _f(full_proj_transform, points)
 
 
-__all__ = ["bind_faces", "bind_frame", "renew_gaussian", "stage3_scales_rotations", "stage3_covariance",
-           "stage3_rot_matrix", "matrix_to_quaternion", "in_frustum", "barycentric_layout"]
+__all__ = ["bind_faces", "bind_frame", "renew_gaussian", "stage3_scales_rotations", "stage3_covariance", "in_frustum",
+           "barycentric_layout"]

@@ -305,6 +305,22 @@ int dmgs_bind_backward(int64_t F, int32_t k, const float *verts, const int64_t *
                            dg, (cudaStream_t)stream);
 }
 
+int dmgs_stage3_forward(int64_t F, int32_t k, const float *rot_t2w, const float *rotation2d, const float *scaling2d,
+                        float thin_z, float *scales, float *quats, float *cov6, void *stream)
+{
+    if (F < 0 || k <= 0 || (F > 0 && (!rot_t2w || !rotation2d || !scaling2d))) { set_error("stage3: bad arguments"); return -6; }
+    return launch_stage3_fwd(F, k, rot_t2w, rotation2d, scaling2d, thin_z, scales, quats, cov6, (cudaStream_t)stream);
+}
+
+int dmgs_stage3_backward(int64_t F, int32_t k, const float *rot_t2w, const float *rotation2d, const float *scaling2d,
+                         float thin_z, const float *dL_dscales, const float *dL_dquats, const float *dL_dcov6,
+                         float *dL_drot, float *dL_drotation2d, float *dL_dscaling2d, void *stream)
+{
+    if (F < 0 || k <= 0 || (F > 0 && (!rot_t2w || !rotation2d || !scaling2d))) { set_error("stage3: bad arguments"); return -6; }
+    return launch_stage3_bwd(F, k, rot_t2w, rotation2d, scaling2d, thin_z, dL_dscales, dL_dquats, dL_dcov6, dL_drot,
+                             dL_drotation2d, dL_dscaling2d, (cudaStream_t)stream);
+}
+
 // ---- rows next to the path -------------------------------------------------
 size_t dmgs_l1_ssim_scratch_bytes(int32_t planes, int32_t H, int32_t W)
 {

@@ -7,7 +7,7 @@ namespace dmgs {
 
 constexpr int BLK = 256;
 #ifndef BWD_MIN_BLOCKS
-#define BWD_MIN_BLOCKS 4
+#define BWD_MIN_BLOCKS 5
 #endif
 
 struct BlendArgs {

@@ -48,6 +48,13 @@ int launch_blend_bwd(const dmgs_params *prm, const void *geom, const GeomLayout 
                      const BinLayout &BL, const void *image, const ImgLayout &IL, const float *dL_dpix,
                      float *grad_blend, cudaStream_t s);
 
+// stage3.cu
+int launch_stage3_fwd(int64_t F, int k, const float *rot_t2w, const float *rotation2d, const float *scaling2d,
+                      float thin_z, float *scales, float *quats, float *cov6, cudaStream_t s);
+int launch_stage3_bwd(int64_t F, int k, const float *rot_t2w, const float *rotation2d, const float *scaling2d,
+                      float thin_z, const float *dL_dscales, const float *dL_dquats, const float *dL_dcov6, float *dL_drot,
+                      float *dL_drotation2d, float *dL_dscaling2d, cudaStream_t s);
+
 // loss.cu
 size_t loss_scratch_bytes(int planes, int H, int W);
 int launch_l1_ssim_fwd(int planes, int H, int W, const float *window11, const float *img, const float *gt,

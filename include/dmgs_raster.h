@@ -129,6 +129,22 @@ int dmgs_bind_backward(int64_t F, int32_t k, const float *verts, const int64_t *
                        float rad_base, float thin_z, const float *g, int32_t adaptive, const float *dL_dxyz,
                        const float *dL_dcov6, const float *dL_drot, float *dverts, float *dg, void *stream);
 
+/* ---- stage-3 binding, per-Gaussian part (scene/gaussian_geo_model_finetune.py:446-453 get_scaling,
+ *      :456-463 get_rotation, :465-482 get_rot_matrix, :501-516 get_covariance).
+ * rot_t2w [F,9]: the face frames (dmgs_bind_forward's rot_t2w output); rotation2d, scaling2d [F*k,2]:
+ * the per-Gaussian parameters `_rotation`, `_scaling` (face-major order f*k + j); thin_z: the constant
+ * third scale.  Outputs (any may be NULL): scales [F*k,3] = (exp s0, exp s1, thin_z); quats [F*k,4] =
+ * normalize(matrix_to_quaternion(R)) (w,x,y,z), R = rot_t2w [[a,-b,0],[b,a,0],[0,0,1]], (a,b) =
+ * normalize(rotation2d); cov6 [F*k,6] = strip_symmetric((R S)(R S)^T).
+ * backward: upstream gradients dL_dscales / dL_dquats / dL_dcov6 (any may be NULL) -> dL_drot [F,9]
+ * (overwritten; feed it to dmgs_bind_backward's dL_drot), dL_drotation2d, dL_dscaling2d [F*k,2]
+ * (overwritten).                                                                             */
+int dmgs_stage3_forward(int64_t F, int32_t k, const float *rot_t2w, const float *rotation2d, const float *scaling2d,
+                        float thin_z, float *scales, float *quats, float *cov6, void *stream);
+int dmgs_stage3_backward(int64_t F, int32_t k, const float *rot_t2w, const float *rotation2d, const float *scaling2d,
+                         float thin_z, const float *dL_dscales, const float *dL_dquats, const float *dL_dcov6,
+                         float *dL_drot, float *dL_drotation2d, float *dL_dscaling2d, void *stream);
+
 /* ==== rows next to the path ========================================== */
 
 /* ---- fused L1 + SSIM image loss (utils/loss_utils.py:17-18 l1_loss, :35-63 ssim/_ssim; caller

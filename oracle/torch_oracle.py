@@ -141,3 +141,62 @@ def render(W, H, tanfovx, tanfovy, bg, view, proj, campos, means3D, opacities, s
              "conic": torch.stack([conx, cony, conz], 1), "rgb": rgb, "depth": tz, "order": o,
              "final_T": Tfinal.view(H, W), "n_contrib_in_visible_order": n_contrib.view(H, W), "vis": vis}
     return img.t().reshape(3, H, W), inter
+
+
+# ------------------------------------------------------------------------------ stage-3 binding
+# CPU restatement (torch ops, autograd gives the gradients) of
+#   get_rot_matrix   /root/reference/scene/gaussian_geo_model_finetune.py:465-482
+#   get_scaling      :446-453          get_covariance  :501-516
+#   get_rotation     :456-463 = normalize(pytorch3d.transforms.matrix_to_quaternion(R)); pytorch3d 0.7.x is a
+#                    dependency that is absent here: its published algorithm (candidate with the largest
+#                    denominator, clamp 0.1) is restated in matrix_to_quaternion below.
+# PINNED by tests/golden/binding_stage3.npz (R, scales, cov6 and the autograd gradients, generated by
+# executing the reference lines); the quaternion conversion is checked through R(q) == R.
+def matrix_to_quaternion(matrix: torch.Tensor) -> torch.Tensor:
+    """Rotation matrices [N,3,3] -> quaternions (w,x,y,z) with non-negative... largest-denominator
+    branch selection, the semantics of pytorch3d.transforms.matrix_to_quaternion that
+    finetune.py:461 calls (restated; pytorch3d is not a dependency)."""
+    m = matrix
+    m00, m01, m02 = m[:, 0, 0], m[:, 0, 1], m[:, 0, 2]
+    m10, m11, m12 = m[:, 1, 0], m[:, 1, 1], m[:, 1, 2]
+    m20, m21, m22 = m[:, 2, 0], m[:, 2, 1], m[:, 2, 2]
+    pos_sqrt = lambda x: torch.where(x > 0, torch.sqrt(torch.clamp_min(x, 1e-30)), torch.zeros_like(x))
+    q_abs = torch.stack([pos_sqrt(1.0 + m00 + m11 + m22), pos_sqrt(1.0 + m00 - m11 - m22),
+                         pos_sqrt(1.0 - m00 + m11 - m22), pos_sqrt(1.0 - m00 - m11 + m22)], dim=-1)
+    cand = torch.stack([
+        torch.stack([q_abs[:, 0] ** 2, m21 - m12, m02 - m20, m10 - m01], dim=-1),
+        torch.stack([m21 - m12, q_abs[:, 1] ** 2, m10 + m01, m02 + m20], dim=-1),
+        torch.stack([m02 - m20, m10 + m01, q_abs[:, 2] ** 2, m12 + m21], dim=-1),
+        torch.stack([m10 - m01, m20 + m02, m21 + m12, q_abs[:, 3] ** 2], dim=-1)], dim=-2)
+    cand = cand / (2.0 * q_abs[:, :, None].clamp_min(0.1))
+    best = q_abs.argmax(dim=-1)
+    return cand[torch.arange(m.shape[0], device=m.device), best]
+
+
+def stage3_rot_matrix(rot_t2w, rotation2d):
+    """R = rot_t2w[f] @ [[a,-b,0],[b,a,0],[0,0,1]], (a,b) = normalize(_rotation) (finetune.py:465-482)."""
+    F = rot_t2w.shape[0]
+    c = torch.nn.functional.normalize(rotation2d, dim=1)
+    a, b = c[:, 0], c[:, 1]
+    z, o = torch.zeros_like(a), torch.ones_like(a)
+    Rt = torch.stack([a, -b, z, b, a, z, z, z, o], dim=1).view(F, -1, 3, 3)
+    return torch.matmul(rot_t2w.view(F, 1, 3, 3), Rt).view(-1, 3, 3)
+
+
+def stage3_scales_rotations(rot_t2w, scaling2d, rotation2d, thin_z_scale):
+    """-> (scales [P,3], rotations [P,4] unit (w,x,y,z)) as finetune.py:446-463 hands to render()."""
+    s = torch.cat([torch.exp(scaling2d), torch.full((scaling2d.shape[0], 1), float(thin_z_scale),
+                                                    device=scaling2d.device)], dim=1)
+    q = matrix_to_quaternion(stage3_rot_matrix(rot_t2w, rotation2d))
+    return s, torch.nn.functional.normalize(q)
+
+
+def stage3_covariance(rot_t2w, scaling2d, rotation2d, thin_z_scale):
+    """Sigma = (R S)(R S)^T stripped to 6 (finetune.py:501-516)."""
+    s = torch.cat([torch.exp(scaling2d), torch.full((scaling2d.shape[0], 1), float(thin_z_scale),
+                                                    device=scaling2d.device)], dim=1)
+    Lm = stage3_rot_matrix(rot_t2w, rotation2d) * s[:, None, :]
+    Sg = Lm @ Lm.transpose(1, 2)
+    return torch.stack([Sg[:, 0, 0], Sg[:, 0, 1], Sg[:, 0, 2], Sg[:, 1, 1], Sg[:, 1, 2], Sg[:, 2, 2]], dim=1)
+
+

@@ -269,3 +269,71 @@ def test_binding_golden_on_gpu():
         ref = g[f"{tag}_dverts"]
         assert np.linalg.norm(v.grad.cpu().numpy() - ref) <= 1e-4 * np.linalg.norm(ref)
         assert abs(sf.grad.item() - g[f"{tag}_dscale_factor"][0]) <= 1e-4 * abs(g[f"{tag}_dscale_factor"][0])
+
+
+# ------------------------------------------------------------------------------ stage-3 binding
+def test_stage3_golden_and_oracle_on_gpu():
+    """dmgs_stage3_forward/backward (+ bind_frame) against tests/golden/binding_stage3.npz (the reference's own lines:
+    R, scales, cov6 and the gradients to verts / _rotation / _scaling) and, for the quaternion path, against the
+    oracle's torch restatement with autograd."""
+    from dmgs_b200.binding import bind_frame, stage3_covariance, stage3_scales_rotations
+    from oracle import torch_oracle as TO
+    from util import golden
+    g = golden("binding_stage3.npz")
+    bc, _ = S.barycentric_layout(3)
+    v = torch.tensor(g["verts"]).cuda().requires_grad_()
+    r2 = torch.tensor(g["rotation2d"]).cuda().requires_grad_()
+    s2 = torch.tensor(g["scaling2d"]).cuda().requires_grad_()
+    xyz, rot = bind_frame(v, torch.tensor(g["faces"]).cuda(), bc.cuda())
+    cov = stage3_covariance(rot, s2, r2, float(g["thin_z"]))
+    assert np.allclose(xyz.detach().cpu().numpy(), g["xyz"], rtol=1e-5, atol=1e-6)
+    c = g["cov6"].astype(np.float64)
+    assert np.linalg.norm(cov.detach().cpu().numpy() - c) <= 5e-6 * np.linalg.norm(c)
+    ((xyz * torch.tensor(g["gxyz"]).cuda()).sum() + (cov * torch.tensor(g["gcov"]).cuda()).sum()).backward()
+    for got, name in ((v.grad, "dverts"), (r2.grad, "drotation2d"), (s2.grad, "dscaling2d")):
+        ref = g[name]
+        assert np.linalg.norm(got.cpu().numpy() - ref) <= 1e-4 * np.linalg.norm(ref), name
+    # (scales, quaternion) path: forward vs golden R / scales, gradients vs the oracle's autograd
+    gen = torch.Generator().manual_seed(21)
+    P = r2.shape[0]
+    gs, gq = torch.randn(P, 3, generator=gen), torch.randn(P, 4, generator=gen)
+    rot_c = torch.tensor(g["rot_t2w"])
+    o_rot, o_r2, o_s2 = (t.clone().double().requires_grad_() for t in (rot_c, torch.tensor(g["rotation2d"]), torch.tensor(g["scaling2d"])))
+    os_, oq = TO.stage3_scales_rotations(o_rot, o_s2, o_r2, float(g["thin_z"]))
+    ((os_ * gs.double()).sum() + (oq * gq.double()).sum()).backward()
+    d_rot, d_r2, d_s2 = (t.clone().cuda().requires_grad_() for t in (rot_c, torch.tensor(g["rotation2d"]), torch.tensor(g["scaling2d"])))
+    sc, q = stage3_scales_rotations(d_rot, d_s2, d_r2, float(g["thin_z"]))
+    np.testing.assert_allclose(sc.detach().cpu().numpy(), g["scales3"], rtol=2e-6)
+    np.testing.assert_allclose(q.detach().cpu().numpy(), oq.detach().float().numpy(), atol=2e-6)
+    np.testing.assert_allclose(TO.quat_to_rot(q.detach().cpu()).numpy(), g["R"], atol=2e-6)
+    ((sc * gs.cuda()).sum() + (q * gq.cuda()).sum()).backward()
+    for got, ref, name in ((d_rot.grad, o_rot.grad, "rot_t2w"), (d_r2.grad, o_r2.grad, "rotation2d"), (d_s2.grad, o_s2.grad, "scaling2d")):
+        ref = ref.numpy()
+        assert np.linalg.norm(got.cpu().numpy() - ref) <= 1e-4 * np.linalg.norm(ref), name
+
+
+def test_stage3_all_quaternion_branches_and_large():
+    """Frames covering all four matrix_to_quaternion candidates (rotations by > 120 degrees about each axis) and a
+    300 k-Gaussian run against the oracle."""
+    from dmgs_b200.binding import stage3_covariance, stage3_scales_rotations
+    from oracle import torch_oracle as TO
+    gen = torch.Generator().manual_seed(8)
+    F, k = 50_000, 6
+    q0 = torch.nn.functional.normalize(torch.randn(F, 4, generator=gen), dim=1)
+    rot = TO.quat_to_rot(q0).contiguous()                      # random proper rotations as face frames
+    r2 = torch.randn(F * k, 2, generator=gen)
+    s2 = torch.randn(F * k, 2, generator=gen) * 0.3 - 3.0
+    ref_s, ref_q = TO.stage3_scales_rotations(rot, s2, r2, 4.43e-6)
+    R = TO.stage3_rot_matrix(rot, r2)
+    t2 = torch.stack([1 + R[:, 0, 0] + R[:, 1, 1] + R[:, 2, 2], 1 + R[:, 0, 0] - R[:, 1, 1] - R[:, 2, 2],
+                      1 - R[:, 0, 0] + R[:, 1, 1] - R[:, 2, 2], 1 - R[:, 0, 0] - R[:, 1, 1] + R[:, 2, 2]], 1)
+    assert set(t2.argmax(1).tolist()) == {0, 1, 2, 3}
+    sc, q = stage3_scales_rotations(rot.cuda(), s2.cuda(), r2.cuda(), 4.43e-6)
+    np.testing.assert_allclose(sc.cpu().numpy(), ref_s.numpy(), rtol=2e-6)
+    # a near tie between two candidates may pick the other one: same rotation, possibly the opposite sign
+    qc = q.cpu()
+    sign = torch.sign((qc * ref_q).sum(1, keepdim=True))
+    assert float((qc * sign - ref_q).abs().max()) <= 5e-6
+    cov = stage3_covariance(rot.cuda(), s2.cuda(), r2.cuda(), 4.43e-6).cpu().double()
+    ref_c = TO.stage3_covariance(rot.double(), s2.double(), r2.double(), 4.43e-6)
+    assert float(torch.linalg.norm(cov - ref_c) / torch.linalg.norm(ref_c)) <= 5e-6

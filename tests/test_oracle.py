@@ -207,3 +207,29 @@ def test_empty_and_culled_inputs():
     assert fwd["bins"]["R"] == 0 and (fwd["geom"]["radii"] == 0).all()
     assert np.allclose(fwd["img"]["color"], np.array([0.1, 0.2, 0.3], np.float32)[:, None, None])
     assert (fwd["img"]["n_contrib"] == 0).all() and (fwd["img"]["final_T"] == 1).all()
+
+
+# ------------------------------------------------------------------------------ stage-3 binding (golden)
+def test_stage3_oracle_matches_reference_golden():
+    """oracle/torch_oracle.py stage-3 restatement against tests/golden/binding_stage3.npz (R, scales, cov6 and the
+    autograd gradients produced by the reference's own lines)."""
+    import torch
+    from oracle import torch_oracle as TO
+    g = golden("binding_stage3.npz")
+    rot = torch.tensor(g["rot_t2w"]).requires_grad_()
+    r2 = torch.tensor(g["rotation2d"]).requires_grad_()
+    s2 = torch.tensor(g["scaling2d"]).requires_grad_()
+    R = TO.stage3_rot_matrix(rot, r2)
+    np.testing.assert_allclose(R.detach().numpy(), g["R"], rtol=1e-6, atol=1e-7)
+    scales, q = TO.stage3_scales_rotations(rot, s2, r2, float(g["thin_z"]))
+    np.testing.assert_allclose(scales.detach().numpy(), g["scales3"], rtol=1e-6)
+    # the quaternion reproduces R (pytorch3d's conversion is restated, not executed)
+    np.testing.assert_allclose(TO.quat_to_rot(q).detach().numpy(), g["R"], atol=2e-6)
+    assert np.allclose(q.detach().norm(dim=1).numpy(), 1.0, atol=1e-6)
+    cov = TO.stage3_covariance(rot, s2, r2, float(g["thin_z"]))
+    c = g["cov6"].astype(np.float64)
+    assert np.linalg.norm(cov.detach().numpy() - c) <= 5e-6 * np.linalg.norm(c)
+    (cov * torch.tensor(g["gcov"])).sum().backward()
+    for got, name in ((r2.grad, "drotation2d"), (s2.grad, "dscaling2d")):
+        ref = g[name]
+        assert np.linalg.norm(got.numpy() - ref) <= 1e-4 * np.linalg.norm(ref), name
