@@ -83,6 +83,16 @@ def bind_frame(verts, faces, bc):
     return xyz, rot
 
 
+def face_normals(vertices, faces, unit=False):
+    """geo/mesh_utils.py:43-57 with unit=True (the only form on the path: mlp_flex.py:268, finetune.py:414):
+    normalize((v1 - v0) x (v2 - v0)), taken from the fused frame kernel (third column of rot_t2w), with grad."""
+    if not unit:
+        raise NotImplementedError("only unit=True is on the binding path (mlp_flex.py:268, finetune.py:414)")
+    bc = torch.full((1, 3), 1.0 / 3.0, dtype=torch.float32, device=vertices.device)
+    _, rot = _BindFaces.apply(vertices, faces, bc, None, 0.0, 0.0, True, False, True)
+    return rot[:, :, 2]
+
+
 def renew_gaussian(verts, faces, bc, rad_base, spatial_lr_scale, scale_factor, features, max_scale=2.0,
                    adaptive_cov=True, active_sh_degree=3, max_sh_degree=3):
     """The gs_info dict of mlp_flex.py:321-334 (minus the FlexiCubes regularisers), for render_dyn."""
@@ -153,5 +163,5 @@ def in_frustum(full_proj_transform, points):
     return _f(full_proj_transform, points)
 
 
-__all__ = ["bind_faces", "bind_frame", "renew_gaussian", "stage3_scales_rotations", "stage3_covariance", "in_frustum",
+__all__ = ["bind_faces", "bind_frame", "face_normals", "renew_gaussian", "stage3_scales_rotations", "stage3_covariance", "in_frustum",
            "barycentric_layout"]

@@ -268,6 +268,10 @@ def test_binding_golden_on_gpu():
         ((xyz * torch.tensor(g[f"{tag}_gxyz"]).cuda()).sum() + (cov6 * torch.tensor(g[f"{tag}_gcov"]).cuda()).sum()).backward()
         ref = g[f"{tag}_dverts"]
         assert np.linalg.norm(v.grad.cpu().numpy() - ref) <= 1e-4 * np.linalg.norm(ref)
+        # face_normals(unit=True) (geo/mesh_utils.py:43-57) = third column of the reference's rot_t2w
+        from dmgs_b200.binding import face_normals
+        n = face_normals(v.detach(), torch.tensor(g[f"{tag}_faces"]).cuda(), unit=True)
+        assert np.allclose(n.cpu().numpy(), g[f"{tag}_rot_t2w"][:, :, 2], rtol=1e-5, atol=1e-6)
         assert abs(sf.grad.item() - g[f"{tag}_dscale_factor"][0]) <= 1e-4 * abs(g[f"{tag}_dscale_factor"][0])
 
 
