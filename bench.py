@@ -142,6 +142,11 @@ def cpu_baseline(workload, frames, warm=1):
     from dmgs_b200 import synthetic as S
     from oracle import oracle as O
     P, W, H, kind, extent, lsm = WORKLOADS[workload]
+    # every core this process may use, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1)
+    try:
+        O.set_threads(len(os.sched_getaffinity(0)))
+    except AttributeError:
+        O.set_threads(os.cpu_count() or 1)
     cl = S.random_cloud(P, seed=0, extent=extent, log_scale_mean=lsm)
     cl_np = {k: v.numpy() for k, v in cl.items()}
     dL = torch.randn(3, H, W, generator=torch.Generator().manual_seed(77)).numpy()

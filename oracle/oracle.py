@@ -181,3 +181,8 @@ def bind_backward(verts, faces, bc, rad_base, thin_z, g, dL_dxyz, dL_dcov6, adap
 
 def num_threads() -> int:
     return int(lib().orc_num_threads())
+
+
+def set_threads(n: int) -> None:
+    """OpenMP threads of the oracle (torchrun exports OMP_NUM_THREADS=1; the CPU baseline uses every core)."""
+    lib().orc_set_threads(C.c_int(int(n)))
