@@ -121,37 +121,43 @@ tile_count_kernel(int P, int T, int gx, int seg, int nseg, const uint4 *__restri
 }
 
 // ------------------------------------------------------------------------------ B: column scan
-// one warp per tile: exclusive scan of the tile's CTA sums down the column (in place) and the tile total
-__global__ void __launch_bounds__(256)
+// Exclusive scan of the per-CTA sums down every tile column (in place) and the tile totals.  A block owns
+// 32 adjacent tiles; its 16 warps cut the column into 16 slabs of consecutive groups.  Lanes <-> tiles, so
+// every load and store is a coalesced 128-byte row segment of gsum[group][tile] (the first version read
+// down the columns: one sector per lane and load).  Pass 1 sums the slabs, a 16-entry scan across the
+// warps gives every slab its base, pass 2 writes the running prefix.
+constexpr int GS_WARPS = 16;
+__global__ void __launch_bounds__(GS_WARPS * 32)
 group_scan_kernel(int T, int groups, uint32_t *__restrict__ gsum, uint32_t *__restrict__ tile_total)
 {
-    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (t >= T) return;
-    uint32_t carry = 0;
-    for (int g0 = 0; g0 < groups; g0 += 128) {
-        uint32_t v[4], sum = 0;  // lane owns 4 consecutive groups of this 128-group chunk
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int g = g0 + lane * 4 + i;
-            v[i] = g < groups ? gsum[(size_t)g * T + t] : 0u;
-            sum += v[i];
-        }
-        uint32_t incl = sum;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += o;
-        }
-        uint32_t run = carry + incl - sum;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int g = g0 + lane * 4 + i;
-            if (g < groups) gsum[(size_t)g * T + t] = run;
-            run += v[i];
-        }
-        carry += __shfl_sync(0xffffffffu, incl, 31);
+    __shared__ uint32_t slab[GS_WARPS][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int t = blockIdx.x * 32 + lane;
+    const int per = (groups + GS_WARPS - 1) / GS_WARPS;
+    const int g0 = w * per, g1 = min(groups, g0 + per);
+    uint32_t sum = 0;
+    if (t < T) {
+#pragma unroll 8
+        for (int g = g0; g < g1; ++g) sum += gsum[(size_t)g * T + t];
     }
-    if (lane == 0) tile_total[t] = carry;
+    slab[w][lane] = sum;
+    __syncthreads();
+    uint32_t run = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < GS_WARPS; ++k) {
+        const uint32_t v = slab[k][lane];
+        if (k < w) run += v;
+        total += v;
+    }
+    if (t < T) {
+#pragma unroll 8
+        for (int g = g0; g < g1; ++g) {
+            const uint32_t v = gsum[(size_t)g * T + t];
+            gsum[(size_t)g * T + t] = run;
+            run += v;
+        }
+        if (w == 0) tile_total[t] = total;
+    }
 }
 
 // one block: exclusive scan of the tile totals (in place -> tile_start) and the tile ranges
@@ -291,7 +297,7 @@ int launch_tile_placement(const PlacePlan &pl, int P, int T, int gx, const uint3
     const int blocks = pl.groups;
     sorted_rect_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, order_a, order_b, stat, rect, srec);
     tile_count_kernel<<<blocks, threads, pl.smem, s>>>(P, T, gx, pl.seg, pl.nseg, srec, table, gsum);
-    group_scan_kernel<<<(T + 7) / 8, 256, 0, s>>>(T, pl.groups, gsum, tile_start);
+    group_scan_kernel<<<(T + 31) / 32, GS_WARPS * 32, 0, s>>>(T, pl.groups, gsum, tile_start);
     tile_scan_kernel<<<1, 1024, 0, s>>>(T, tile_start, ranges, (uint32_t)capacity, overflow);
     tile_place_kernel<<<blocks, threads, pl.smem, s>>>(P, T, gx, pl.seg, pl.nseg, srec, table, gsum, tile_start, overflow, out_gidx);
     DMGS_CUDA(cudaGetLastError());
