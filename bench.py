@@ -227,7 +227,9 @@ def run_ours(args):
     # N > 1: the summed buffer lives in symmetric memory and is exchanged over NVLink peer memory
     # (dmgs_allreduce_peer; DMGS_BENCH_ALLREDUCE=nccl forces torch.distributed.all_reduce)
     use_peer = world > 1 and os.environ.get("DMGS_BENCH_ALLREDUCE", "peer") != "nccl"
-    vs = MV.ViewStreams(P, MV.RASTER_WIDTHS_SH, dev, n=N_STREAMS, peer_group=dist.group.WORLD if use_peer else None)
+    deferred = os.environ.get("DMGS_BENCH_DEFERRED_SH", "1") == "1"
+    vs = MV.ViewStreams(P, MV.RASTER_WIDTHS_SH, dev, n=N_STREAMS, peer_group=dist.group.WORLD if use_peer else None,
+                        deferred_sh_views=VIEWS_PER_RANK if deferred else 0)
     flat = vs.buf.flat
     if world == 1:
         allreduce_kind = "none (single GPU)"
@@ -249,6 +251,7 @@ def run_ours(args):
     r_dev = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(N_STREAMS)]
 
     def one_view(j, v, record, acc):
+        rec = vs.sh_record(j, settings[v].campos)
         events = []
         if record:
             e0 = torch.cuda.Event(enable_timing=True)
@@ -258,7 +261,7 @@ def run_ours(args):
         color, radii, st = rasterize_forward(settings[v], d["means3D"], d["opacities"], d["shs"], None,
                                              d["scales"], d["rotations"], None, stage_hook=hook)
         rasterize_backward(st, dLs[j % len(dLs)], d["means3D"], d["shs"], d["scales"], d["rotations"], None, False,
-                           stage_hook=hook, accumulate_into=acc)
+                           stage_hook=hook, accumulate_into=acc, sh_record=rec)
         if st._count_dev is not None:
             r_dev[j % N_STREAMS].add_(st._count_dev)
         else:
@@ -271,14 +274,16 @@ def run_ours(args):
         # single=True: every view on the current stream into the first accumulator (the stage-timing steps
         # after the timed region; record=True puts CUDA events between the stages)
         if single:
-            vs.buf.zero_()
+            vs.begin()
             for j, v in enumerate(my_views):
                 one_view(j, v, record, vs.buf.views)
+            if deferred:
+                vs.finish(d["means3D"], 3)
         else:
             vs.begin()
             for j, v in enumerate(my_views):
                 vs.run(j, lambda acc, j=j, v=v: one_view(j, v, False, acc))
-            vs.finish()
+            vs.finish(d["means3D"], 3)
         if world > 1:
             vs.all_reduce_()
         if not dmgs_b200.check_async():  # a frame overflowed its binning buffer: the step does not count
@@ -382,9 +387,10 @@ def run_ours(args):
         losses = []
         for j, v in enumerate(my_views):
             dl = dLs[j % len(dLs)]
-            losses.append(vs.run(j, lambda acc, v=v, dl=dl: MV.accumulate_view(
-                settings[v], inputs, lambda img: ((img * dl).sum(), dl), acc)[0]))
-        vs.finish()
+            rec = vs.sh_record(j, settings[v].campos)
+            losses.append(vs.run(j, lambda acc, v=v, dl=dl, rec=rec: MV.accumulate_view(
+                settings[v], inputs, lambda img: ((img * dl).sum(), dl), acc, sh_record=rec)[0]))
+        vs.finish(inputs["means3D"], 3)
         if world > 1:
             vs.all_reduce_()
         host_loss = float(torch.stack(losses).sum().cpu())  # device -> host read of the step's result
@@ -451,6 +457,8 @@ def run_ours(args):
                    "one all-reduce of the flat gradient buffer per step)" if world > 1 else "single GPU",
                    "all_reduce": allreduce_kind,
                    "avg_instances_R": Ravg, "view_streams": N_STREAMS,
+                   "sh_gradient": "deferred: 16-byte records per view, rows formed once per step (dmgs_sh_grad_expand)" if deferred
+                   else "read-modify-write of the [P,16,3] rows every view",
                    "stage_timing": "2 single-stream steps right after the timed region, CUDA events between stages",
                    "binning": "host read-back of the instance count every frame" if args.sync_binning else
                    "sync-free (capacity from earlier frames, overflow flags checked once per step)",

@@ -471,6 +471,10 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
                 if (pr.sh_act == 0) g[ch] = (cb >> ch) & 1 ? 0.0f : dcol[ch];
                 else g[ch] = dcol[ch] * (sg[ch] * (1.0f - sg[ch]));
             }
+            // deferred mode: this view's contribution to dL/dsh is rank one per channel (basis(dir) x g), so
+            // only g is recorded -- 16 bytes instead of a 192-byte read-modify-write -- and
+            // sh_grad_expand_kernel forms the rows once per step from all views' records
+            if (accumulate == 2) reinterpret_cast<float4 *>(dL_dshs)[i] = make_float4(g[0], g[1], g[2], 1.0f);
             // h[k] = sum_ch sh[k][ch] * g[ch]: the view-direction gradient is linear in it, so the basis
             // Jacobian below is applied once instead of once per channel
             float h[16];
@@ -492,7 +496,7 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
                         h[k] = on ? fma_(qv[c], g[ch], h[k]) : h[k];
                         ov[c] = on ? bas[k] * g[ch] : 0.0f;
                     }
-                    row4[j] = make_float4(ov[0], ov[1], ov[2], ov[3]);
+                    if (accumulate != 2) row4[j] = make_float4(ov[0], ov[1], ov[2], ov[3]);
                 }
             } else {
 #pragma unroll
@@ -502,7 +506,7 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
                         const size_t idx = pr.sh_layout == 0 ? ((size_t)i * M + k) * 3 + ch : ((size_t)i * 3 + ch) * M + k;
                         if (k < nb) {
                             h[k] = fma_(__ldg(shs + idx), g[ch], h[k]);
-                            dL_dshs[idx] = accumulate ? dL_dshs[idx] + bas[k] * g[ch] : bas[k] * g[ch];
+                            if (accumulate != 2) dL_dshs[idx] = accumulate ? dL_dshs[idx] + bas[k] * g[ch] : bas[k] * g[ch];
                         } else if (k < M && !accumulate) {
                             dL_dshs[idx] = 0.0f;
                         }
@@ -537,6 +541,8 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
                 gm[1] += (-ox * oy * ddx + (s2 - oy * oy) * ddy - oz * oy * ddz) * inv3;
                 gm[2] += (-ox * oz * ddx - oy * oz * ddy + (s2 - oz * oz) * ddz) * inv3;
             }
+        } else if (inb && accumulate == 2) {
+            reinterpret_cast<float4 *>(dL_dshs)[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // not seen by this view
         } else if (inb && !accumulate) {
             if (SHMODE) {  // culled Gaussian: a row of zeros
                 float4 *row4 = reinterpret_cast<float4 *>(stage.row);
@@ -548,7 +554,8 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
         }
         if (SHMODE) {
             // store: every in-range row (zeros for culled Gaussians); accumulate: only rows with a gradient
-            if (inb && (vis || !accumulate)) stage.flush_row(dL_dshs + (size_t)i * SH_ROW_FLOATS, accumulate != 0);
+            if (accumulate != 2 && inb && (vis || !accumulate))
+                stage.flush_row(dL_dshs + (size_t)i * SH_ROW_FLOATS, accumulate != 0);
         }
     }
 
@@ -627,6 +634,105 @@ int launch_preprocess_bwd(const dmgs_params *prm, const float *means3D, const fl
     else if (mode == 2) preprocess_bwd_kernel<2><<<grid, 256, SH_STAGE_SMEM, s>>>(DMGS_BWD_ARGS);
     else preprocess_bwd_kernel<0><<<grid, 256, 0, s>>>(DMGS_BWD_ARGS);
 #undef DMGS_BWD_ARGS
+    DMGS_CUDA(cudaGetLastError());
+    count_launches(1);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------ deferred SH gradient
+// dL/dsh[i] = sum over the step's views v that saw Gaussian i of basis(dir_v(i)) (x) g_v(i), from the
+// 16-byte records {g.r, g.g, g.b, seen} written by preprocess_bwd_kernel (accumulate == 2).  Per Gaussian
+// and step this moves V * 16 B of records + one 192-byte row instead of V read-modify-writes of the row.
+struct ExpandArgs {
+    int P, V, sh_degree, M, layout, accumulate;
+    long long view_stride;  // floats between two views' record arrays
+    float cam[DMGS_MAX_STEP_VIEWS][3];
+};
+
+template <int SHMODE>
+__global__ void __launch_bounds__(256)
+sh_grad_expand_kernel(const __grid_constant__ ExpandArgs a, const float *__restrict__ means3D,
+                      const float *__restrict__ records, float *__restrict__ dL_dshs)
+{
+    extern __shared__ __align__(16) unsigned char dsm[];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool inb = i < a.P;
+    ShStage stage;
+    if (SHMODE) stage.init(dsm);
+    float acc[16][3];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k][0] = acc[k][1] = acc[k][2] = 0.0f;
+    bool any = false;
+    if (inb) {
+        const float x = means3D[3 * (size_t)i], y = means3D[3 * (size_t)i + 1], z = means3D[3 * (size_t)i + 2];
+        for (int v = 0; v < a.V; ++v) {
+            const float4 g = reinterpret_cast<const float4 *>(records + (size_t)v * a.view_stride)[i];
+            if (g.w == 0.0f) continue;
+            any = true;
+            const float ox = x - a.cam[v][0], oy = y - a.cam[v][1], oz = z - a.cam[v][2];
+            const float len = sqrtf(dot3(ox, ox, oy, oy, oz, oz));
+            float bas[16];
+            const int nb = sh_basis(a.sh_degree, ox / len, oy / len, oz / len, bas);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                if (k < nb) {
+                    acc[k][0] = fma_(bas[k], g.x, acc[k][0]);
+                    acc[k][1] = fma_(bas[k], g.y, acc[k][1]);
+                    acc[k][2] = fma_(bas[k], g.z, acc[k][2]);
+                }
+            }
+        }
+    }
+    if (SHMODE) {
+        // overwrite: every in-range row (zeros when no view saw the Gaussian); accumulate: rows with a gradient
+        if (inb && (any || !a.accumulate)) {
+            float4 *row4 = reinterpret_cast<float4 *>(stage.row);
+#pragma unroll
+            for (int j = 0; j < SH_ROW_FLOATS / 4; ++j) {
+                float ov[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int f = 4 * j + c;
+                    const int k = SHMODE == 1 ? f / 3 : f % 16, ch = SHMODE == 1 ? f % 3 : f / 16;
+                    ov[c] = acc[k][ch];
+                }
+                row4[j] = make_float4(ov[0], ov[1], ov[2], ov[3]);
+            }
+            stage.flush_row(dL_dshs + (size_t)i * SH_ROW_FLOATS, a.accumulate != 0);
+        }
+        stage.flush();
+    } else if (inb && (any || !a.accumulate)) {
+        for (int ch = 0; ch < 3; ++ch)
+            for (int k = 0; k < a.M; ++k) {
+                const size_t idx = a.layout == 0 ? ((size_t)i * a.M + k) * 3 + ch : ((size_t)i * 3 + ch) * a.M + k;
+                const float v = k < 16 ? acc[k][ch] : 0.0f;
+                dL_dshs[idx] = a.accumulate ? dL_dshs[idx] + v : v;
+            }
+    }
+}
+
+int launch_sh_grad_expand(int P, int sh_degree, int M, int layout, int V, const float *campos_host, const float *means3D,
+                          const float *records, int64_t view_stride, float *dL_dshs, int accumulate, cudaStream_t s)
+{
+    if (P <= 0) return 0;
+    if (V < 0 || V > DMGS_MAX_STEP_VIEWS) { set_error("sh_grad_expand: 0..%d views per call, got %d", DMGS_MAX_STEP_VIEWS, V); return -14; }
+    static bool attr_set = false;
+    if (!attr_set) {
+        DMGS_CUDA(cudaFuncSetAttribute(sh_grad_expand_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_STAGE_SMEM));
+        DMGS_CUDA(cudaFuncSetAttribute(sh_grad_expand_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_STAGE_SMEM));
+        attr_set = true;
+    }
+    ExpandArgs a;
+    memset(&a, 0, sizeof(a));
+    a.P = P; a.V = V; a.sh_degree = sh_degree; a.M = M; a.layout = layout; a.accumulate = accumulate;
+    a.view_stride = view_stride;
+    for (int v = 0; v < V; ++v)
+        for (int c = 0; c < 3; ++c) a.cam[v][c] = campos_host[3 * v + c];
+    const bool staged = M == 16 && !(reinterpret_cast<uintptr_t>(dL_dshs) & 15);
+    const int grid = (P + 255) / 256;
+    if (staged && layout == 0) sh_grad_expand_kernel<1><<<grid, 256, SH_STAGE_SMEM, s>>>(a, means3D, records, dL_dshs);
+    else if (staged) sh_grad_expand_kernel<2><<<grid, 256, SH_STAGE_SMEM, s>>>(a, means3D, records, dL_dshs);
+    else sh_grad_expand_kernel<0><<<grid, 256, 0, s>>>(a, means3D, records, dL_dshs);
     DMGS_CUDA(cudaGetLastError());
     count_launches(1);
     return 0;

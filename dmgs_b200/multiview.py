@@ -171,8 +171,13 @@ class ViewStreams:
     per-Gaussian accumulators are read-modify-written without atomics by the per-Gaussian backward
     (one thread owns one row), hence one buffer per stream rather than one shared buffer."""
 
-    def __init__(self, P: int, widths: Dict[str, Tuple[int, ...]], device, n: int = 2, peer_group=None):
-        """peer_group: a process group of ranks on ONE box -> the summed buffer lives in symmetric memory
+    def __init__(self, P: int, widths: Dict[str, Tuple[int, ...]], device, n: int = 2, peer_group=None,
+                 deferred_sh_views: int = 0, sh_key: str = "shs"):
+        """deferred_sh_views: > 0 enables the deferred SH gradient for up to that many local views per step:
+        every view records only its 16-byte {dL/dcolour, seen} per Gaussian (`sh_record(i, campos)` hands the
+        view its record array) and `finish(means3D, sh_degree)` forms the [P,16,3] gradient rows once from all
+        records -- V*16 B + one row per Gaussian and step instead of V read-modify-writes of the 192-byte row.
+        peer_group: a process group of ranks on ONE box -> the summed buffer lives in symmetric memory
         and `all_reduce_()` exchanges it over NVLink peer memory (falls back to NCCL if symmetric memory
         cannot be set up); None -> `all_reduce_()` is torch.distributed.all_reduce."""
         if n < 1:
@@ -194,6 +199,16 @@ class ViewStreams:
             self.peer, self.peer_error = None, f"{type(e).__name__}: {e}"
             first = FlatGradBuffer(P, widths, device)
         self.bufs = [first] + [FlatGradBuffer(P, widths, device) for _ in range(n - 1)]
+        self.sh_key, self.P = sh_key, int(P)
+        self.records = (torch.zeros(int(deferred_sh_views), int(P), 4, dtype=torch.float32, device=device)
+                        if deferred_sh_views > 0 and sh_key in widths else None)
+        self._campos, self._used = {}, 0
+        if self.records is not None:
+            # the SH field is last in the flat layout: the part before it is what begin() zeroes and finish() sums
+            off, _ = first.offsets[sh_key]
+            if any(o > off for o, _ in first.offsets.values()):
+                raise ValueError("deferred SH needs the SH field last in the flat buffer")
+            self._dense = off
         self.streams = [torch.cuda.Stream(device=device) for _ in range(n)] if n > 1 else [None]
         self.device = device
 
@@ -204,13 +219,15 @@ class ViewStreams:
     def begin(self):
         """Zeroes the accumulators; the side streams start after everything queued on the current stream."""
         cur = torch.cuda.current_stream(self.device)
+        self._campos, self._used = {}, 0
+        zero = (lambda b: b.flat[:self._dense].zero_()) if self.records is not None else (lambda b: b.zero_())
         for b, st in zip(self.bufs, self.streams):
             if st is None:
-                b.zero_()
+                zero(b)
                 continue
             st.wait_stream(cur)
             with torch.cuda.stream(st):
-                b.zero_()
+                zero(b)
 
     def run(self, i: int, fn: Callable[[Dict[str, torch.Tensor]], object]):
         """Calls fn(acc_views) for the i-th local view on stream i mod n."""
@@ -220,14 +237,43 @@ class ViewStreams:
         with torch.cuda.stream(self.streams[k]):
             return fn(self.bufs[k].views)
 
-    def finish(self) -> FlatGradBuffer:
-        """Joins the streams on the current stream and returns the buffer holding the sum of all views."""
+    def sh_record(self, i: int, campos) -> Optional[torch.Tensor]:
+        """Record array [P,4] of the i-th local view of the step (deferred SH mode; None otherwise); campos is
+        the view's camera centre (settings.campos)."""
+        if self.records is None:
+            return None
+        if not 0 <= i < self.records.shape[0]:
+            raise IndexError(f"view {i}: ViewStreams was built for {self.records.shape[0]} deferred-SH views per step")
+        self._campos[i] = campos
+        self._used = max(self._used, i + 1)
+        return self.records[i]
+
+    def finish(self, means3D: Optional[torch.Tensor] = None, sh_degree: int = 3, sh_layout: int = 0) -> FlatGradBuffer:
+        """Joins the streams on the current stream and returns the buffer holding the sum of all views
+        (deferred SH mode: means3D / sh_degree / sh_layout of the step are needed to form the SH rows)."""
         cur = torch.cuda.current_stream(self.device)
         for st in self.streams:
             if st is not None:
                 cur.wait_stream(st)
+        if self.records is None:
+            for b in self.bufs[1:]:
+                self.bufs[0].flat.add_(b.flat)
+            return self.bufs[0]
         for b in self.bufs[1:]:
-            self.bufs[0].flat.add_(b.flat)
+            self.bufs[0].flat[:self._dense].add_(b.flat[:self._dense])
+        if means3D is None:
+            raise ValueError("deferred SH mode: finish(means3D, sh_degree) forms the SH gradient rows")
+        if sorted(self._campos) != list(range(self._used)):
+            raise RuntimeError("deferred SH mode: every view 0..n-1 of the step must have taken its sh_record")
+        from .rasterizer import sh_grad_expand
+        out = self.bufs[0].views[self.sh_key]
+        V, step = self._used, 32
+        if V == 0:
+            out.zero_()
+        for v0 in range(0, V, step):  # DMGS_MAX_STEP_VIEWS views per launch
+            v1 = min(V, v0 + step)
+            sh_grad_expand(self.records[v0:v1], [self._campos[v] for v in range(v0, v1)], means3D, sh_degree, out,
+                           sh_layout=sh_layout, accumulate=v0 > 0)
         return self.bufs[0]
 
     def all_reduce_(self, scale: float = 1.0) -> FlatGradBuffer:
@@ -244,10 +290,11 @@ class ViewStreams:
 
 
 def accumulate_view(settings, inputs: Dict[str, Optional[torch.Tensor]], image_grad: Callable, acc: Dict[str, torch.Tensor],
-                    sh_layout: int = 0, sh_activation: int = 0):
+                    sh_layout: int = 0, sh_activation: int = 0, sh_record=None):
     """One view forward + backward on the CUDA path with gradients ADDED into `acc`.
 
     inputs: means3D, opacities and the optional shs / colors_precomp / scales / rotations / cov3D_precomp.
+    sh_record: ViewStreams.sh_record(i, settings.campos) in deferred-SH mode (see ViewStreams).
     image_grad(image) -> (loss 0-d tensor or None, dL/dimage [3,H,W]).  Returns (loss, image, radii)."""
     from .rasterizer import rasterize_backward, rasterize_forward
     g = inputs.get
@@ -256,7 +303,7 @@ def accumulate_view(settings, inputs: Dict[str, Optional[torch.Tensor]], image_g
                                             sh_layout, sh_activation)
     loss, dL = image_grad(color)
     rasterize_backward(state, dL.contiguous(), inputs["means3D"], g("shs"), g("scales"), g("rotations"),
-                       g("cov3D_precomp"), g("colors_precomp") is not None, accumulate_into=acc)
+                       g("cov3D_precomp"), g("colors_precomp") is not None, accumulate_into=acc, sh_record=sh_record)
     return loss, color, radii
 
 

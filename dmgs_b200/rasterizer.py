@@ -251,9 +251,12 @@ def rasterize_forward(settings, means3D, opacities, shs, colors_precomp, scales,
 
 
 def rasterize_backward(state: RasterState, grad_color, means3D, shs, scales, rotations, cov3D_precomp,
-                       want_colors_precomp, stage_hook=None, accumulate_into=None):
+                       want_colors_precomp, stage_hook=None, accumulate_into=None, sh_record=None):
     """accumulate_into: optional dict of preallocated gradient tensors (keys means3D, means2D, opacities,
-    colors_precomp, shs, scales, rotations, cov3D_precomp) that the gradients are ADDED to."""
+    colors_precomp, shs, scales, rotations, cov3D_precomp) that the gradients are ADDED to.
+    sh_record: with accumulate_into, a float32 [P,4] tensor that receives this view's deferred SH gradient
+    record {g.r, g.g, g.b, seen} instead of the [P,16,3] rows being read-modify-written
+    (dmgs_preprocess_backward accumulate = 2; `sh_grad_expand` forms the rows once per step)."""
     lib = L.lib()
     prm, P, dev = state.prm, state.prm.P, means3D.device
     z = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
@@ -268,6 +271,10 @@ def rasterize_backward(state: RasterState, grad_color, means3D, shs, scales, rot
         g_means3D, g_means2D, g_op = a["means3D"], a["means2D"], a["opacities"]
         g_col = a.get("colors_precomp") if want_colors_precomp else None
         g_shs = a.get("shs") if shs is not None else None
+        if sh_record is not None and shs is not None:
+            if sh_record.shape != (P, 4) or sh_record.dtype != torch.float32 or not sh_record.is_contiguous():
+                raise ValueError("sh_record must be a contiguous float32 [P,4] tensor")
+            g_shs = sh_record
         g_scales = a.get("scales") if scales is not None else None
         g_rots = a.get("rotations") if rotations is not None else None
         g_cov = a.get("cov3D_precomp") if cov3D_precomp is not None else None
@@ -282,11 +289,31 @@ def rasterize_backward(state: RasterState, grad_color, means3D, shs, scales, rot
                                          L.ptr(cov3D_precomp), L.ptr(shs), L.ptr(state.radii), L.ptr(state.geom),
                                          L.ptr(scratch), L.ptr(g_means3D), L.ptr(g_means2D), L.ptr(g_op), L.ptr(g_col),
                                          L.ptr(g_shs), L.ptr(g_scales), L.ptr(g_rots), L.ptr(g_cov),
-                                         1 if accumulate_into is not None else 0, stream),
+                                         (2 if (sh_record is not None and shs is not None) else 1)
+                                         if accumulate_into is not None else 0, stream),
             "dmgs_preprocess_backward")
     if stage_hook is not None:
         stage_hook("preprocess_bwd")
     return g_means3D, g_means2D, g_shs, g_col, g_op, g_scales, g_rots, g_cov
+
+
+def sh_grad_expand(records, camera_centers, means3D, sh_degree, out, sh_layout=0, accumulate=False):
+    """Forms dL/dsh from the deferred records of a step's views (libdmgs_raster.so: dmgs_sh_grad_expand).
+    records: float32 [V,P,4] (views along dim 0); camera_centers: V tensors/sequences of 3 floats (the campos of
+    each view's settings, in the same order); out: the [P,M,3] (sh_layout 0) or [P,3,M] (1) gradient tensor,
+    overwritten (accumulate=False) or added to."""
+    V, P = int(records.shape[0]), int(records.shape[1])
+    M = int(out.shape[1] if sh_layout == 0 else out.shape[2])
+    cams = []
+    for c in camera_centers:
+        cams.extend(_host_values([c])[0] if isinstance(c, torch.Tensor) else [float(x) for x in c])
+    if len(cams) != 3 * V:
+        raise ValueError("one camera centre per view")
+    arr = (C.c_float * (3 * V))(*cams)
+    stride = int(records.stride(0)) if V > 1 else P * 4
+    L.check(L.lib().dmgs_sh_grad_expand(P, int(sh_degree), M, int(sh_layout), V, arr, L.ptr(means3D), L.ptr(records), stride,
+                                        L.ptr(out), int(bool(accumulate)), _stream()), "dmgs_sh_grad_expand")
+    return out
 
 
 class _RasterizeGaussians(torch.autograd.Function):

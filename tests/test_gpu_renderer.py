@@ -134,6 +134,43 @@ def test_view_streams_equal_single_stream():
         grad_close(out[1][name].reshape(P, -1), out[0][name].reshape(P, -1), rtol=2e-4, name=name)
 
 
+@pytest.mark.parametrize("layout", ["PM3", "P3M_sigmoid"])
+def test_deferred_sh_gradient_equals_row_accumulation(layout):
+    """ViewStreams(deferred_sh_views=...): 16-byte records per view + one dmgs_sh_grad_expand per step give the same
+    gradients as the read-modify-write of the SH rows every view (both SH layouts / activations; cameras on a
+    close orbit so that part of the cloud is culled in every view)."""
+    from dmgs_b200 import multiview as MV
+    from gpu_util import settings_for
+    P, W, H, NV = 6000, 160, 120, 5
+    cl = S.random_cloud(P, seed=10, extent=1.5, log_scale_mean=math.log(0.05))
+    d = {k: v.cuda() for k, v in cl.items()}
+    cams = [S.look_at_camera([1.6 * math.cos(v), 0.4, 1.6 * math.sin(v)], W, H, fovx=0.8) for v in range(NV)]
+    sets = [settings_for(c, (0, 0, 0)) for c in cams]
+    dLs = [torch.randn(3, H, W, generator=torch.Generator().manual_seed(v)).cuda() for v in range(NV)]
+    if layout == "PM3":
+        widths, shs, kw, lay = MV.RASTER_WIDTHS_SH, d["shs"], {}, 0
+    else:
+        widths = {"means3D": (3,), "means2D": (3,), "opacities": (1,), "scales": (3,), "rotations": (4,), "shs": (3, 16)}
+        shs, kw, lay = d["shs"].transpose(1, 2).contiguous(), dict(sh_layout=1, sh_activation=1), 1
+    inputs = dict(means3D=d["means3D"], opacities=d["opacities"], shs=shs, scales=d["scales"], rotations=d["rotations"])
+    out = []
+    for deferred in (0, NV):
+        vs = MV.ViewStreams(P, widths, torch.device("cuda"), n=2, deferred_sh_views=deferred)
+        for _ in range(2):  # twice: begin() resets the records' bookkeeping and the dense part
+            vs.begin()
+            for v in range(NV):
+                rec = vs.sh_record(v, sets[v].campos)
+                vs.run(v, lambda acc, v=v, rec=rec: MV.accumulate_view(sets[v], inputs, lambda img: (None, dLs[v]), acc,
+                                                                       sh_record=rec, **kw))
+            buf = vs.finish(d["means3D"], 3, sh_layout=lay)
+        torch.cuda.synchronize()
+        out.append({k: x.cpu().numpy().copy() for k, x in buf.views.items()})
+    assert np.abs(out[0]["shs"]).max() > 0
+    assert (out[1]["shs"].reshape(P, -1) == 0).all(axis=1).sum() > 0  # some Gaussians are seen by no view
+    for name in out[0]:
+        grad_close(out[1][name].reshape(P, -1), out[0][name].reshape(P, -1), rtol=2e-4, name=name)
+
+
 def test_async_binning_matches_sync_and_reports_overflow():
     """configure(async_binning=True): same image / gradients without the host read-back; a frame whose
     instance list outgrows the remembered capacity renders as background, check_async() reports it,
