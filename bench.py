@@ -278,12 +278,12 @@ def run_ours(args):
             for j, v in enumerate(my_views):
                 one_view(j, v, record, vs.buf.views)
             if deferred:
-                vs.finish(d["means3D"], 3)
+                vs.finish(d["means3D"], d["shs"], 3)
         else:
             vs.begin()
             for j, v in enumerate(my_views):
                 vs.run(j, lambda acc, j=j, v=v: one_view(j, v, False, acc))
-            vs.finish(d["means3D"], 3)
+            vs.finish(d["means3D"], d["shs"], 3)
         if world > 1:
             vs.all_reduce_()
         if not dmgs_b200.check_async():  # a frame overflowed its binning buffer: the step does not count
@@ -390,7 +390,7 @@ def run_ours(args):
             rec = vs.sh_record(j, settings[v].campos)
             losses.append(vs.run(j, lambda acc, v=v, dl=dl, rec=rec: MV.accumulate_view(
                 settings[v], inputs, lambda img: ((img * dl).sum(), dl), acc, sh_record=rec)[0]))
-        vs.finish(inputs["means3D"], 3)
+        vs.finish(inputs["means3D"], inputs["shs"], 3)
         if world > 1:
             vs.all_reduce_()
         host_loss = float(torch.stack(losses).sum().cpu())  # device -> host read of the step's result

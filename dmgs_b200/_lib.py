@@ -49,7 +49,7 @@ _SIGS = {
     "dmgs_mark_visible": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp]),
     "dmgs_bind_forward": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _f, _f, _vp, _i32, _vp, _vp, _vp, _vp]),
     "dmgs_bind_backward": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _f, _f, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "dmgs_sh_grad_expand": (C.c_int, [_i32, _i32, _i32, _i32, _i32, C.POINTER(_f), _vp, _vp, _i64, _vp, _i32, _vp]),
+    "dmgs_sh_grad_expand": (C.c_int, [_i32, _i32, _i32, _i32, _i32, C.POINTER(_f), _vp, _vp, _vp, _i64, _vp, _vp, _i32, _vp]),
     "dmgs_stage3_forward": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp]),
     "dmgs_stage3_backward": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dmgs_l1_ssim_scratch_bytes": (C.c_size_t, [_i32, _i32, _i32]),

@@ -306,13 +306,13 @@ int dmgs_bind_backward(int64_t F, int32_t k, const float *verts, const int64_t *
 }
 
 int dmgs_sh_grad_expand(int32_t P, int32_t sh_degree, int32_t sh_coeffs, int32_t sh_layout, int32_t n_views,
-                        const float *campos_host, const float *means3D, const float *records, int64_t view_stride,
-                        float *dL_dshs, int32_t accumulate, void *stream)
+                        const float *campos_host, const float *means3D, const float *shs, const float *records,
+                        int64_t view_stride, float *dL_dshs, float *dL_dmeans3D, int32_t accumulate, void *stream)
 {
     if (P < 0 || sh_degree < 0 || sh_degree > 3 || sh_coeffs < (sh_degree + 1) * (sh_degree + 1)) { set_error("sh_grad_expand: bad shape"); return -14; }
-    if (P > 0 && (!campos_host || !means3D || !records || !dL_dshs)) { set_error("sh_grad_expand: NULL pointer"); return -6; }
-    return launch_sh_grad_expand(P, sh_degree, sh_coeffs, sh_layout, n_views, campos_host, means3D, records, view_stride,
-                                 dL_dshs, accumulate, (cudaStream_t)stream);
+    if (P > 0 && (!campos_host || !means3D || !shs || !records || !dL_dshs || !dL_dmeans3D)) { set_error("sh_grad_expand: NULL pointer"); return -6; }
+    return launch_sh_grad_expand(P, sh_degree, sh_coeffs, sh_layout, n_views, campos_host, means3D, shs, records, view_stride,
+                                 dL_dshs, dL_dmeans3D, accumulate, (cudaStream_t)stream);
 }
 
 int dmgs_stage3_forward(int64_t F, int32_t k, const float *rot_t2w, const float *rotation2d, const float *scaling2d,

@@ -49,7 +49,8 @@ int launch_blend_bwd(const dmgs_params *prm, const void *geom, const GeomLayout 
                      float *grad_blend, cudaStream_t s);
 
 int launch_sh_grad_expand(int P, int sh_degree, int M, int layout, int V, const float *campos_host, const float *means3D,
-                          const float *records, int64_t view_stride, float *dL_dshs, int accumulate, cudaStream_t s);
+                          const float *shs, const float *records, int64_t view_stride, float *dL_dshs,
+                          float *dL_dmeans3D, int accumulate, cudaStream_t s);
 
 // stage3.cu
 int launch_stage3_fwd(int64_t F, int k, const float *rot_t2w, const float *rotation2d, const float *scaling2d,

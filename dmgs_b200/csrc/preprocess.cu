@@ -337,6 +337,38 @@ int launch_preprocess_fwd(const dmgs_params *prm, const float *means3D, const fl
     return 0;
 }
 
+// View-direction term of dL/dmean: the colour depends on the mean through dir = normalize(mean - campos).
+// h[k] = sum_ch sh[k][ch] * g[ch] (g = dL/dcolour after the activation); (ox,oy,oz) = mean - campos, s2 = |o|^2,
+// (dxn,dyn,dzn) = o / |o|.  Adds the gradient to gm.
+__device__ __forceinline__ void sh_dir_grad(int deg, const float *h, float ox, float oy, float oz, float s2, float dxn,
+                                            float dyn, float dzn, float *gm)
+{
+    if (deg > 0) {
+        const float xx = dxn * dxn, yy = dyn * dyn, zz = dzn * dzn, xy_ = dxn * dyn, yz = dyn * dzn, xz = dxn * dzn;
+        float ddx = -SH_C1 * h[3], ddy = -SH_C1 * h[1], ddz = SH_C1 * h[2];
+        if (deg > 1) {
+            ddx += SH_C2_0 * dyn * h[4] + SH_C2_2 * 2.0f * -dxn * h[6] + SH_C2_3 * dzn * h[7] + SH_C2_4 * 2.0f * dxn * h[8];
+            ddy += SH_C2_0 * dxn * h[4] + SH_C2_1 * dzn * h[5] + SH_C2_2 * 2.0f * -dyn * h[6] + SH_C2_4 * 2.0f * -dyn * h[8];
+            ddz += SH_C2_1 * dyn * h[5] + SH_C2_2 * 2.0f * 2.0f * dzn * h[6] + SH_C2_3 * dxn * h[7];
+            if (deg > 2) {
+                ddx += SH_C3_0 * h[9] * 3.0f * 2.0f * xy_ + SH_C3_1 * h[10] * yz + SH_C3_2 * h[11] * -2.0f * xy_ +
+                       SH_C3_3 * h[12] * -3.0f * 2.0f * xz + SH_C3_4 * h[13] * (-3.0f * xx + 4.0f * zz - yy) +
+                       SH_C3_5 * h[14] * 2.0f * xz + SH_C3_6 * h[15] * 3.0f * (xx - yy);
+                ddy += SH_C3_0 * h[9] * 3.0f * (xx - yy) + SH_C3_1 * h[10] * xz +
+                       SH_C3_2 * h[11] * (-3.0f * yy + 4.0f * zz - xx) + SH_C3_3 * h[12] * -3.0f * 2.0f * yz +
+                       SH_C3_4 * h[13] * -2.0f * xy_ + SH_C3_5 * h[14] * -2.0f * yz + SH_C3_6 * h[15] * -3.0f * 2.0f * xy_;
+                ddz += SH_C3_1 * h[10] * xy_ + SH_C3_2 * h[11] * 4.0f * 2.0f * yz +
+                       SH_C3_3 * h[12] * 3.0f * (2.0f * zz - xx - yy) + SH_C3_4 * h[13] * 4.0f * 2.0f * xz +
+                       SH_C3_5 * h[14] * (xx - yy);
+            }
+        }
+        const float inv3 = 1.0f / sqrtf(s2 * s2 * s2);
+        gm[0] += ((s2 - ox * ox) * ddx - oy * ox * ddy - oz * ox * ddz) * inv3;
+        gm[1] += (-ox * oy * ddx + (s2 - oy * oy) * ddy - oz * oy * ddz) * inv3;
+        gm[2] += (-ox * oz * ddx - oy * oz * ddy + (s2 - oz * oz) * ddz) * inv3;
+    }
+}
+
 // ------------------------------------------------------------------------------ backward
 // grad_blend: per Gaussian 12 floats {dmean2D.x, dmean2D.y, dconic.a, dconic.b(half), dconic.c,
 // dopacity, dcolor.r, dcolor.g, dcolor.b, pad x3} accumulated by the blend backward.
@@ -360,7 +392,7 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
     ShStage stage;
     if (SHMODE) {
         stage.init(dsm);
-        stage.load(vis && do_sh, shs + (size_t)i * SH_ROW_FLOATS);
+        stage.load(vis && do_sh && accumulate != 2, shs + (size_t)i * SH_ROW_FLOATS);
     }
     float gm[3] = {0, 0, 0}, g6[6] = {0, 0, 0, 0, 0, 0};
     float gs[3] = {0, 0, 0}, gq[4] = {0, 0, 0, 0};
@@ -471,10 +503,11 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
                 if (pr.sh_act == 0) g[ch] = (cb >> ch) & 1 ? 0.0f : dcol[ch];
                 else g[ch] = dcol[ch] * (sg[ch] * (1.0f - sg[ch]));
             }
-            // deferred mode: this view's contribution to dL/dsh is rank one per channel (basis(dir) x g), so
-            // only g is recorded -- 16 bytes instead of a 192-byte read-modify-write -- and
-            // sh_grad_expand_kernel forms the rows once per step from all views' records
+            // deferred mode: this view's contribution to dL/dsh is rank one per channel (basis(dir) x g) and its
+            // view-direction term of dL/dmean is linear in g as well, so only g is recorded -- 16 bytes, and the
+            // SH row is not even read -- and sh_grad_expand_kernel forms both once per step from all views' records
             if (accumulate == 2) reinterpret_cast<float4 *>(dL_dshs)[i] = make_float4(g[0], g[1], g[2], 1.0f);
+            if (accumulate != 2) {
             // h[k] = sum_ch sh[k][ch] * g[ch]: the view-direction gradient is linear in it, so the basis
             // Jacobian below is applied once instead of once per channel
             float h[16];
@@ -517,29 +550,7 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
                     }
                 }
             }
-            if (pr.sh_degree > 0) {
-                const float xx = dxn * dxn, yy = dyn * dyn, zz = dzn * dzn, xy_ = dxn * dyn, yz = dyn * dzn, xz = dxn * dzn;
-                float ddx = -SH_C1 * h[3], ddy = -SH_C1 * h[1], ddz = SH_C1 * h[2];
-                if (pr.sh_degree > 1) {
-                    ddx += SH_C2_0 * dyn * h[4] + SH_C2_2 * 2.0f * -dxn * h[6] + SH_C2_3 * dzn * h[7] + SH_C2_4 * 2.0f * dxn * h[8];
-                    ddy += SH_C2_0 * dxn * h[4] + SH_C2_1 * dzn * h[5] + SH_C2_2 * 2.0f * -dyn * h[6] + SH_C2_4 * 2.0f * -dyn * h[8];
-                    ddz += SH_C2_1 * dyn * h[5] + SH_C2_2 * 2.0f * 2.0f * dzn * h[6] + SH_C2_3 * dxn * h[7];
-                    if (pr.sh_degree > 2) {
-                        ddx += SH_C3_0 * h[9] * 3.0f * 2.0f * xy_ + SH_C3_1 * h[10] * yz + SH_C3_2 * h[11] * -2.0f * xy_ +
-                               SH_C3_3 * h[12] * -3.0f * 2.0f * xz + SH_C3_4 * h[13] * (-3.0f * xx + 4.0f * zz - yy) +
-                               SH_C3_5 * h[14] * 2.0f * xz + SH_C3_6 * h[15] * 3.0f * (xx - yy);
-                        ddy += SH_C3_0 * h[9] * 3.0f * (xx - yy) + SH_C3_1 * h[10] * xz +
-                               SH_C3_2 * h[11] * (-3.0f * yy + 4.0f * zz - xx) + SH_C3_3 * h[12] * -3.0f * 2.0f * yz +
-                               SH_C3_4 * h[13] * -2.0f * xy_ + SH_C3_5 * h[14] * -2.0f * yz + SH_C3_6 * h[15] * -3.0f * 2.0f * xy_;
-                        ddz += SH_C3_1 * h[10] * xy_ + SH_C3_2 * h[11] * 4.0f * 2.0f * yz +
-                               SH_C3_3 * h[12] * 3.0f * (2.0f * zz - xx - yy) + SH_C3_4 * h[13] * 4.0f * 2.0f * xz +
-                               SH_C3_5 * h[14] * (xx - yy);
-                    }
-                }
-                const float inv3 = 1.0f / sqrtf(s2 * s2 * s2);
-                gm[0] += ((s2 - ox * ox) * ddx - oy * ox * ddy - oz * ox * ddz) * inv3;
-                gm[1] += (-ox * oy * ddx + (s2 - oy * oy) * ddy - oz * oy * ddz) * inv3;
-                gm[2] += (-ox * oz * ddx - oy * oz * ddy + (s2 - oz * oz) * ddz) * inv3;
+            sh_dir_grad(pr.sh_degree, h, ox, oy, oz, s2, dxn, dyn, dzn, gm);
             }
         } else if (inb && accumulate == 2) {
             reinterpret_cast<float4 *>(dL_dshs)[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // not seen by this view
@@ -623,7 +634,7 @@ int launch_preprocess_bwd(const dmgs_params *prm, const float *means3D, const fl
         DMGS_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_STAGE_SMEM));
         attr_set = true;
     }
-    int mode = (dL_dshs && !(reinterpret_cast<uintptr_t>(dL_dshs) & 15)) ? sh_mode(prm, shs) : 0;
+    int mode = (accumulate != 2 && dL_dshs && !(reinterpret_cast<uintptr_t>(dL_dshs) & 15)) ? sh_mode(prm, shs) : 0;
     const DevParams dp = make_dev_params(prm);
 #define DMGS_BWD_ARGS                                                                                                  \
     dp, means3D, scales, rotations, cov3D_precomp, shs, radii, at<float>(geom, L.cov3D), at<uint8_t>(geom, L.clamped), \
@@ -640,9 +651,11 @@ int launch_preprocess_bwd(const dmgs_params *prm, const float *means3D, const fl
 }
 
 // ------------------------------------------------------------------------------ deferred SH gradient
-// dL/dsh[i] = sum over the step's views v that saw Gaussian i of basis(dir_v(i)) (x) g_v(i), from the
-// 16-byte records {g.r, g.g, g.b, seen} written by preprocess_bwd_kernel (accumulate == 2).  Per Gaussian
-// and step this moves V * 16 B of records + one 192-byte row instead of V read-modify-writes of the row.
+// dL/dsh[i] = sum over the step's views v that saw Gaussian i of basis(dir_v(i)) (x) g_v(i), and the
+// view-direction term of dL/dmean[i] (linear in g_v as well), from the 16-byte records {g.r, g.g, g.b,
+// seen} written by preprocess_bwd_kernel (accumulate == 2).  Per Gaussian and step this moves V * 16 B of
+// records, one read of the coefficient row and one write of the gradient row instead of V reads of the
+// coefficients and V read-modify-writes of the gradient row.
 struct ExpandArgs {
     int P, V, sh_degree, M, layout, accumulate;
     long long view_stride;  // floats between two views' record arrays
@@ -651,40 +664,78 @@ struct ExpandArgs {
 
 template <int SHMODE>
 __global__ void __launch_bounds__(256)
-sh_grad_expand_kernel(const __grid_constant__ ExpandArgs a, const float *__restrict__ means3D,
-                      const float *__restrict__ records, float *__restrict__ dL_dshs)
+sh_grad_expand_kernel(const __grid_constant__ ExpandArgs a, const float *__restrict__ means3D, const float *__restrict__ shs,
+                      const float *__restrict__ records, float *__restrict__ dL_dshs, float *__restrict__ dL_dmeans3D)
 {
     extern __shared__ __align__(16) unsigned char dsm[];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool inb = i < a.P;
     ShStage stage;
-    if (SHMODE) stage.init(dsm);
-    float acc[16][3];
+    if (SHMODE) {
+        stage.init(dsm);
+        stage.load(inb, shs + (size_t)i * SH_ROW_FLOATS);  // the coefficients: needed for the direction term
+    }
+    float acc[16][3], gm[3] = {0.0f, 0.0f, 0.0f};
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc[k][0] = acc[k][1] = acc[k][2] = 0.0f;
     bool any = false;
+    float x = 0, y = 0, z = 0;
+    if (inb) { x = means3D[3 * (size_t)i]; y = means3D[3 * (size_t)i + 1]; z = means3D[3 * (size_t)i + 2]; }
+    if (SHMODE) stage.wait();
     if (inb) {
-        const float x = means3D[3 * (size_t)i], y = means3D[3 * (size_t)i + 1], z = means3D[3 * (size_t)i + 2];
         for (int v = 0; v < a.V; ++v) {
-            const float4 g = reinterpret_cast<const float4 *>(records + (size_t)v * a.view_stride)[i];
-            if (g.w == 0.0f) continue;
+            const float4 g4 = reinterpret_cast<const float4 *>(records + (size_t)v * a.view_stride)[i];
+            if (g4.w == 0.0f) continue;
             any = true;
+            const float g[3] = {g4.x, g4.y, g4.z};
             const float ox = x - a.cam[v][0], oy = y - a.cam[v][1], oz = z - a.cam[v][2];
-            const float len = sqrtf(dot3(ox, ox, oy, oy, oz, oz));
-            float bas[16];
-            const int nb = sh_basis(a.sh_degree, ox / len, oy / len, oz / len, bas);
+            const float s2 = dot3(ox, ox, oy, oy, oz, oz);
+            const float len = sqrtf(s2);
+            const float dxn = ox / len, dyn = oy / len, dzn = oz / len;
+            float bas[16], h[16];
+            const int nb = sh_basis(a.sh_degree, dxn, dyn, dzn, bas);
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
+                h[k] = 0.0f;
                 if (k < nb) {
-                    acc[k][0] = fma_(bas[k], g.x, acc[k][0]);
-                    acc[k][1] = fma_(bas[k], g.y, acc[k][1]);
-                    acc[k][2] = fma_(bas[k], g.z, acc[k][2]);
+                    acc[k][0] = fma_(bas[k], g[0], acc[k][0]);
+                    acc[k][1] = fma_(bas[k], g[1], acc[k][1]);
+                    acc[k][2] = fma_(bas[k], g[2], acc[k][2]);
                 }
             }
+            if (a.sh_degree > 0) {
+                // h[k] = sum_ch sh[k][ch] * g[ch], streamed from the staged row (or read directly)
+                if (SHMODE) {
+                    const float4 *row4 = reinterpret_cast<const float4 *>(stage.row);
+#pragma unroll
+                    for (int j = 0; j < SH_ROW_FLOATS / 4; ++j) {
+                        const float4 q4 = row4[j];
+                        const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int f = 4 * j + c;
+                            const int k = SHMODE == 1 ? f / 3 : f % 16, ch = SHMODE == 1 ? f % 3 : f / 16;
+                            h[k] = k < nb ? fma_(qv[c], g[ch], h[k]) : h[k];
+                        }
+                    }
+                } else {
+                    for (int ch = 0; ch < 3; ++ch)
+                        for (int k = 0; k < nb; ++k) {
+                            const size_t idx = a.layout == 0 ? ((size_t)i * a.M + k) * 3 + ch : ((size_t)i * 3 + ch) * a.M + k;
+                            h[k] = fma_(__ldg(shs + idx), g[ch], h[k]);
+                        }
+                }
+                sh_dir_grad(a.sh_degree, h, ox, oy, oz, s2, dxn, dyn, dzn, gm);
+            }
+        }
+        if (any && a.sh_degree > 0) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) dL_dmeans3D[3 * (size_t)i + k] += gm[k];
         }
     }
     if (SHMODE) {
         // overwrite: every in-range row (zeros when no view saw the Gaussian); accumulate: rows with a gradient
+        __syncwarp();
         if (inb && (any || !a.accumulate)) {
             float4 *row4 = reinterpret_cast<float4 *>(stage.row);
 #pragma unroll
@@ -712,7 +763,8 @@ sh_grad_expand_kernel(const __grid_constant__ ExpandArgs a, const float *__restr
 }
 
 int launch_sh_grad_expand(int P, int sh_degree, int M, int layout, int V, const float *campos_host, const float *means3D,
-                          const float *records, int64_t view_stride, float *dL_dshs, int accumulate, cudaStream_t s)
+                          const float *shs, const float *records, int64_t view_stride, float *dL_dshs,
+                          float *dL_dmeans3D, int accumulate, cudaStream_t s)
 {
     if (P <= 0) return 0;
     if (V < 0 || V > DMGS_MAX_STEP_VIEWS) { set_error("sh_grad_expand: 0..%d views per call, got %d", DMGS_MAX_STEP_VIEWS, V); return -14; }
@@ -728,11 +780,11 @@ int launch_sh_grad_expand(int P, int sh_degree, int M, int layout, int V, const 
     a.view_stride = view_stride;
     for (int v = 0; v < V; ++v)
         for (int c = 0; c < 3; ++c) a.cam[v][c] = campos_host[3 * v + c];
-    const bool staged = M == 16 && !(reinterpret_cast<uintptr_t>(dL_dshs) & 15);
+    const bool staged = M == 16 && !((reinterpret_cast<uintptr_t>(dL_dshs) | reinterpret_cast<uintptr_t>(shs)) & 15);
     const int grid = (P + 255) / 256;
-    if (staged && layout == 0) sh_grad_expand_kernel<1><<<grid, 256, SH_STAGE_SMEM, s>>>(a, means3D, records, dL_dshs);
-    else if (staged) sh_grad_expand_kernel<2><<<grid, 256, SH_STAGE_SMEM, s>>>(a, means3D, records, dL_dshs);
-    else sh_grad_expand_kernel<0><<<grid, 256, 0, s>>>(a, means3D, records, dL_dshs);
+    if (staged && layout == 0) sh_grad_expand_kernel<1><<<grid, 256, SH_STAGE_SMEM, s>>>(a, means3D, shs, records, dL_dshs, dL_dmeans3D);
+    else if (staged) sh_grad_expand_kernel<2><<<grid, 256, SH_STAGE_SMEM, s>>>(a, means3D, shs, records, dL_dshs, dL_dmeans3D);
+    else sh_grad_expand_kernel<0><<<grid, 256, 0, s>>>(a, means3D, shs, records, dL_dshs, dL_dmeans3D);
     DMGS_CUDA(cudaGetLastError());
     count_launches(1);
     return 0;

@@ -248,9 +248,11 @@ class ViewStreams:
         self._used = max(self._used, i + 1)
         return self.records[i]
 
-    def finish(self, means3D: Optional[torch.Tensor] = None, sh_degree: int = 3, sh_layout: int = 0) -> FlatGradBuffer:
+    def finish(self, means3D: Optional[torch.Tensor] = None, shs: Optional[torch.Tensor] = None, sh_degree: int = 3,
+               sh_layout: int = 0, means3D_key: str = "means3D") -> FlatGradBuffer:
         """Joins the streams on the current stream and returns the buffer holding the sum of all views
-        (deferred SH mode: means3D / sh_degree / sh_layout of the step are needed to form the SH rows)."""
+        (deferred SH mode: means3D / shs / sh_degree / sh_layout of the step are needed to form the SH rows and
+        the view-direction term of the means3D gradient)."""
         cur = torch.cuda.current_stream(self.device)
         for st in self.streams:
             if st is not None:
@@ -261,8 +263,8 @@ class ViewStreams:
             return self.bufs[0]
         for b in self.bufs[1:]:
             self.bufs[0].flat[:self._dense].add_(b.flat[:self._dense])
-        if means3D is None:
-            raise ValueError("deferred SH mode: finish(means3D, sh_degree) forms the SH gradient rows")
+        if means3D is None or shs is None:
+            raise ValueError("deferred SH mode: finish(means3D, shs, sh_degree) forms the SH gradient rows")
         if sorted(self._campos) != list(range(self._used)):
             raise RuntimeError("deferred SH mode: every view 0..n-1 of the step must have taken its sh_record")
         from .rasterizer import sh_grad_expand
@@ -272,8 +274,8 @@ class ViewStreams:
             out.zero_()
         for v0 in range(0, V, step):  # DMGS_MAX_STEP_VIEWS views per launch
             v1 = min(V, v0 + step)
-            sh_grad_expand(self.records[v0:v1], [self._campos[v] for v in range(v0, v1)], means3D, sh_degree, out,
-                           sh_layout=sh_layout, accumulate=v0 > 0)
+            sh_grad_expand(self.records[v0:v1], [self._campos[v] for v in range(v0, v1)], means3D, shs, sh_degree, out,
+                           self.bufs[0].views[means3D_key], sh_layout=sh_layout, accumulate=v0 > 0)
         return self.bufs[0]
 
     def all_reduce_(self, scale: float = 1.0) -> FlatGradBuffer:

@@ -297,11 +297,12 @@ def rasterize_backward(state: RasterState, grad_color, means3D, shs, scales, rot
     return g_means3D, g_means2D, g_shs, g_col, g_op, g_scales, g_rots, g_cov
 
 
-def sh_grad_expand(records, camera_centers, means3D, sh_degree, out, sh_layout=0, accumulate=False):
-    """Forms dL/dsh from the deferred records of a step's views (libdmgs_raster.so: dmgs_sh_grad_expand).
-    records: float32 [V,P,4] (views along dim 0); camera_centers: V tensors/sequences of 3 floats (the campos of
-    each view's settings, in the same order); out: the [P,M,3] (sh_layout 0) or [P,3,M] (1) gradient tensor,
-    overwritten (accumulate=False) or added to."""
+def sh_grad_expand(records, camera_centers, means3D, shs, sh_degree, out, out_means3D, sh_layout=0, accumulate=False):
+    """Forms dL/dsh and the view-direction term of dL/dmeans3D from the deferred records of a step's views
+    (libdmgs_raster.so: dmgs_sh_grad_expand).  records: float32 [V,P,4] (views along dim 0); camera_centers: V
+    tensors/sequences of 3 floats (the campos of each view's settings, in the same order); shs: the coefficients;
+    out: the [P,M,3] (sh_layout 0) or [P,3,M] (1) gradient tensor, overwritten (accumulate=False) or added to;
+    out_means3D: [P,3], always added to."""
     V, P = int(records.shape[0]), int(records.shape[1])
     M = int(out.shape[1] if sh_layout == 0 else out.shape[2])
     cams = []
@@ -311,8 +312,9 @@ def sh_grad_expand(records, camera_centers, means3D, sh_degree, out, sh_layout=0
         raise ValueError("one camera centre per view")
     arr = (C.c_float * (3 * V))(*cams)
     stride = int(records.stride(0)) if V > 1 else P * 4
-    L.check(L.lib().dmgs_sh_grad_expand(P, int(sh_degree), M, int(sh_layout), V, arr, L.ptr(means3D), L.ptr(records), stride,
-                                        L.ptr(out), int(bool(accumulate)), _stream()), "dmgs_sh_grad_expand")
+    L.check(L.lib().dmgs_sh_grad_expand(P, int(sh_degree), M, int(sh_layout), V, arr, L.ptr(means3D), L.ptr(shs),
+                                        L.ptr(records), stride, L.ptr(out), L.ptr(out_means3D), int(bool(accumulate)),
+                                        _stream()), "dmgs_sh_grad_expand")
     return out
 
 

@@ -111,16 +111,19 @@ int dmgs_preprocess_backward(const dmgs_params *prm, const float *means3D, const
 
 /* ---- deferred SH gradient for view-batched training (dmgs_preprocess_backward with accumulate = 2).
  * A view's contribution to dL/dsh is rank one per channel, basis(dir) (x) g with g = dL/dcolour after the
- * activation, so in this mode dmgs_preprocess_backward does NOT touch the SH gradient rows: its dL_dshs
- * argument is this view's record array float[P][4] = {g.r, g.g, g.b, seen} (every other gradient is
- * accumulated as with accumulate = 1).  Once per step dmgs_sh_grad_expand forms the rows from the
- * records of all V views (records + v * view_stride floats, campos_host [V,3] HOST floats: the cameras'
- * centres) and stores (accumulate = 0) or adds (accumulate = 1) them: V * 16 B + one 192-byte row per
- * Gaussian and step instead of V read-modify-writes of the row.                                     */
+ * activation, and its view-direction term of dL/dmean is linear in g as well.  In this mode
+ * dmgs_preprocess_backward does NOT touch the SH rows (neither the coefficients nor their gradients): its
+ * dL_dshs argument is this view's record array float[P][4] = {g.r, g.g, g.b, seen} (every other gradient is
+ * accumulated as with accumulate = 1, the view-direction term of dL_dmeans3D excepted).  Once per step
+ * dmgs_sh_grad_expand forms the gradient rows from the records of all V views (records + v * view_stride
+ * floats; campos_host [V,3] HOST floats: the cameras' centres), stores (accumulate = 0) or adds
+ * (accumulate = 1) them, and ADDS the view-direction term to dL_dmeans3D (shs = the coefficients):
+ * V * 16 B + one coefficient row + one gradient row per Gaussian and step instead of V reads of the
+ * coefficients and V read-modify-writes of the gradient row.                                      */
 #define DMGS_MAX_STEP_VIEWS 32
 int dmgs_sh_grad_expand(int32_t P, int32_t sh_degree, int32_t sh_coeffs, int32_t sh_layout, int32_t n_views,
-                        const float *campos_host, const float *means3D, const float *records, int64_t view_stride,
-                        float *dL_dshs, int32_t accumulate, void *stream);
+                        const float *campos_host, const float *means3D, const float *shs, const float *records,
+                        int64_t view_stride, float *dL_dshs, float *dL_dmeans3D, int32_t accumulate, void *stream);
 
 /* ---- markVisible (K10): visible[i] = view-space z > 0.2 */
 int dmgs_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,

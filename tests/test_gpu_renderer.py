@@ -162,7 +162,7 @@ def test_deferred_sh_gradient_equals_row_accumulation(layout):
                 rec = vs.sh_record(v, sets[v].campos)
                 vs.run(v, lambda acc, v=v, rec=rec: MV.accumulate_view(sets[v], inputs, lambda img: (None, dLs[v]), acc,
                                                                        sh_record=rec, **kw))
-            buf = vs.finish(d["means3D"], 3, sh_layout=lay)
+            buf = vs.finish(d["means3D"], shs, 3, sh_layout=lay)
         torch.cuda.synchronize()
         out.append({k: x.cpu().numpy().copy() for k, x in buf.views.items()})
     assert np.abs(out[0]["shs"]).max() > 0
