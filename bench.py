@@ -36,7 +36,7 @@ WORKLOADS = {
     "c3": (1_000_000, 1245, 825, "bicycle", 3.0, math.log(0.008)),
 }
 VIEWS_PER_RANK = int(os.environ.get("DMGS_BENCH_VIEWS", "8"))
-N_STREAMS = int(os.environ.get("DMGS_BENCH_STREAMS", "2"))
+N_STREAMS = int(os.environ.get("DMGS_BENCH_STREAMS", "4"))
 
 
 def make_camera(kind, idx, W, H):
