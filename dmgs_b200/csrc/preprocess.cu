@@ -372,8 +372,9 @@ __device__ __forceinline__ void sh_dir_grad(int deg, const float *h, float ox, f
 // ------------------------------------------------------------------------------ backward
 // grad_blend: per Gaussian 12 floats {dmean2D.x, dmean2D.y, dconic.a, dconic.b(half), dconic.c,
 // dopacity, dcolor.r, dcolor.g, dcolor.b, pad x3} accumulated by the blend backward.
+// SHMODE 3 = deferred SH gradient (accumulate == 2): no SH row is read or written, only the 16-byte record
 template <int SHMODE>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, SHMODE == 3 ? 4 : 3)
 preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restrict__ means3D, const float *__restrict__ scales,
                       const float *__restrict__ rotations, const float *__restrict__ cov3D_precomp,
                       const float *__restrict__ shs, const int32_t *__restrict__ radii,
@@ -385,14 +386,15 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
                       const int accumulate)
 {
     extern __shared__ __align__(16) unsigned char dsm[];
+    constexpr bool STAGED = SHMODE == 1 || SHMODE == 2, DEFER = SHMODE == 3;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool inb = i < pr.P;
     const bool vis = inb && radii[i] > 0;
     const bool do_sh = shs && dL_dshs;
     ShStage stage;
-    if (SHMODE) {
+    if (STAGED) {
         stage.init(dsm);
-        stage.load(vis && do_sh && accumulate != 2, shs + (size_t)i * SH_ROW_FLOATS);
+        stage.load(vis && do_sh, shs + (size_t)i * SH_ROW_FLOATS);
     }
     float gm[3] = {0, 0, 0}, g6[6] = {0, 0, 0, 0, 0, 0};
     float gs[3] = {0, 0, 0}, gq[4] = {0, 0, 0, 0};
@@ -485,7 +487,7 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
     }
 
     // ---- SH backward: dL/dsh rows and the view-direction term of dL/dmean
-    if (SHMODE) stage.wait();  // warp-uniform
+    if (STAGED) stage.wait();  // warp-uniform
     if (do_sh) {
         if (vis) {
             const float ox = x - pr.cam[0], oy = y - pr.cam[1], oz = z - pr.cam[2];
@@ -506,14 +508,14 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
             // deferred mode: this view's contribution to dL/dsh is rank one per channel (basis(dir) x g) and its
             // view-direction term of dL/dmean is linear in g as well, so only g is recorded -- 16 bytes, and the
             // SH row is not even read -- and sh_grad_expand_kernel forms both once per step from all views' records
-            if (accumulate == 2) reinterpret_cast<float4 *>(dL_dshs)[i] = make_float4(g[0], g[1], g[2], 1.0f);
-            if (accumulate != 2) {
+            if (DEFER) reinterpret_cast<float4 *>(dL_dshs)[i] = make_float4(g[0], g[1], g[2], 1.0f);
+            if (!DEFER) {
             // h[k] = sum_ch sh[k][ch] * g[ch]: the view-direction gradient is linear in it, so the basis
             // Jacobian below is applied once instead of once per channel
             float h[16];
 #pragma unroll
             for (int k = 0; k < 16; ++k) h[k] = 0.0f;
-            if (SHMODE) {
+            if (STAGED) {
                 // stream the staged row in place: read 4 coefficients, write their 4 gradients back
                 float4 *row4 = reinterpret_cast<float4 *>(stage.row);
 #pragma unroll
@@ -529,7 +531,7 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
                         h[k] = on ? fma_(qv[c], g[ch], h[k]) : h[k];
                         ov[c] = on ? bas[k] * g[ch] : 0.0f;
                     }
-                    if (accumulate != 2) row4[j] = make_float4(ov[0], ov[1], ov[2], ov[3]);
+                    row4[j] = make_float4(ov[0], ov[1], ov[2], ov[3]);
                 }
             } else {
 #pragma unroll
@@ -539,7 +541,7 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
                         const size_t idx = pr.sh_layout == 0 ? ((size_t)i * M + k) * 3 + ch : ((size_t)i * 3 + ch) * M + k;
                         if (k < nb) {
                             h[k] = fma_(__ldg(shs + idx), g[ch], h[k]);
-                            if (accumulate != 2) dL_dshs[idx] = accumulate ? dL_dshs[idx] + bas[k] * g[ch] : bas[k] * g[ch];
+                            dL_dshs[idx] = accumulate ? dL_dshs[idx] + bas[k] * g[ch] : bas[k] * g[ch];
                         } else if (k < M && !accumulate) {
                             dL_dshs[idx] = 0.0f;
                         }
@@ -552,10 +554,10 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
             }
             sh_dir_grad(pr.sh_degree, h, ox, oy, oz, s2, dxn, dyn, dzn, gm);
             }
-        } else if (inb && accumulate == 2) {
+        } else if (inb && DEFER) {
             reinterpret_cast<float4 *>(dL_dshs)[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // not seen by this view
         } else if (inb && !accumulate) {
-            if (SHMODE) {  // culled Gaussian: a row of zeros
+            if (STAGED) {  // culled Gaussian: a row of zeros
                 float4 *row4 = reinterpret_cast<float4 *>(stage.row);
 #pragma unroll
                 for (int j = 0; j < SH_ROW_FLOATS / 4; ++j) row4[j] = make_float4(0, 0, 0, 0);
@@ -563,9 +565,9 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
                 for (int k = 0; k < 3 * M; ++k) dL_dshs[(size_t)i * 3 * M + k] = 0.0f;
             }
         }
-        if (SHMODE) {
+        if (STAGED) {
             // store: every in-range row (zeros for culled Gaussians); accumulate: only rows with a gradient
-            if (accumulate != 2 && inb && (vis || !accumulate))
+            if (inb && (vis || !accumulate))
                 stage.flush_row(dL_dshs + (size_t)i * SH_ROW_FLOATS, accumulate != 0);
         }
     }
@@ -617,7 +619,7 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
             if (dL_drots) reinterpret_cast<float4 *>(dL_drots)[i] = make_float4(gq[0], gq[1], gq[2], gq[3]);
         }
     }
-    if (SHMODE) stage.flush();  // shared rows must stay valid until the bulk stores have read them
+    if (STAGED) stage.flush();  // shared rows must stay valid until the bulk stores have read them
 }
 
 int launch_preprocess_bwd(const dmgs_params *prm, const float *means3D, const float *scales, const float *rotations,
@@ -634,7 +636,11 @@ int launch_preprocess_bwd(const dmgs_params *prm, const float *means3D, const fl
         DMGS_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_STAGE_SMEM));
         attr_set = true;
     }
-    int mode = (accumulate != 2 && dL_dshs && !(reinterpret_cast<uintptr_t>(dL_dshs) & 15)) ? sh_mode(prm, shs) : 0;
+    int mode = (dL_dshs && !(reinterpret_cast<uintptr_t>(dL_dshs) & 15)) ? sh_mode(prm, shs) : 0;
+    if (accumulate == 2) {
+        if (!dL_dshs || !shs || (reinterpret_cast<uintptr_t>(dL_dshs) & 15)) { set_error("accumulate = 2 needs shs and a 16-byte aligned record array"); return -6; }
+        mode = 3;
+    }
     const DevParams dp = make_dev_params(prm);
 #define DMGS_BWD_ARGS                                                                                                  \
     dp, means3D, scales, rotations, cov3D_precomp, shs, radii, at<float>(geom, L.cov3D), at<uint8_t>(geom, L.clamped), \
@@ -643,6 +649,7 @@ int launch_preprocess_bwd(const dmgs_params *prm, const float *means3D, const fl
     const int grid = (P + 255) / 256;
     if (mode == 1) preprocess_bwd_kernel<1><<<grid, 256, SH_STAGE_SMEM, s>>>(DMGS_BWD_ARGS);
     else if (mode == 2) preprocess_bwd_kernel<2><<<grid, 256, SH_STAGE_SMEM, s>>>(DMGS_BWD_ARGS);
+    else if (mode == 3) preprocess_bwd_kernel<3><<<grid, 256, 0, s>>>(DMGS_BWD_ARGS);
     else preprocess_bwd_kernel<0><<<grid, 256, 0, s>>>(DMGS_BWD_ARGS);
 #undef DMGS_BWD_ARGS
     DMGS_CUDA(cudaGetLastError());
