@@ -35,6 +35,10 @@ WORKLOADS = {
     "c1": (100_000, 800, 800, "nerf", 1.3, math.log(0.01)),
     "c3": (1_000_000, 1245, 825, "bicycle", 3.0, math.log(0.008)),
 }
+# DRAM bytes per launch of the kernels that can dominate, from the committed ncu --set full capture of workload
+# H0 (profiles/r1_s6_ncu_full_h0_raw.csv); far below the algorithmic bytes for the blend kernels because
+# only ~8 % of every tile's list is consumed before its pixels saturate and the records are served from L2
+NCU_TRAFFIC = {("h0", "blend_bwd"): 38.9e6, ("h0", "blend_fwd"): 27.2e6, ("h0", "preprocess_bwd"): 208.0e6}
 VIEWS_PER_RANK = int(os.environ.get("DMGS_BENCH_VIEWS", "8"))
 N_STREAMS = int(os.environ.get("DMGS_BENCH_STREAMS", "4"))
 
@@ -438,7 +442,9 @@ def run_ours(args):
         "binning": 8 * Ravg + 2 * 16 * Ravg + 4 * Ravg + 8 * T,
         "blend_fwd": 40 * Ravg + 20 * W * H,
         "blend_bwd": 40 * Ravg + 20 * W * H + 40 * P,
-        "preprocess_bwd": P * (B_in + B_geo + 40) + P * B_gin,
+        # deferred SH gradient: no SH row is read or written by the per-view kernel (44 B of other inputs, the
+        # state, the blend's 48-byte gradient record, 13 small gradients read-modify-written, a 16-byte record)
+        "preprocess_bwd": P * (44 + B_geo + 48 + 2 * 52 + 16) if deferred else P * (B_in + B_geo + 40) + P * B_gin,
     }
     single = ["blend_fwd", "blend_bwd", "preprocess_bwd"]
     dom = max(single, key=lambda k: stage_ms.get(k, 0.0))
@@ -465,7 +471,9 @@ def run_ours(args):
                    "steps_repeated_after_overflow": stats["redone"], "l2": "inputs (236 MB) + state (>230 MB) exceed the 126 MB L2; no flush needed"},
         "stages": stages,
         "roofline": {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                     "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": ach / peak, "traffic": NCU_TRAFFIC.get((args.workload, dom)), "peak_source": peak_src,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture "
+                                       "profiles/r1_s6_ncu_full_h0_raw.csv" if (args.workload, dom) in NCU_TRAFFIC else None,
                      "note": "blend kernels are FP32-issue bound, not HBM bound (DESIGN.md section 5)"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "steps": Ke, "api": "dmgs_b200.multiview training step (ViewStreams + accumulate_view over the C ABI), "
