@@ -124,7 +124,7 @@ __device__ __forceinline__ float sh_get(const float *__restrict__ shs, const Dev
 }
 
 template <int SHMODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 preprocess_fwd_kernel(const __grid_constant__ DevParams pr, const float *__restrict__ means3D, const float *__restrict__ scales,
                       const float *__restrict__ rotations, const float *__restrict__ cov3D_precomp,
                       const float *__restrict__ opacities, const float *__restrict__ shs,
