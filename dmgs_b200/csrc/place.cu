@@ -81,9 +81,11 @@ sorted_rect_kernel(int P, const uint32_t *__restrict__ order_a, const uint32_t *
 }
 
 // ------------------------------------------------------------------------------ A: count
-// lane <-> Gaussian; order is irrelevant for counting, so lanes add their rectangles with shared
-// atomics.  Each warp writes its row of table[nseg][T]; the CTA also writes the sum of its rows to
-// gsum[cta][T], the coarse level of the column scan.
+// Every warp counts the tiles its segment touches as a 2-D difference image: a rectangle [x0,x1) x [y0,y1)
+// is FOUR shared atomics (+1, -1, -1, +1 at its corners on a (gy+1) x (gx+1) grid), whatever its size, instead
+// of one per covered tile; two prefix passes (lanes over rows, then lanes over columns; row stride gx+1 is
+// odd for the common image sizes, so both passes are bank-conflict free) turn the image into the per-tile counts.  Each warp writes its row
+// of table[nseg][T]; the CTA also writes the sum of its rows to gsum[cta][T], the coarse level of the column scan.
 __global__ void __launch_bounds__(128)
 tile_count_kernel(int P, int T, int gx, int seg, int nseg, const uint4 *__restrict__ srec, uint32_t *__restrict__ table,
                   uint32_t *__restrict__ gsum)
@@ -91,31 +93,40 @@ tile_count_kernel(int P, int T, int gx, int seg, int nseg, const uint4 *__restri
     extern __shared__ uint32_t s_cnt[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int sg = blockIdx.x * wpb + w;
-    uint32_t *cnt = s_cnt + (size_t)w * T;
-    for (int t = lane; t < T; t += 32) cnt[t] = 0;
+    const int gy = T / gx, sx = gx + 1, G = sx * (gy + 1);
+    uint32_t *cnt = s_cnt + (size_t)w * G;
+    for (int t = lane; t < G; t += 32) cnt[t] = 0;
     __syncwarp();
     if (sg < nseg) {
         const int s0 = sg * seg, s1 = min(P, s0 + seg);
-        uint4 nxt = s0 + lane < s1 ? srec[s0 + lane] : make_uint4(0, 0, 0, 0);
-        for (int sb = s0; sb < s1; sb += 32) {
-            const uint4 rc = nxt;
-            const int sn = sb + 32 + lane;
-            nxt = sn < s1 ? srec[sn] : make_uint4(0, 0, 0, 0);  // prefetch the next batch
+        for (int sb = s0 + lane; sb < s1; sb += 32) {
+            const uint4 rc = srec[sb];
             const int x0 = rc.x & 0xffff, x1 = rc.x >> 16, y0 = rc.y & 0xffff, y1 = rc.y >> 16;
-            for (int y = y0; y < y1; ++y) {
-                uint32_t *rowp = cnt + y * gx;
-                for (int x = x0; x < x1; ++x) atomicAdd(rowp + x, 1u);
+            if (x1 > x0 && y1 > y0) {
+                atomicAdd(cnt + y0 * sx + x0, 1u);
+                atomicAdd(cnt + y0 * sx + x1, 0xffffffffu);
+                atomicAdd(cnt + y1 * sx + x0, 0xffffffffu);
+                atomicAdd(cnt + y1 * sx + x1, 1u);
             }
         }
         __syncwarp();
+        for (int y = lane; y < gy; y += 32) {  // prefix along x
+            uint32_t run = 0;
+            for (int x = 0; x < gx; ++x) { run += cnt[y * sx + x]; cnt[y * sx + x] = run; }
+        }
+        __syncwarp();
         uint32_t *row = table + (size_t)sg * T;
-        for (int t = lane; t < T; t += 32) row[t] = cnt[t];
+        for (int x = lane; x < gx; x += 32) {  // prefix along y; the finished counts go straight to the table
+            uint32_t run = 0;
+            for (int y = 0; y < gy; ++y) { run += cnt[y * sx + x]; cnt[y * sx + x] = run; row[y * gx + x] = run; }
+        }
     }
     __syncthreads();
     uint32_t *grow = gsum + (size_t)blockIdx.x * T;
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        const int y = t / gx, x = t - y * gx;
         uint32_t sum = 0;
-        for (int k = 0; k < wpb; ++k) sum += s_cnt[(size_t)k * T + t];
+        for (int k = 0; k < wpb; ++k) sum += s_cnt[(size_t)k * G + y * sx + x];
         grow[t] = sum;
     }
 }
@@ -296,7 +307,8 @@ int launch_tile_placement(const PlacePlan &pl, int P, int T, int gx, const uint3
     const int threads = pl.wpb * 32;
     const int blocks = pl.groups;
     sorted_rect_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, order_a, order_b, stat, rect, srec);
-    tile_count_kernel<<<blocks, threads, pl.smem, s>>>(P, T, gx, pl.seg, pl.nseg, srec, table, gsum);
+    const size_t count_smem = (size_t)pl.wpb * (gx + 1) * (T / gx + 1) * sizeof(uint32_t);  // the difference images
+    tile_count_kernel<<<blocks, threads, count_smem, s>>>(P, T, gx, pl.seg, pl.nseg, srec, table, gsum);
     group_scan_kernel<<<(T + 31) / 32, GS_WARPS * 32, 0, s>>>(T, pl.groups, gsum, tile_start);
     tile_scan_kernel<<<1, 1024, 0, s>>>(T, tile_start, ranges, (uint32_t)capacity, overflow);
     tile_place_kernel<<<blocks, threads, pl.smem, s>>>(P, T, gx, pl.seg, pl.nseg, srec, table, gsum, tile_start, overflow, out_gidx);
