@@ -670,7 +670,7 @@ struct ExpandArgs {
 };
 
 template <int SHMODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 sh_grad_expand_kernel(const __grid_constant__ ExpandArgs a, const float *__restrict__ means3D, const float *__restrict__ shs,
                       const float *__restrict__ records, float *__restrict__ dL_dshs, float *__restrict__ dL_dmeans3D)
 {
