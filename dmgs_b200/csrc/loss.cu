@@ -76,7 +76,7 @@ __device__ __forceinline__ void load16(float *v, const float *row)
 // kernels sit at the FP32-issue / shared-memory balance point instead of being LDS bound.
 
 // sums[(plane * tiles + tile) * 2 + {0,1}] = sum |x-y|, sum ssim_map over the tile
-__global__ void __launch_bounds__(LTHREADS)
+__global__ void __launch_bounds__(LTHREADS, 4)
 l1_ssim_fwd_kernel(int H, int W, int tiles_x, const __grid_constant__ Window11 win, const float *__restrict__ img,
                    const float *__restrict__ gt, float *__restrict__ deriv, float *__restrict__ sums)
 {
@@ -221,7 +221,7 @@ l1_ssim_finish_kernel(int tiles, double inv_n, const float *__restrict__ sums, f
 
 // grad[p] = up_l1[plane] * sign(x - y) + up_ssim[plane] * (G*Da + 2 x G*Db + y G*Dc); up_* are device
 // arrays (the upstream gradient times the loss weights, already divided by the pixel count)
-__global__ void __launch_bounds__(LTHREADS)
+__global__ void __launch_bounds__(LTHREADS, 4)
 l1_ssim_bwd_kernel(int H, int W, int tiles_x, const __grid_constant__ Window11 win, const float *__restrict__ img,
                    const float *__restrict__ gt, const float *__restrict__ deriv, const float *__restrict__ up,
                    float *__restrict__ grad)
