@@ -141,7 +141,6 @@ def oracle_frame(O, pr, cl_np, dL):
 
 def cpu_baseline(workload, frames, warm=1):
     """Times the CPU oracle (port of the same splat math) on `frames` frames of the workload."""
-    import numpy as np
     import torch
     from dmgs_b200 import synthetic as S
     from oracle import oracle as O
@@ -189,7 +188,6 @@ def run_reference(args):
 
 
 def run_ours(args):
-    import numpy as np
     import torch
     import torch.distributed as dist
 

@@ -2,7 +2,7 @@
 L2 or L2 flushed between iterations, against the HBM roofline and against the op-by-op PyTorch
 formulation the reference runs (same math written with torch ops in this file; the reference itself
 is not on the GPU box).  python scripts/bench_next_rows.py > gpurun_out/next_rows.jsonl"""
-import json, math, os, sys
+import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.nn.functional as F

@@ -4,7 +4,7 @@ import math, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import dmgs_b200
-from dmgs_b200 import GaussianRasterizationSettings, frustum as FR, loss_utils as LU, multiview as MV, synthetic as S
+from dmgs_b200 import frustum as FR, loss_utils as LU, multiview as MV, synthetic as S
 from dmgs_b200.binding import bind_faces, bind_frame, stage3_scales_rotations
 from dmgs_b200.optim import FusedAdam
 

@@ -9,7 +9,6 @@ size-independent properties -- the CPU oracle takes too long at these sizes:
     coefficients agrees with <grad, direction>."""
 import math
 
-import numpy as np
 import pytest
 import torch
 

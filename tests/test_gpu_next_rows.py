@@ -2,7 +2,6 @@
 fused L1+SSIM loss, frustum test + face compaction, fused Adam -- against the golden vectors produced
 by the reference's own Python, against the CPU oracle on seeded inputs, and at full size through
 size-independent properties."""
-import math
 import os
 
 import numpy as np
