@@ -171,6 +171,46 @@ def test_deferred_sh_gradient_equals_row_accumulation(layout):
         grad_close(out[1][name].reshape(P, -1), out[0][name].reshape(P, -1), rtol=2e-4, name=name)
 
 
+def test_view_batched_training_step_reduces_the_loss():
+    """The INTEGRATION.md section 5 sequence end to end: ViewStreams (deferred SH) -> accumulate_view with the fused
+    L1+SSIM loss -> finish -> FusedAdam on the flat buffer.  A few steps towards a target rendered from perturbed
+    parameters must reduce the loss."""
+    from dmgs_b200 import loss_utils as LU, multiview as MV
+    from dmgs_b200.optim import FusedAdam
+    from dmgs_b200.rasterizer import rasterize_forward
+    from gpu_util import settings_for
+    P, W, H, NV = 4000, 128, 96, 4
+    cl = S.random_cloud(P, seed=12, extent=1.0, log_scale_mean=math.log(0.06))
+    sets = [settings_for(S.nerf_synthetic_camera(v, W, H), (0, 0, 0)) for v in range(NV)]
+    target = {k: v.cuda() for k, v in cl.items()}
+    with torch.no_grad():
+        gts = [rasterize_forward(s_, target["means3D"], target["opacities"], target["shs"], None, target["scales"],
+                                 target["rotations"], None)[0].clone() for s_ in sets]
+    gen = torch.Generator().manual_seed(1)
+    params = {k: v.clone() for k, v in target.items()}
+    params["shs"] = (params["shs"] + 0.2 * torch.randn(P, 16, 3, generator=gen).cuda()).contiguous()
+    params["opacities"] = (params["opacities"] * 0.7).contiguous()
+    opt = FusedAdam([{"params": [params[k]], "lr": lr, "name": k} for k, lr in
+                     (("means3D", 0.0), ("opacities", 0.02), ("scales", 0.0), ("rotations", 0.0), ("shs", 0.02))],
+                    lr=0.0, eps=1e-15)
+    vs = MV.ViewStreams(P, MV.RASTER_WIDTHS_SH, torch.device("cuda"), n=2, deferred_sh_views=NV)
+    losses = []
+    for step in range(6):
+        vs.begin()
+        per_view = []
+        for j in range(NV):
+            rec = vs.sh_record(j, sets[j].campos)
+            per_view.append(vs.run(j, lambda acc, j=j, rec=rec: MV.accumulate_view(
+                sets[j], params, lambda img, j=j: LU.l1_ssim_loss_and_grad(img, gts[j], 0.2), acc, sh_record=rec)[0]))
+        vs.finish(params["means3D"], params["shs"], 3)
+        vs.all_reduce_(scale=1.0 / NV)
+        opt.step(grads=vs.buf.views)
+        params["opacities"].clamp_(1e-3, 0.999)
+        losses.append(float(torch.stack(per_view).mean()))
+    assert losses[-1] < 0.7 * losses[0], losses
+    assert all(torch.isfinite(v).all() for v in params.values())
+
+
 def test_async_binning_matches_sync_and_reports_overflow():
     """configure(async_binning=True): same image / gradients without the host read-back; a frame whose
     instance list outgrows the remembered capacity renders as background, check_async() reports it,
