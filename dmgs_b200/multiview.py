@@ -175,7 +175,7 @@ class ViewStreams:
                  deferred_sh_views: int = 0, sh_key: str = "shs"):
         """deferred_sh_views: > 0 enables the deferred SH gradient for up to that many local views per step:
         every view records only its 16-byte {dL/dcolour, seen} per Gaussian (`sh_record(i, campos)` hands the
-        view its record array) and `finish(means3D, sh_degree)` forms the [P,16,3] gradient rows once from all
+        view its record array) and `finish(means3D, shs, sh_degree)` forms the [P,16,3] gradient rows once from all
         records -- V*16 B + one row per Gaussian and step instead of V read-modify-writes of the 192-byte row.
         peer_group: a process group of ranks on ONE box -> the summed buffer lives in symmetric memory
         and `all_reduce_()` exchanges it over NVLink peer memory (falls back to NCCL if symmetric memory
