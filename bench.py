@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- fwd+bwd frames/s of the splatting hot path (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload h0|c1|c3]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload h0|c1|c3|c4]
 
 Workload (N=1 default) = H0, the shape the metric is quoted on: 1 M random Gaussians, SH degree 3,
 `shs`+`scales`+`rotations` mode, 800x800 NeRF-synthetic cameras.  A step renders
@@ -34,17 +34,38 @@ WORKLOADS = {
     "h0": (1_000_000, 800, 800, "nerf", 1.3, math.log(0.01)),
     "c1": (100_000, 800, 800, "nerf", 1.3, math.log(0.01)),
     "c3": (1_000_000, 1245, 825, "bicycle", 3.0, math.log(0.008)),
+    # BASELINE.json configs[3]: 3 M Gaussians garden-scale, a 64-view batch partitioned across the ranks
+    # (strong scaling: the batch is fixed, 64 / N views per rank), ring of bicycle-shaped cameras
+    "c4": (3_000_000, 1245, 825, "ring64", 5.0, math.log(0.008)),
 }
-# DRAM bytes per launch of the kernels that can dominate, from the committed ncu --set full capture of workload
-# H0 (profiles/r1_s6_ncu_full_h0_raw.csv); far below the algorithmic bytes for the blend kernels because
-# only ~8 % of every tile's list is consumed before its pixels saturate and the records are served from L2
-NCU_TRAFFIC = {("h0", "blend_bwd"): 38.9e6, ("h0", "blend_fwd"): 27.2e6, ("h0", "preprocess_bwd"): 208.0e6}
+C4_TOTAL_VIEWS = 64
+# Per-launch hardware counters of the kernels that can dominate (instructions executed, shared-memory wavefronts,
+# DRAM bytes, issue-active %), read from the committed table the ncu --set full capture of THIS build was reduced
+# to (scripts/ncu_counters.py -> profiles/r2_kernel_counters.json).  They are properties of the workload (same
+# seed, same view), so dividing them by the LIVE CUDA-event duration gives live rates.
+COUNTERS_FILE = os.path.join(ROOT, "profiles", "r2_kernel_counters.json")
 VIEWS_PER_RANK = int(os.environ.get("DMGS_BENCH_VIEWS", "8"))
 N_STREAMS = int(os.environ.get("DMGS_BENCH_STREAMS", "4"))
 
 
+def kernel_counters(workload):
+    try:
+        with open(COUNTERS_FILE) as fh:
+            tab = json.load(fh)
+        return tab.get("workloads", {}).get(workload, {}), tab.get("source")
+    except (OSError, ValueError):
+        return {}, None
+
+
+_RING = {}
+
+
 def make_camera(kind, idx, W, H):
     from dmgs_b200 import synthetic as S
+    if kind == "ring64":
+        if (W, H) not in _RING:
+            _RING[(W, H)] = S.ring_cameras(C4_TOTAL_VIEWS, W, H, radius=6.0, fovx=0.9, seed=0)
+        return _RING[(W, H)][idx % C4_TOTAL_VIEWS]
     return S.nerf_synthetic_camera(idx, W, H) if kind == "nerf" else S.bicycle_camera(idx, W, H)
 
 
@@ -145,6 +166,7 @@ def cpu_baseline(workload, frames, warm=1):
     from dmgs_b200 import synthetic as S
     from oracle import oracle as O
     P, W, H, kind, extent, lsm = WORKLOADS[workload]
+    flags = O.use_native()  # the same source rebuilt with -O3 -march=native for the cores it is timed on
     # every core this process may use, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1)
     try:
         O.set_threads(len(os.sched_getaffinity(0)))
@@ -165,7 +187,7 @@ def cpu_baseline(workload, frames, warm=1):
     t = sum(times[warm:])
     return {"value": frames / t, "unit": "frames/s", "cores": O.num_threads(), "kind": "port",
             "sample": f"{frames} full frames (fwd+bwd) of workload {workload} ({P} Gaussians, {W}x{H}), "
-                      f"OpenMP over Gaussians/tiles, {warm} warm-up frame"}, t / frames
+                      f"OpenMP over Gaussians/tiles, {warm} warm-up frame; gcc {flags}"}, t / frames
 
 
 def run_reference(args):
@@ -211,11 +233,13 @@ def run_ours(args):
 
     P, W, H, kind, extent, lsm = WORKLOADS[args.workload]
     K, Wm = args.steps, max(args.warmup, 3)
+    strong = args.workload == "c4"  # a fixed 64-view batch split over the ranks; everything else: 8 views per rank
+    views_per_rank = (C4_TOTAL_VIEWS // world) if strong else VIEWS_PER_RANK
     cl = S.random_cloud(P, seed=0, extent=extent, log_scale_mean=lsm)  # replicated on every rank
     names = ["means3D", "scales", "rotations", "opacities", "shs"]
     host = {k: cl[k].pin_memory() for k in names}
     d = {k: host[k].to(dev) for k in names}
-    n_views = VIEWS_PER_RANK * world
+    n_views = views_per_rank * world
     cams = [make_camera(kind, v, W, H).to(dev) for v in range(n_views)]
     my_views = MV.partition_views(n_views, world, rank)
     bg = torch.zeros(3, device=dev)
@@ -231,8 +255,7 @@ def run_ours(args):
     use_peer = world > 1 and os.environ.get("DMGS_BENCH_ALLREDUCE", "peer") != "nccl"
     deferred = os.environ.get("DMGS_BENCH_DEFERRED_SH", "1") == "1"
     vs = MV.ViewStreams(P, MV.RASTER_WIDTHS_SH, dev, n=N_STREAMS, peer_group=dist.group.WORLD if use_peer else None,
-                        deferred_sh_views=VIEWS_PER_RANK if deferred else 0)
-    flat = vs.buf.flat
+                        deferred_sh_views=views_per_rank if deferred else 0)
     if world == 1:
         allreduce_kind = "none (single GPU)"
     elif vs.peer is not None:
@@ -263,16 +286,16 @@ def run_ours(args):
         color, radii, st = rasterize_forward(settings[v], d["means3D"], d["opacities"], d["shs"], None,
                                              d["scales"], d["rotations"], None, stage_hook=hook)
         rasterize_backward(st, dLs[j % len(dLs)], d["means3D"], d["shs"], d["scales"], d["rotations"], None, False,
-                           stage_hook=hook, accumulate_into=acc, sh_record=rec)
-        if st._count_dev is not None:
-            r_dev[j % N_STREAMS].add_(st._count_dev)
+                           stage_hook=hook, accumulate_into=acc, sh_record=rec, verify=False)
+        if st._count is None:  # sync-free frame: the count is still on the device (same stream: ordered)
+            r_dev[j % N_STREAMS].add_(st.ws.meta[0:1])
         else:
             stats["R"] += st.num_rendered
         stats["frames"] += 1
         if record:
             ev_log.append(events)
 
-    def step(record, single=False):
+    def step(record, single=False, exchange=True):
         # single=True: every view on the current stream into the first accumulator (the stage-timing steps
         # after the timed region; record=True puts CUDA events between the stages)
         if single:
@@ -286,14 +309,14 @@ def run_ours(args):
             for j, v in enumerate(my_views):
                 vs.run(j, lambda acc, j=j, v=v: one_view(j, v, False, acc))
             vs.finish(d["means3D"], d["shs"], 3)
-        if world > 1:
+        if world > 1 and exchange:
             vs.all_reduce_()
         if not dmgs_b200.check_async():  # a frame overflowed its binning buffer: the step does not count
             stats["redone"] += 1
             if record:
                 del ev_log[-len(my_views):]
             stats["frames"] -= len(my_views)
-            step(record, single)
+            step(record, single, exchange)
 
     for _ in range(Wm):
         step(False)
@@ -327,6 +350,13 @@ def run_ours(args):
         dist.all_reduce(lt)
         launches = int(lt.item())
     frames_timed, redone_timed = stats["frames"], stats["redone"]
+
+    # ---- multi-GPU correctness, outside the timed region (driver-visible: keys of the JSON line)
+    mgpu = None
+    if world > 1:
+        mgpu = multi_gpu_checks(torch, dist, MV, vs, dev, world, rank, P, n_views, settings, d, dLs, step,
+                                rasterize_forward, rasterize_backward)
+
     # per-stage kernel durations: two more steps on ONE stream with CUDA events between the stages (with
     # several views in flight the stages of different views overlap and cannot be timed individually)
     step(False, single=True)  # the caching allocator's per-stream pools: first single-stream step allocates
@@ -341,15 +371,49 @@ def run_ours(args):
         stage_ms[k] /= max(len(ev_log), 1)
     Ravg = (stats["R"] + sum(int(t.item()) for t in r_dev)) / max(stats["frames"] + len(my_views) * stats["redone"], 1)
     stats["redone"] = redone_timed
-    value = (VIEWS_PER_RANK * world * K) / (ms / 1e3)
+    value = (views_per_rank * world * K) / (ms / 1e3)
+
+    # ---- the DROP-IN path, device resident: what the reference's trainers would see (one view per iteration
+    # through the GaussianRasterizer nn.Module, autograd backward, zero_grad(set_to_none=True);
+    # train_geo_stage2.py:91-132 / gaussian_renderer/__init__.py:18-101).  Timed with CUDA events over >= 2 s.
+    def dropin_loop(n_frames):
+        t = {k: d[k].detach().requires_grad_() for k in names}
+        for i in range(n_frames):
+            v = my_views[i % len(my_views)]
+            ras = GaussianRasterizer(settings[v])
+            m2d = torch.zeros_like(t["means3D"], requires_grad=True)  # screenspace_points of render()
+            img, radii = ras(means3D=t["means3D"], means2D=m2d, shs=t["shs"], colors_precomp=None,
+                             opacities=t["opacities"], scales=t["scales"], rotations=t["rotations"], cov3D_precomp=None)
+            img.backward(dLs[i % len(dLs)])
+            for x in t.values():
+                x.grad = None
+
+    def time_dropin(sync_free):
+        dmgs_b200.configure(async_binning=sync_free)
+        try:
+            dropin_loop(2 * len(my_views))
+            torch.cuda.synchronize()
+            n = max(views_per_rank * K, 64)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            dropin_loop(n)
+            b.record()
+            torch.cuda.synchronize()
+            dmgs_b200.check_async()
+            return n / (a.elapsed_time(b) / 1e3)
+        finally:
+            dmgs_b200.configure(async_binning=not args.sync_binning)
+
+    value_dropin = time_dropin(False) if world == 1 else None          # default settings: upstream's host read-back
+    value_dropin_syncfree = time_dropin(True) if world == 1 else None  # configure(async_binning=True)
 
     # ---- end-to-end with HOST inputs (rank-local; max over ranks).  Every step copies all inputs from
     # pinned host memory (double-buffered on a copy stream, so the copy of step i+1 overlaps the kernels
     # of step i) and reads the step's loss back to the host.  Two public entry points are measured:
+    #   "autograd_module" (= e2e.value): the drop-in GaussianRasterizer nn.Module, one view after the other,
+    #                    autograd accumulating .grad over the views of the step
     #   "training_step": dmgs_b200.multiview (ViewStreams + accumulate_view over the C ABI) -- the same call
-    #                    sequence as the `value` region, plus the copies and the loss;  this is `e2e`
-    #   "autograd_module": the drop-in GaussianRasterizer nn.Module, one view after the other, autograd
-    #                    accumulating .grad (reported next to it as e2e.autograd_module)
+    #                    sequence as the `value` region, plus the copies and the loss
     staged = MV.StagedInputs(host, dev)
 
     def e2e_step_module(i, last):
@@ -359,23 +423,25 @@ def run_ours(args):
             staged.prefetch(slot ^ 1)
         t = {k: bufs[k].detach().requires_grad_() for k in names}
         loss = torch.zeros((), device=dev)
-        for j, v in enumerate(my_views):
-            ras = GaussianRasterizer(settings[v])
-            m2d = torch.zeros_like(t["means3D"], requires_grad=True)
-            img, radii = ras(means3D=t["means3D"], means2D=m2d, shs=t["shs"], colors_precomp=None,
-                             opacities=t["opacities"], scales=t["scales"], rotations=t["rotations"],
-                             cov3D_precomp=None)
-            l = (img * dLs[j % len(dLs)]).sum()
-            l.backward()
-            loss = loss + l.detach()
+        try:
+            for j, v in enumerate(my_views):
+                ras = GaussianRasterizer(settings[v])
+                m2d = torch.zeros_like(t["means3D"], requires_grad=True)
+                img, radii = ras(means3D=t["means3D"], means2D=m2d, shs=t["shs"], colors_precomp=None,
+                                 opacities=t["opacities"], scales=t["scales"], rotations=t["rotations"],
+                                 cov3D_precomp=None)
+                l = (img * dLs[j % len(dLs)]).sum()
+                l.backward()
+                loss = loss + l.detach()
+        except dmgs_b200.rasterizer.BinningOverflowError:  # capacity raised: repeat the step on the same inputs
+            staged.ready[slot] = torch.cuda.Event()
+            staged.ready[slot].record()
+            return e2e_step_module(i, last)
         if world > 1:
             g = torch.cat([t[k].grad.reshape(-1) for k in names])
             dist.all_reduce(g)
         host_loss = float(loss.cpu())  # device -> host read of the step's result
-        if not dmgs_b200.check_async():  # overflowed binning buffer: repeat the step on the same inputs
-            staged.ready[slot] = torch.cuda.Event()
-            staged.ready[slot].record()
-            return e2e_step_module(i, last)
+        dmgs_b200.check_async()
         staged.release(slot)
         return host_loss
 
@@ -420,10 +486,10 @@ def run_ours(args):
             tm = torch.tensor([dt], device=dev)
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
             dt = float(tm.item())
-        return (VIEWS_PER_RANK * world * Ke) / dt
+        return (views_per_rank * world * Ke) / dt
 
     e2e_module = time_e2e(e2e_step_module)
-    e2e_value = time_e2e(e2e_step_training)
+    e2e_training = time_e2e(e2e_step_training)
     h2d = staged.bytes_per_step
 
     if rank != 0:
@@ -431,7 +497,9 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (single-kernel stages are timed exactly by the hooks)
+    # ---- rooflines.  Single-kernel stages are timed exactly by the hooks.  The blend kernels are bound by the
+    # SMs' instruction issue rate (DRAM 1-2 %), so their roof is warp-instructions/s; the per-Gaussian kernels
+    # are HBM bound.  `roofline` describes the dominant kernel on ITS roof; `roofline_hbm` the dominant HBM kernel.
     peak, peak_src = peaks()
     T = ((W + 15) // 16) * ((H + 15) // 16)
     B_in, B_geo, B_gin = 236, 75, 232
@@ -446,18 +514,53 @@ def run_ours(args):
     }
     single = ["blend_fwd", "blend_bwd", "preprocess_bwd"]
     dom = max(single, key=lambda k: stage_ms.get(k, 0.0))
-    ach = alg[dom] / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms.get(dom) else 0.0
     stages = {k: {"ms": round(v, 4), "alg_GBps": round(alg[k] / (v * 1e-3) / 1e9, 1) if v > 0 else None}
               for k, v in stage_ms.items()}
+    counters, counters_src = kernel_counters(args.workload)
+
+    def hbm_roof(kname):
+        sec = stage_ms.get(kname, 0.0) * 1e-3
+        ach = alg[kname] / sec / 1e9 if sec > 0 else 0.0
+        c = counters.get(kname, {})
+        return {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": c.get("dram_bytes"), "peak_source": peak_src,
+                "traffic_source": f"dram__bytes_read.sum + dram__bytes_write.sum per launch, from capture {counters_src}"
+                if c.get("dram_bytes") is not None else None}
+
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    issue_peak = n_sms * 4 * sm_mhz * 1e6 / 1e9  # G warp-instructions/s: one per scheduler and clock
+    if dom in ("blend_fwd", "blend_bwd"):
+        c = counters.get(dom, {})
+        sec = stage_ms[dom] * 1e-3
+        inst = c.get("inst_executed")
+        ach = inst / sec / 1e9 if inst else None
+        roofline = {"kernel": dom, "bound": "fp32_issue", "achieved": ach, "peak": issue_peak, "unit": "Gwarp-inst/s",
+                    "frac": (ach / issue_peak) if ach else None,
+                    "peak_source": f"{n_sms} SMs x 4 schedulers x {sm_mhz:.0f} MHz (clock sampled during the run)",
+                    "inst_executed_per_launch": inst, "issue_active_pct_in_capture": c.get("issue_active_pct"),
+                    "smem_wavefronts_per_s": (c["smem_wavefronts"] / sec) if c.get("smem_wavefronts") else None,
+                    "warp_entry_pairs_per_s": (c["warp_entry_pairs"] / sec) if c.get("warp_entry_pairs") else None,
+                    "traffic": c.get("dram_bytes"),
+                    "counters_source": f"per-launch counters from capture {counters_src}; duration live (CUDA events)"
+                    if c else "no committed capture for this workload",
+                    "hbm": {k: v for k, v in hbm_roof(dom).items() if k in ("achieved", "peak", "frac", "unit")},
+                    "note": "blend kernels read ~10 % of their algorithmic bytes from DRAM (only the first part of every "
+                            "tile list is consumed, records hit L2): the HBM fraction is reported for the contract, the "
+                            "issue rate is the roof (DESIGN.md section 5)"}
+    else:
+        roofline = hbm_roof(dom)
+    hbm_dom = max(["preprocess_bwd"], key=lambda k: stage_ms.get(k, 0.0))
     cb = None
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_baseline(args.workload, 3)
+    wl = {"h0": "H0", "c1": "C1", "c3": "C3", "c4": "C4"}[args.workload]
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
-        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": f"{args.workload.upper()}: {P} random Gaussians SH-3, {W}x{H}, shs+scales+rotations, fwd+bwd",
-                   "views_per_rank_per_step": VIEWS_PER_RANK, "parallelism": f"views x{world} (replicated Gaussians, "
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{wl}: {P} random Gaussians SH-3, {W}x{H}, shs+scales+rotations, fwd+bwd",
+                   "views_per_rank_per_step": views_per_rank, "parallelism": f"views x{world} (replicated Gaussians, "
                    "one all-reduce of the flat gradient buffer per step)" if world > 1 else "single GPU",
                    "all_reduce": allreduce_kind,
                    "avg_instances_R": Ravg, "view_streams": N_STREAMS,
@@ -466,25 +569,86 @@ def run_ours(args):
                    "stage_timing": "2 single-stream steps right after the timed region, CUDA events between stages",
                    "binning": "host read-back of the instance count every frame" if args.sync_binning else
                    "sync-free (capacity from earlier frames, overflow flags checked once per step)",
-                   "steps_repeated_after_overflow": stats["redone"], "l2": "inputs (236 MB) + state (>230 MB) exceed the 126 MB L2; no flush needed"},
+                   "steps_repeated_after_overflow": stats["redone"],
+                   "l2": f"inputs ({h2d / 1e6:.0f} MB) + state exceed the 126 MB L2; no flush needed"},
         "stages": stages,
-        "roofline": {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                     "frac": ach / peak, "traffic": NCU_TRAFFIC.get((args.workload, dom)), "peak_source": peak_src,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture "
-                                       "profiles/r1_s6_ncu_full_h0_raw.csv" if (args.workload, dom) in NCU_TRAFFIC else None,
-                     "note": "blend kernels are FP32-issue bound, not HBM bound (DESIGN.md section 5)"},
-        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "steps": Ke, "api": "dmgs_b200.multiview training step (ViewStreams + accumulate_view over the C ABI), "
-                "host inputs staged from pinned memory every step, loss read back every step",
-                "autograd_module": e2e_module,
-                "autograd_module_api": "drop-in GaussianRasterizer nn.Module, views one after the other, same copies"},
+        "roofline": roofline,
+        "roofline_hbm": hbm_roof(hbm_dom),
+        "value_dropin": value_dropin,
+        "value_dropin_syncfree": value_dropin_syncfree,
+        "value_dropin_api": "GaussianRasterizer nn.Module, ONE view per iteration, autograd backward, grads set to None "
+                            "(what train_geo_stage2.py:91-132 would see), inputs resident, CUDA events; value_dropin = "
+                            "default settings (host read-back of the instance count, as upstream), _syncfree = "
+                            "configure(async_binning=True)",
+        "e2e": {"value": e2e_module, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "steps": Ke, "api": "drop-in GaussianRasterizer nn.Module (the reference-facing call), the step's views one "
+                "after the other, autograd accumulating .grad; host inputs staged from pinned memory every step, loss "
+                "read back every step",
+                "training_step": e2e_training,
+                "training_step_api": "dmgs_b200.multiview training step (ViewStreams + accumulate_view over the C ABI), "
+                                     "same copies and read-back"},
         "gpu_launches": int(launches), "clocks": clocks,
     }
+    if mgpu is not None:
+        line.update(mgpu)
     if cb is not None:
         line["cpu_baseline"] = cb
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def multi_gpu_checks(torch, dist, MV, vs, dev, world, rank, P, n_views, settings, d, dLs, step, rasterize_forward,
+                     rasterize_backward):
+    """Outside the timed region: (i) the peer-memory all-reduce against NCCL on the same data; (ii) the N-rank
+    reduced gradient buffer against rank 0 rendering ALL views alone (row accumulation, no deferred SH, one
+    stream: an independent path).  Returns keys for the JSON line."""
+    out = {}
+    flat = vs.buf.flat
+    # (i) same random payload on both paths
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    payload = torch.randn(flat.numel(), generator=g, device=dev)
+    ref = payload.clone()
+    dist.all_reduce(ref)
+    flat.copy_(payload)
+    torch.cuda.synchronize()
+    dist.barrier()
+    vs.all_reduce_()
+    torch.cuda.synchronize()
+    err = float(((flat - ref).abs().max() / ref.abs().max()).item())
+    digest = flat.view(torch.int32).long().sum().reshape(1)  # order-independent checksum of the bit patterns
+    digests = [torch.zeros_like(digest) for _ in range(world)]
+    dist.all_gather(digests, digest)
+    out["allreduce_check"] = {"max_rel_err_vs_nccl": err, "same_bits_across_ranks": bool(all(int(x) == int(digests[0]) for x in digests)),
+                              "payload_floats": int(flat.numel()),
+                              "path": "dmgs_allreduce_peer" if vs.peer is not None else "nccl (peer memory unavailable)"}
+    # (ii) one normal N-rank step, then rank 0 alone over all views
+    step(False)
+    torch.cuda.synchronize()
+    reduced = {k: v.clone() for k, v in vs.buf.views.items()}
+    worst, per_field = 0.0, {}
+    if rank == 0:
+        solo = MV.FlatGradBuffer(P, MV.RASTER_WIDTHS_SH, dev)
+        for v in range(n_views):
+            j = v // world  # the local index this view has on its owning rank: the same dL/dimage
+            color, radii, st = rasterize_forward(settings[v], d["means3D"], d["opacities"], d["shs"], None, d["scales"],
+                                                 d["rotations"], None)
+            rasterize_backward(st, dLs[j % len(dLs)], d["means3D"], d["shs"], d["scales"], d["rotations"], None, False,
+                               accumulate_into=solo.views)
+        torch.cuda.synchronize()
+        for k, v in solo.views.items():
+            den = float(torch.linalg.norm(v.double()))
+            e = float(torch.linalg.norm((reduced[k] - v).double())) / max(den, 1e-30)
+            per_field[k] = e
+            worst = max(worst, e)
+        del solo
+    w = torch.tensor([worst], device=dev)
+    dist.all_reduce(w, op=dist.ReduceOp.MAX)
+    out["nrank_vs_1rank_rel_err"] = float(w.item())
+    if rank == 0:
+        out["nrank_vs_1rank_per_field"] = per_field
+    dist.barrier()
+    return out
 
 
 def main():
@@ -493,7 +657,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="h0", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=os.environ.get("DMGS_BENCH_WORKLOAD", "h0"), choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sync-binning", action="store_true",
                     help="read the instance count back every frame (upstream behaviour) instead of sync-free binning")

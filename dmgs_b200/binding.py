@@ -22,8 +22,8 @@ from . import _lib as L
 from .synthetic import barycentric_layout  # geo/mesh_utils.py:16-40 constants
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(dev=None):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
 class _BindFaces(torch.autograd.Function):
@@ -31,6 +31,16 @@ class _BindFaces(torch.autograd.Function):
     def forward(ctx, verts, faces, bc, g, rad_base, thin_z, adaptive, want_cov, want_rot):
         if verts.device.type != "cuda":
             raise RuntimeError("dmgs_b200 binding needs CUDA tensors; there is no CPU path")
+        if bc.dim() == 3 and bc.shape[0] == 1:  # the reference also uses bc_coords.view(1, -1, 3) (mlp_flex.py:281)
+            bc = bc[0]
+        if bc.dim() != 2 or bc.shape[1] != 3 or bc.shape[0] < 1:
+            raise ValueError(f"bc: expected the [k,3] barycentric table (geo/mesh_utils.py:16-40), got {tuple(bc.shape)}")
+        if faces.dim() != 2 or faces.shape[1] != 3:
+            raise ValueError(f"faces: expected [F,3], got {tuple(faces.shape)}")
+        if verts.dim() != 2 or verts.shape[1] != 3:
+            raise ValueError(f"verts: expected [V,3], got {tuple(verts.shape)}")
+        if faces.device != verts.device or bc.device != verts.device:
+            raise ValueError("verts, faces and bc must live on the same CUDA device")
         verts_c = verts.detach().float().contiguous()
         faces_c = faces.to(torch.int64).contiguous()
         bc_c = bc.detach().float().contiguous()
@@ -40,9 +50,10 @@ class _BindFaces(torch.autograd.Function):
         xyz = torch.empty(F * k, 3, dtype=torch.float32, device=dev)
         cov6 = torch.empty(F * k, 6, dtype=torch.float32, device=dev) if want_cov else None
         rot = torch.empty(F, 3, 3, dtype=torch.float32, device=dev) if want_rot else None
-        L.check(L.lib().dmgs_bind_forward(F, k, L.ptr(verts_c), L.ptr(faces_c), L.ptr(bc_c), float(rad_base),
-                                          float(thin_z), L.ptr(g_c), int(adaptive), L.ptr(xyz), L.ptr(cov6),
-                                          L.ptr(rot), _stream()), "dmgs_bind_forward")
+        with torch.cuda.device(dev):
+            L.check(L.lib().dmgs_bind_forward(F, k, L.ptr(verts_c), L.ptr(faces_c), L.ptr(bc_c), float(rad_base),
+                                              float(thin_z), L.ptr(g_c), int(adaptive), L.ptr(xyz), L.ptr(cov6),
+                                              L.ptr(rot), _stream(dev)), "dmgs_bind_forward")
         ctx.save_for_backward(verts_c, faces_c, bc_c, g_c if g_c is not None else torch.empty(0, device=dev))
         ctx.meta = (float(rad_base), float(thin_z), int(adaptive), g is not None, want_cov, want_rot)
         outs = [xyz]
@@ -64,9 +75,11 @@ class _BindFaces(torch.autograd.Function):
         F, k = int(faces_c.shape[0]), int(bc_c.shape[0])
         dverts = torch.zeros_like(verts_c)
         dg = torch.zeros(1, dtype=torch.float32, device=verts_c.device)
-        L.check(L.lib().dmgs_bind_backward(F, k, L.ptr(verts_c), L.ptr(faces_c), L.ptr(bc_c), rad_base, thin_z,
-                                           L.ptr(g_c if has_g else None), adaptive, L.ptr(g_xyz), L.ptr(g_cov),
-                                           L.ptr(g_rot), L.ptr(dverts), L.ptr(dg), _stream()), "dmgs_bind_backward")
+        with torch.cuda.device(verts_c.device):
+            L.check(L.lib().dmgs_bind_backward(F, k, L.ptr(verts_c), L.ptr(faces_c), L.ptr(bc_c), rad_base, thin_z,
+                                               L.ptr(g_c if has_g else None), adaptive, L.ptr(g_xyz), L.ptr(g_cov),
+                                               L.ptr(g_rot), L.ptr(dverts), L.ptr(dg), _stream(verts_c.device)),
+                    "dmgs_bind_backward")
         return dverts, None, None, (dg if has_g else None), None, None, None, None, None
 
 
@@ -124,8 +137,9 @@ class _Stage3(torch.autograd.Function):
         scales = torch.empty(P, 3, dtype=torch.float32, device=dev) if "scales" in want else None
         quats = torch.empty(P, 4, dtype=torch.float32, device=dev) if "quats" in want else None
         cov6 = torch.empty(P, 6, dtype=torch.float32, device=dev) if "cov6" in want else None
-        L.check(L.lib().dmgs_stage3_forward(F, k, L.ptr(rot), L.ptr(r2), L.ptr(s2), float(thin_z), L.ptr(scales),
-                                            L.ptr(quats), L.ptr(cov6), _stream()), "dmgs_stage3_forward")
+        with torch.cuda.device(dev):
+            L.check(L.lib().dmgs_stage3_forward(F, k, L.ptr(rot), L.ptr(r2), L.ptr(s2), float(thin_z), L.ptr(scales),
+                                                L.ptr(quats), L.ptr(cov6), _stream(dev)), "dmgs_stage3_forward")
         ctx.save_for_backward(rot, s2, r2)
         ctx.meta = (F, k, float(thin_z), want)
         return tuple(t for t in (scales, quats, cov6) if t is not None)
@@ -140,9 +154,10 @@ class _Stage3(torch.autograd.Function):
         g_q = fix(next(it)) if "quats" in want else None
         g_c = fix(next(it)) if "cov6" in want else None
         d_rot, d_r2, d_s2 = torch.empty_like(rot), torch.empty_like(r2), torch.empty_like(s2)
-        L.check(L.lib().dmgs_stage3_backward(F, k, L.ptr(rot), L.ptr(r2), L.ptr(s2), thin_z, L.ptr(g_s), L.ptr(g_q),
-                                             L.ptr(g_c), L.ptr(d_rot), L.ptr(d_r2), L.ptr(d_s2), _stream()),
-                "dmgs_stage3_backward")
+        with torch.cuda.device(rot.device):
+            L.check(L.lib().dmgs_stage3_backward(F, k, L.ptr(rot), L.ptr(r2), L.ptr(s2), thin_z, L.ptr(g_s), L.ptr(g_q),
+                                                 L.ptr(g_c), L.ptr(d_rot), L.ptr(d_r2), L.ptr(d_s2), _stream(rot.device)),
+                    "dmgs_stage3_backward")
         return d_rot, d_s2, d_r2, None, None
 
 

@@ -121,7 +121,7 @@ int launch_adam(int nseg, const dmgs_adam_segment *segs, double beta1, double be
     a.eps = (float)eps; a.grad_scale = grad_scale; a.zero_grad = zero_grad;
     if (pos == 0) return 0;
     long long blocks = (nmax / 4 + 255) / 256;
-    const long long cap = (long long)DMGS_NUM_SMS * 8;
+    const long long cap = (long long)num_sms() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     adam_kernel<<<dim3((unsigned)blocks, (unsigned)nseg), 256, 0, s>>>(a);

@@ -12,6 +12,35 @@ static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add((uint64_t)n); }
 
+static int current_device()
+{
+    int d = -1;
+    if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return d;
+}
+int num_sms()
+{
+    static std::atomic<int> cache[64];
+    const int d = current_device();
+    if (d < 0 || d >= 64) return DMGS_DEFAULT_SMS;
+    int n = cache[d].load();
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            n = DMGS_DEFAULT_SMS;
+        }
+        cache[d].store(n);
+    }
+    return n;
+}
+bool once_per_device(int slot)
+{
+    static std::atomic<bool> seen[ONCE_SLOTS][64];
+    const int d = current_device();
+    if (d < 0 || d >= 64) return true;  // unknown device: set the attributes every time (cheap)
+    return !seen[slot][d].exchange(true);
+}
+
 void set_error(const char *fmt, ...)
 {
     va_list ap;
@@ -45,6 +74,16 @@ static int validate(const dmgs_params *p)
     if (p->P < 0 || p->image_width <= 0 || p->image_height <= 0) { set_error("bad sizes P=%d W=%d H=%d", p->P, p->image_width, p->image_height); return -2; }
     if (p->image_width > 65535 * DMGS_TILE || p->image_height > 65535 * DMGS_TILE) { set_error("image too large"); return -2; }
     if (p->sh_degree < 0 || p->sh_degree > 3) { set_error("sh_degree %d not in 0..3", p->sh_degree); return -3; }
+    return 0;
+}
+
+// the SH rows must hold at least the coefficients of the active degree
+static int validate_sh(const dmgs_params *p, const float *shs)
+{
+    if (shs && p->sh_coeffs < (p->sh_degree + 1) * (p->sh_degree + 1)) {
+        set_error("sh_coeffs %d < (sh_degree + 1)^2 = %d", p->sh_coeffs, (p->sh_degree + 1) * (p->sh_degree + 1));
+        return -3;
+    }
     return 0;
 }
 
@@ -97,6 +136,7 @@ int dmgs_preprocess_forward(const dmgs_params *prm, const float *means3D, const 
         return -5;
     }
     if (!num_rendered) { set_error("num_rendered is NULL"); return -6; }
+    if ((rc = validate_sh(prm, shs))) return rc;
     const int P = prm->P;
     if (P == 0) {
         DMGS_CUDA(cudaMemsetAsync(num_rendered, 0, sizeof(uint32_t), s));
@@ -255,6 +295,7 @@ int dmgs_preprocess_backward(const dmgs_params *prm, const float *means3D, const
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const int P = prm->P;
+    if ((rc = validate_sh(prm, shs))) return rc;
     if (P == 0) return 0;
     if (!means3D || !radii || !geom || !dL_dmeans3D || !dL_dmeans2D || !dL_dopacity || !scratch) {
         set_error("NULL required pointer");

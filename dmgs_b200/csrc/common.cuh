@@ -16,7 +16,7 @@
 
 #define DMGS_TILE 16
 #define DMGS_NEAR 0.2f
-#define DMGS_NUM_SMS 148        /* B200 */
+#define DMGS_DEFAULT_SMS 148    /* B200; used only when no device can be queried (host-only size calls) */
 #define PLACE_MAX_TILES 16384   /* direct tile placement (place.cu) up to this many tiles, radix partition above */
 
 namespace dmgs {
@@ -25,6 +25,11 @@ namespace dmgs {
 void set_error(const char *fmt, ...);
 int check_stage(const dmgs_params *prm, cudaStream_t s, const char *stage);
 void count_launches(int n);  // kernels launched by this library (bench.py reports it)
+// Per-DEVICE launch state (a process may drive several GPUs): multiprocessor count of the current device
+// (DMGS_DEFAULT_SMS when none can be queried) and a once-per-device latch for the cudaFuncSetAttribute opt-ins.
+int num_sms();
+enum { ONCE_PREPROCESS_FWD = 0, ONCE_PREPROCESS_BWD, ONCE_SH_EXPAND, ONCE_PLACE, ONCE_BIND_FUSED, ONCE_SLOTS };
+bool once_per_device(int slot);
 
 #define DMGS_CUDA(call)                                                              \
     do {                                                                             \

@@ -103,7 +103,7 @@ int launch_allreduce_peer(int64_t n, int world, int rank, const void *const *pee
     const long long begin4 = (long long)rank * per, end4 = begin4 + per < n4 ? begin4 + per : n4;
     if (end4 <= begin4) return 0;
     long long blocks = (end4 - begin4 + 255) / 256;
-    const long long cap = (long long)DMGS_NUM_SMS * 8;
+    const long long cap = (long long)num_sms() * 8;
     if (blocks > cap) blocks = cap;
     if (multicast_ptr) {
         allreduce_multimem_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<float *>(multicast_ptr), begin4, end4, scale);

@@ -43,7 +43,7 @@ PlacePlan place_plan(int32_t P, int T)
     if (wps > 32) wps = 32;
     if (wps < 2) return p;
     p.wpb = wps >= 4 ? 4 : wps >= 2 ? 2 : 1;
-    const int nseg_max = DMGS_NUM_SMS * (wps / p.wpb) * p.wpb;
+    const int nseg_max = num_sms() * (wps / p.wpb) * p.wpb;
     const int64_t n = P > 0 ? P : 1;
     int seg = (int)((n + nseg_max - 1) / nseg_max);
     if (seg < 64) seg = 64;
@@ -295,14 +295,12 @@ int launch_tile_placement(const PlacePlan &pl, int P, int T, int gx, const uint3
                           uint4 *srec, uint32_t *table, uint32_t *gsum, uint32_t *tile_start, uint2 *ranges,
                           uint32_t *out_gidx, int64_t capacity, uint32_t *overflow, cudaStream_t s)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (once_per_device(ONCE_PLACE)) {
         DMGS_CUDA(cudaFuncSetAttribute(tile_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         DMGS_CUDA(cudaFuncSetAttribute(tile_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         // the plan counts on ~200 KB of shared memory per SM: ask for the largest carve-out
         DMGS_CUDA(cudaFuncSetAttribute(tile_count_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         DMGS_CUDA(cudaFuncSetAttribute(tile_place_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        attr_set = true;
     }
     const int threads = pl.wpb * 32;
     const int blocks = pl.groups;

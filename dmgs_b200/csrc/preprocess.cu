@@ -314,11 +314,9 @@ int launch_preprocess_fwd(const dmgs_params *prm, const float *means3D, const fl
 {
     const int P = prm->P;
     if (P <= 0) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (once_per_device(ONCE_PREPROCESS_FWD)) {
         DMGS_CUDA(cudaFuncSetAttribute(preprocess_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_STAGE_SMEM));
         DMGS_CUDA(cudaFuncSetAttribute(preprocess_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_STAGE_SMEM));
-        attr_set = true;
     }
     const int mode = sh_mode(prm, shs);
     const DevParams dp = make_dev_params(prm);
@@ -630,11 +628,9 @@ int launch_preprocess_bwd(const dmgs_params *prm, const float *means3D, const fl
 {
     const int P = prm->P;
     if (P <= 0) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (once_per_device(ONCE_PREPROCESS_BWD)) {
         DMGS_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_STAGE_SMEM));
         DMGS_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_STAGE_SMEM));
-        attr_set = true;
     }
     int mode = (dL_dshs && !(reinterpret_cast<uintptr_t>(dL_dshs) & 15)) ? sh_mode(prm, shs) : 0;
     if (accumulate == 2) {
@@ -775,11 +771,9 @@ int launch_sh_grad_expand(int P, int sh_degree, int M, int layout, int V, const 
 {
     if (P <= 0) return 0;
     if (V < 0 || V > DMGS_MAX_STEP_VIEWS) { set_error("sh_grad_expand: 0..%d views per call, got %d", DMGS_MAX_STEP_VIEWS, V); return -14; }
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (once_per_device(ONCE_SH_EXPAND)) {
         DMGS_CUDA(cudaFuncSetAttribute(sh_grad_expand_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_STAGE_SMEM));
         DMGS_CUDA(cudaFuncSetAttribute(sh_grad_expand_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_STAGE_SMEM));
-        attr_set = true;
     }
     ExpandArgs a;
     memset(&a, 0, sizeof(a));

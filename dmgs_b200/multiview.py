@@ -305,7 +305,8 @@ def accumulate_view(settings, inputs: Dict[str, Optional[torch.Tensor]], image_g
                                             sh_layout, sh_activation)
     loss, dL = image_grad(color)
     rasterize_backward(state, dL.contiguous(), inputs["means3D"], g("shs"), g("scales"), g("rotations"),
-                       g("cov3D_precomp"), g("colors_precomp") is not None, accumulate_into=acc, sh_record=sh_record)
+                       g("cov3D_precomp"), g("colors_precomp") is not None, accumulate_into=acc, sh_record=sh_record,
+                       verify=False)  # sync-free binning: the step polls dmgs_b200.check_async() once, after its views
     return loss, color, radii
 
 

@@ -51,8 +51,17 @@ class FusedAdam:
         segs, keep = [], []
         betas, eps = None, None
         for g in self.param_groups:
+            if grads is not None:
+                # gradients are looked up by GROUP name: that is only unambiguous for one tensor per group (the
+                # reference's layout, finetune.py:526-537), and a name missing from `grads` is an error, not a skip
+                if len(g["params"]) != 1:
+                    raise RuntimeError(f"FusedAdam.step(grads=...): group {g.get('name')!r} holds {len(g['params'])} tensors; "
+                                       "name-keyed gradients need one tensor per group")
+                if g.get("name") not in grads:
+                    raise KeyError(f"FusedAdam.step(grads=...): no gradient for group {g.get('name')!r} "
+                                   f"(have {sorted(grads)})")
             for p in g["params"]:
-                grad = grads.get(g.get("name")) if grads is not None else p.grad
+                grad = grads[g.get("name")] if grads is not None else p.grad
                 if grad is None:
                     continue
                 if grad.dtype != torch.float32 or not grad.is_contiguous() or grad.numel() != p.numel():
@@ -77,6 +86,59 @@ class FusedAdam:
                 arr = (L.AdamSegment * len(chunk))(*chunk)
                 L.check(lib.dmgs_adam_step(len(chunk), arr, betas[0], betas[1], eps, t, float(grad_scale),
                                            int(zero_grad), stream), "dmgs_adam_step")
+
+    # ---- torch.optim.Optimizer's checkpoint surface (the reference's capture() calls optimizer.state_dict(),
+    # scene/gaussian_geo_model_mlp_flex.py:102, finetune.py:92-107; restore loads it back)
+    def state_dict(self) -> dict:
+        """Same layout as torch.optim.Optimizer.state_dict(): {'state': {index: {...}}, 'param_groups': [...]}
+        with parameters replaced by their running index."""
+        index, packed_groups = {}, []
+        for g in self.param_groups:
+            pg = {k: v for k, v in g.items() if k != "params"}
+            pg["params"] = []
+            for p in g["params"]:
+                index.setdefault(id(p), len(index))
+                pg["params"].append(index[id(p)])
+            packed_groups.append(pg)
+        state = {}
+        for p, st in self.state.items():
+            if id(p) in index:
+                state[index[id(p)]] = {"step": torch.tensor(float(st["step"])), "exp_avg": st["exp_avg"],
+                                       "exp_avg_sq": st["exp_avg_sq"]}
+        return {"state": state, "param_groups": packed_groups}
+
+    def load_state_dict(self, sd: dict):
+        groups = sd["param_groups"]
+        if len(groups) != len(self.param_groups) or any(len(a["params"]) != len(b["params"])
+                                                       for a, b in zip(groups, self.param_groups)):
+            raise ValueError("loaded state dict has different parameter groups")
+        by_index = {}
+        for saved, g in zip(groups, self.param_groups):
+            for i, p in zip(saved["params"], g["params"]):
+                by_index[i] = p
+            for k, v in saved.items():
+                if k != "params":
+                    g[k] = v
+        self.state = {}
+        for i, st in sd["state"].items():
+            p = by_index[int(i)]
+            step = st["step"]
+            self.state[p] = {"step": int(step.item() if isinstance(step, torch.Tensor) else step),
+                             "exp_avg": st["exp_avg"].to(p.device, torch.float32).contiguous().clone(),
+                             "exp_avg_sq": st["exp_avg_sq"].to(p.device, torch.float32).contiguous().clone()}
+
+    def add_param_group(self, group: dict):
+        g = dict(group)
+        ps = g["params"]
+        g["params"] = [ps] if isinstance(ps, torch.Tensor) else list(ps)
+        for k, v in self.defaults.items():
+            g.setdefault(k, v)
+        for p in g["params"]:
+            if p.device.type != "cuda" or p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError("FusedAdam needs contiguous fp32 CUDA parameters; there is no CPU path")
+            if any(p is q for og in self.param_groups for q in og["params"]):
+                raise ValueError("some parameters appear in more than one parameter group")
+        self.param_groups.append(g)
 
     def zero_grad(self, set_to_none: bool = True):
         for g in self.param_groups:

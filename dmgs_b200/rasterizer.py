@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import ctypes as C
 import weakref
+from collections import OrderedDict
 from typing import NamedTuple, Optional
 
 import torch
@@ -43,13 +44,28 @@ class GaussianRasterizationSettings(NamedTuple):
 
 _HOST_CACHE: dict = {}
 
+
+class BinningOverflowError(RuntimeError):
+    """A frame rendered with sync-free binning did not fit its binning buffer (it rendered as background with
+    zero gradients).  The capacity for its shape has been raised; repeat the step."""
+
+
 # ---- optional sync-free binning (see the module docstring) ------------------------------------------
-_ASYNC = {"on": False, "slack": 1.25, "capacity": {}, "pending": []}
+# capacity: instances the binning buffer is sized for, per (device, P, W, H); no_async: shapes that cannot use
+# the placement path (> 16384 tiles) and stay synchronous; pending: the probes (count + overflow flag on their
+# way to pinned memory) of the frames nobody has looked at yet, per device.
+_ASYNC = {"on": False, "slack": 1.25, "capacity": {}, "no_async": set(), "pending": {}}
+_MAX_PENDING = 256
 
 
 def configure(async_binning: Optional[bool] = None, capacity_slack: Optional[float] = None):
     """async_binning: size the binning buffer from earlier frames instead of reading the instance
-    count back (default False = upstream behaviour).  capacity_slack: head-room factor (default 1.25)."""
+    count back (default False = upstream behaviour).  capacity_slack: head-room factor (default 1.25).
+
+    Sync-free frames are verified, never trusted silently: every frame copies its instance count and
+    overflow flag to pinned host memory behind an event; `rasterize_backward` (and the autograd
+    backward) waits for that event -- long complete by then -- and raises `BinningOverflowError` if
+    the frame overflowed, `check_async()` polls all frames since the last call."""
     if async_binning is not None:
         _ASYNC["on"] = bool(async_binning)
     if capacity_slack is not None:
@@ -58,21 +74,112 @@ def configure(async_binning: Optional[bool] = None, capacity_slack: Optional[flo
         _ASYNC["pending"].clear()
 
 
-def check_async() -> bool:
-    """True if every async-binned frame since the last call fitted its buffer.  Synchronises (one
-    small device->host copy).  On overflow the capacity for that shape is raised and False is
-    returned: the caller repeats the step."""
-    pend, _ASYNC["pending"] = _ASYNC["pending"], []
-    if not pend:
-        return True
-    flags = torch.cat([f for _, f, _ in pend]).cpu().tolist()
-    counts = torch.cat([n for _, _, n in pend]).cpu().tolist()
+def _raise_capacity(key, need):
+    cap = _ASYNC["capacity"].get(key, 0)
+    _ASYNC["capacity"][key] = max(cap, int(need * _ASYNC["slack"]) + 4096)
+
+
+def check_async(device=None) -> bool:
+    """True if every sync-free frame since the last call fitted its buffer (all devices, or `device`).
+    Waits for those frames' events (one per frame, normally complete already).  On overflow the capacity
+    for that shape is raised and False is returned: the caller repeats the step."""
     ok = True
-    for (key, _, _), need, count in zip(pend, flags, counts):
-        cap = _ASYNC["capacity"].get(key, 0)
-        _ASYNC["capacity"][key] = max(cap, int(max(need, count) * _ASYNC["slack"]) + 4096)
-        ok = ok and need == 0
+    for dev_index in list(_ASYNC["pending"]):
+        if device is not None and torch.device(device).index not in (None, dev_index):
+            continue
+        pend, _ASYNC["pending"][dev_index] = _ASYNC["pending"][dev_index], []
+        for probe in pend:
+            if not probe.resolve():
+                ok = False
     return ok
+
+
+class _Probe:
+    """(instance count, overflow flag) of one sync-free frame on its way to pinned host memory."""
+
+    __slots__ = ("key", "capacity", "host", "event", "count", "need")
+
+    def __init__(self, key, capacity, meta, stream):
+        self.key, self.capacity, self.count, self.need = key, capacity, None, None
+        self.host = torch.empty(2, dtype=torch.int32, pin_memory=True)
+        self.host.copy_(meta, non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record(stream)
+
+    def resolve(self) -> bool:
+        """Waits for the copy (normally long complete); raises the shape's capacity; True if the frame fitted."""
+        if self.count is None:
+            self.event.synchronize()
+            self.count, self.need = int(self.host[0]), int(self.host[1])
+            self.host = self.event = None
+            _raise_capacity(self.key, max(self.count, self.need))
+        return self.need == 0
+
+
+# ---- per-(device, stream, P, W, H) workspaces -----------------------------------------------------------
+class _Workspace:
+    """The caller-owned byte buffers of ONE frame in flight (geom / binning / image / backward scratch),
+    recycled through a pool instead of four allocations per call.  A workspace belongs to one stream (work
+    on it is stream-ordered, so reuse needs no events) and goes back to the pool when the RasterState that
+    checked it out dies -- i.e. after the autograd graph of that frame has been released."""
+
+    __slots__ = ("key", "geom", "image", "binning", "scratch", "meta", "generation")
+
+    def __init__(self, key, dev, P, W, H):
+        lib = L.lib()
+        self.key = key
+        self.geom = torch.empty(lib.dmgs_geom_bytes(P), dtype=torch.uint8, device=dev)
+        self.image = torch.empty(lib.dmgs_image_bytes(W, H), dtype=torch.uint8, device=dev)
+        self.binning = None
+        self.scratch = None
+        self.meta = torch.zeros(2, dtype=torch.int32, device=dev)  # {instance count, overflow: count needed}
+        self.generation = 0
+
+    def ensure_binning(self, nbytes):
+        if self.binning is None or self.binning.numel() < nbytes:
+            self.binning = None  # free before growing
+            self.binning = torch.empty(int(nbytes), dtype=torch.uint8, device=self.geom.device)
+        return self.binning
+
+    def ensure_scratch(self, nbytes):
+        if self.scratch is None or self.scratch.numel() < nbytes:
+            self.scratch = torch.empty(int(nbytes), dtype=torch.uint8, device=self.geom.device)
+        return self.scratch
+
+
+_POOL: "OrderedDict" = OrderedDict()  # key -> free workspaces, least recently used key first
+_POOL_MAX_PER_KEY = 4
+_POOL_MAX_KEYS = 16
+
+
+def _acquire(dev, stream_id, P, W, H) -> _Workspace:
+    key = (dev.index, int(stream_id), P, W, H)
+    free = _POOL.get(key)
+    if free is not None:
+        _POOL.move_to_end(key)
+    ws = free.pop() if free else _Workspace(key, dev, P, W, H)
+    ws.generation += 1
+    return ws
+
+
+def _release(ws: _Workspace):
+    free = _POOL.setdefault(ws.key, [])
+    if len(free) < _POOL_MAX_PER_KEY:
+        free.append(ws)
+    while len(_POOL) > _POOL_MAX_KEYS:  # shapes that are no longer rendered give their memory back
+        _POOL.popitem(last=False)
+
+
+def release_workspaces():
+    """Drops every pooled workspace (frees the device memory once the allocator's cache is emptied)."""
+    _POOL.clear()
+
+
+def _version_of(t):
+    try:
+        return t._version
+    except Exception:  # inference tensors do not track versions
+        return None
 
 
 def _host_values(tensors):
@@ -84,7 +191,7 @@ def _host_values(tensors):
     out, miss = [None] * len(tensors), []
     for i, t in enumerate(tensors):
         hit = _HOST_CACHE.get(id(t))
-        if hit is not None and hit[0]() is t and hit[1] == t._version:
+        if hit is not None and hit[0]() is t and hit[1] == _version_of(t):
             out[i] = hit[2]
         else:
             miss.append(i)
@@ -98,8 +205,11 @@ def _host_values(tensors):
             o += n
             out[i] = vals
             key = id(t)
+            ver = _version_of(t)
+            if ver is None:
+                continue  # inference-mode tensors carry no version counter: never cached
             try:
-                _HOST_CACHE[key] = (weakref.ref(t, lambda _r, k=key: _HOST_CACHE.pop(k, None)), t._version, vals)
+                _HOST_CACHE[key] = (weakref.ref(t, lambda _r, k=key: _HOST_CACHE.pop(k, None)), ver, vals)
             except TypeError:
                 pass
     return out
@@ -129,24 +239,87 @@ def _f32c(t: Optional[torch.Tensor]):
     return t.contiguous()
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(dev=None):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _check(name, t, shape=None, dtype=torch.float32, device=None):
+    """The C ABI takes raw pointers: refuse anything that is not a contiguous CUDA tensor of the expected dtype /
+    shape on the expected device (None passes: optional inputs).  `shape` entries of None are free."""
+    if t is None:
+        return
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name}: dmgs_b200 needs CUDA tensors; there is no CPU path")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous (got strides {tuple(t.stride())})")
+    if device is not None and t.device != device:
+        raise ValueError(f"{name}: on {t.device}, expected {device}")
+    if shape is not None:
+        if t.dim() != len(shape) or any(e is not None and int(e) != int(g) for e, g in zip(shape, t.shape)):
+            raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+
+
+def _check_inputs(P, dev, means3D, opacities, shs, colors_precomp, scales, rotations, cov3D_precomp, sh_layout):
+    _check("means3D", means3D, (P, 3), device=dev)
+    if opacities is not None and opacities.numel() != P:
+        raise ValueError(f"opacities: expected {P} elements, got {tuple(opacities.shape)}")
+    _check("opacities", opacities, None, device=dev)
+    _check("colors_precomp", colors_precomp, (P, 3), device=dev)
+    _check("scales", scales, (P, 3), device=dev)
+    _check("rotations", rotations, (P, 4), device=dev)
+    _check("cov3D_precomp", cov3D_precomp, (P, 6), device=dev)
+    _check("shs", shs, (P, None, 3) if sh_layout == 0 else (P, 3, None), device=dev)
 
 
 class RasterState:
-    """Caller-owned state of one forward (the geom / binning / image byte buffers)."""
+    """Caller-owned state of one forward (the geom / binning / image byte buffers of a pooled workspace)."""
 
-    def __init__(self, prm, geom, binning, image, num_rendered, radii, count_dev=None):
-        self.prm, self.geom, self.binning, self.image = prm, geom, binning, image
+    def __init__(self, prm, ws, num_rendered, radii, capacity=None, probe=None):
+        self.prm, self.ws, self.radii, self._probe = prm, ws, radii, probe
+        self._gen = ws.generation
         # layout_R sizes the binning layout in every later C call: the instance count on the synchronous
-        # path, the buffer capacity on the async path (where the real count stays on the device)
-        self.layout_R, self.radii, self._count_dev = num_rendered, radii, count_dev
-        self._count = None if count_dev is not None else num_rendered
+        # path, the buffer capacity on the sync-free path (where the real count stays on the device)
+        self.layout_R = num_rendered if capacity is None else capacity
+        self._count = num_rendered if capacity is None else None
+        self._verified = capacity is None
+        self._overflow = 0
+
+    def __del__(self):
+        ws, self.ws = getattr(self, "ws", None), None
+        if ws is not None and ws.generation == self._gen:
+            try:
+                _release(ws)
+            except Exception:
+                pass
+
+    def _live(self):
+        if self.ws is None or self.ws.generation != self._gen:
+            raise RuntimeError("the state buffers of this frame have been recycled")
+        return self.ws
+
+    geom = property(lambda self: self._live().geom)
+    binning = property(lambda self: self._live().binning)
+    image = property(lambda self: self._live().image)
+
+    def verify(self, raise_on_overflow=True) -> bool:
+        """Sync-free frames: waits for the frame's (count, overflow) copy and checks it.  False / raises when the
+        frame overflowed its binning buffer (the capacity for its shape is raised either way)."""
+        if not self._verified:
+            self._probe.resolve()
+            self._count, self._overflow, self._verified = self._probe.count, self._probe.need, True
+        if self._overflow and raise_on_overflow:
+            raise BinningOverflowError(
+                f"sync-free binning: the frame needed {self._overflow} instances but its buffer held {self.layout_R}; "
+                "it rendered as background.  The capacity has been raised -- repeat the step "
+                "(dmgs_b200.check_async() reports this without raising).")
+        return not self._overflow
 
     @property
     def num_rendered(self) -> int:
         if self._count is None:
-            self._count = int(self._count_dev.item())
+            self.verify(raise_on_overflow=False)
         return self._count
 
     # typed views for the parity tests -------------------------------------------------
@@ -190,110 +363,150 @@ class RasterState:
         keys = torch.empty(max(R, 1), dtype=torch.int64, device=self.geom.device)
         if self.layout_R != R:
             raise RuntimeError("sorted_keys() is an inspection helper of the synchronous path")
-        L.check(L.lib().dmgs_sorted_keys(L.ptr(self.geom), L.ptr(self.binning), self.prm.P, R, self.prm.image_width,
-                                         self.prm.image_height, L.ptr(keys), _stream()), "dmgs_sorted_keys")
+        with torch.cuda.device(self.geom.device):
+            L.check(L.lib().dmgs_sorted_keys(L.ptr(self.geom), L.ptr(self.binning), self.prm.P, R, self.prm.image_width,
+                                             self.prm.image_height, L.ptr(keys), _stream(self.geom.device)), "dmgs_sorted_keys")
         return keys[:R]
 
 
 def rasterize_forward(settings, means3D, opacities, shs, colors_precomp, scales, rotations, cov3D_precomp,
                       sh_layout=0, sh_activation=0, stage_hook=None):
-    """Runs the three forward stages; returns (color [3,H,W], radii [P] int32, RasterState)."""
+    """Runs the three forward stages; returns (color [3,H,W], radii [P] int32, RasterState).
+    Inputs: contiguous float32 CUDA tensors on one device (checked); work is enqueued on that device's current
+    stream."""
     dev = means3D.device
     if dev.type != "cuda":
         raise RuntimeError("dmgs_b200 rasteriser needs CUDA tensors; there is no CPU path")
     lib = L.lib()
     P = int(means3D.shape[0])
     H, W = int(settings.image_height), int(settings.image_width)
+    _check_inputs(P, dev, means3D, opacities, shs, colors_precomp, scales, rotations, cov3D_precomp, sh_layout)
     M = 0
     if shs is not None:
         M = int(shs.shape[1] if sh_layout == 0 else shs.shape[2])
+        if M < (int(settings.sh_degree) + 1) ** 2:
+            raise ValueError(f"shs holds {M} coefficients per channel, sh_degree {settings.sh_degree} needs "
+                             f"{(int(settings.sh_degree) + 1) ** 2}")
     prm = make_params(settings, P, M, sh_layout, sh_activation)
-    stream = _stream()
-    radii = torch.zeros(P, dtype=torch.int32, device=dev)
-    color = torch.empty(3, H, W, dtype=torch.float32, device=dev)
-    geom = torch.empty(lib.dmgs_geom_bytes(P), dtype=torch.uint8, device=dev)
-    image = torch.empty(lib.dmgs_image_bytes(W, H), dtype=torch.uint8, device=dev)
-    nr = torch.zeros(1, dtype=torch.int32, device=dev)
-    L.check(lib.dmgs_preprocess_forward(C.byref(prm), L.ptr(means3D), L.ptr(scales), L.ptr(rotations),
-                                        L.ptr(cov3D_precomp), L.ptr(opacities), L.ptr(shs), L.ptr(colors_precomp),
-                                        L.ptr(radii), L.ptr(geom), L.ptr(nr), stream), "dmgs_preprocess_forward")
-    if stage_hook is not None:
-        stage_hook("preprocess_sort_scan")
-    key = (dev.index, P, W, H)
-    cap = _ASYNC["capacity"].get(key) if _ASYNC["on"] else None
-    count_dev = None
-    if cap is not None:
-        # sync-free: buffer sized from earlier frames of this shape; the count stays on the device
-        R = int(cap)
-        binning = torch.empty(lib.dmgs_binning_bytes(P, R, W, H), dtype=torch.uint8, device=dev)
-        flag = torch.empty(1, dtype=torch.int32, device=dev)
-        rc = lib.dmgs_bin_forward_async(C.byref(prm), L.ptr(geom), R, L.ptr(binning), L.ptr(flag), stream)
-        if rc == -9:  # image too large for the placement path: synchronous from now on
-            _ASYNC["capacity"].pop(key, None)
-            cap = None
-        else:
-            L.check(rc, "dmgs_bin_forward_async")
-            _ASYNC["pending"].append((key, flag, nr))
-            count_dev = nr
-    if cap is None:
-        R = int(nr.item())  # the one host read-back of the forward (upstream does the same after its scan)
-        if _ASYNC["on"]:
-            _ASYNC["capacity"][key] = max(_ASYNC["capacity"].get(key, 0), int(R * _ASYNC["slack"]) + 4096)
-        binning = torch.empty(lib.dmgs_binning_bytes(P, R, W, H), dtype=torch.uint8, device=dev)
-        L.check(lib.dmgs_bin_forward(C.byref(prm), L.ptr(geom), R, L.ptr(binning), stream), "dmgs_bin_forward")
-    if stage_hook is not None:
-        stage_hook("binning")
-    L.check(lib.dmgs_blend_forward(C.byref(prm), L.ptr(geom), L.ptr(binning), R, L.ptr(color), L.ptr(image), stream),
-            "dmgs_blend_forward")
-    if stage_hook is not None:
-        stage_hook("blend_fwd")
-    return color, radii, RasterState(prm, geom, binning, image, R, radii, count_dev)
+    with torch.cuda.device(dev):
+        cur = torch.cuda.current_stream(dev)
+        stream = C.c_void_p(cur.cuda_stream)
+        radii = torch.zeros(P, dtype=torch.int32, device=dev)
+        color = torch.empty(3, H, W, dtype=torch.float32, device=dev)
+        ws = _acquire(dev, cur.cuda_stream, P, W, H)
+        nr, flag = ws.meta[0:1], ws.meta[1:2]
+        L.check(lib.dmgs_preprocess_forward(C.byref(prm), L.ptr(means3D), L.ptr(scales), L.ptr(rotations),
+                                            L.ptr(cov3D_precomp), L.ptr(opacities), L.ptr(shs), L.ptr(colors_precomp),
+                                            L.ptr(radii), L.ptr(ws.geom), L.ptr(nr), stream), "dmgs_preprocess_forward")
+        if stage_hook is not None:
+            stage_hook("preprocess_sort_scan")
+        key = (dev.index, P, W, H)
+        cap = None
+        if _ASYNC["on"] and key not in _ASYNC["no_async"]:
+            cap = _ASYNC["capacity"].get(key)
+        state = None
+        if cap is not None:
+            # sync-free: buffer sized from earlier frames of this shape; the count stays on the device and is
+            # copied, with the overflow flag, to pinned memory behind an event (RasterState.verify)
+            R = int(cap)
+            binning = ws.ensure_binning(lib.dmgs_binning_bytes(P, R, W, H))
+            rc = lib.dmgs_bin_forward_async(C.byref(prm), L.ptr(ws.geom), R, L.ptr(binning), L.ptr(flag), stream)
+            if rc == -9:  # image too large for the placement path: this shape stays synchronous
+                _ASYNC["no_async"].add(key)
+                _ASYNC["capacity"].pop(key, None)
+                cap = None
+            else:
+                L.check(rc, "dmgs_bin_forward_async")
+                probe = _Probe(key, R, ws.meta, cur)
+                state = RasterState(prm, ws, None, radii, capacity=R, probe=probe)
+                pend = _ASYNC["pending"].setdefault(dev.index, [])
+                if len(pend) >= _MAX_PENDING:  # nobody polls check_async(): resolve the oldest frames ourselves
+                    old, pend[:] = pend[:_MAX_PENDING // 2], pend[_MAX_PENDING // 2:]
+                    if not all([pr_.resolve() for pr_ in old]):
+                        raise BinningOverflowError("sync-free binning: earlier frames overflowed their binning buffer and "
+                                                   "nobody called dmgs_b200.check_async(); capacities have been raised")
+                pend.append(probe)
+        if cap is None:
+            R = int(nr.item())  # the one host read-back of the forward (upstream does the same after its scan)
+            if _ASYNC["on"] and key not in _ASYNC["no_async"]:
+                _raise_capacity(key, R)
+            binning = ws.ensure_binning(lib.dmgs_binning_bytes(P, R, W, H))
+            L.check(lib.dmgs_bin_forward(C.byref(prm), L.ptr(ws.geom), R, L.ptr(binning), stream), "dmgs_bin_forward")
+            state = RasterState(prm, ws, R, radii)
+        if stage_hook is not None:
+            stage_hook("binning")
+        L.check(lib.dmgs_blend_forward(C.byref(prm), L.ptr(ws.geom), L.ptr(binning), R, L.ptr(color), L.ptr(ws.image),
+                                       stream), "dmgs_blend_forward")
+        if stage_hook is not None:
+            stage_hook("blend_fwd")
+    return color, radii, state
 
 
 def rasterize_backward(state: RasterState, grad_color, means3D, shs, scales, rotations, cov3D_precomp,
-                       want_colors_precomp, stage_hook=None, accumulate_into=None, sh_record=None):
+                       want_colors_precomp, stage_hook=None, accumulate_into=None, sh_record=None, verify=True):
     """accumulate_into: optional dict of preallocated gradient tensors (keys means3D, means2D, opacities,
     colors_precomp, shs, scales, rotations, cov3D_precomp) that the gradients are ADDED to.
     sh_record: with accumulate_into, a float32 [P,4] tensor that receives this view's deferred SH gradient
     record {g.r, g.g, g.b, seen} instead of the [P,16,3] rows being read-modify-written
-    (dmgs_preprocess_backward accumulate = 2; `sh_grad_expand` forms the rows once per step)."""
+    (dmgs_preprocess_backward accumulate = 2; `sh_grad_expand` forms the rows once per step).
+    verify: sync-free frames are checked for a binning overflow first (BinningOverflowError); a training step that
+    polls `check_async()` itself once per step passes verify=False to keep the host running ahead."""
     lib = L.lib()
     prm, P, dev = state.prm, state.prm.P, means3D.device
+    H, W = prm.image_height, prm.image_width
+    sh_layout = prm.sh_layout
+    _check("grad_color", grad_color, (3, H, W), device=dev)
+    _check_inputs(P, dev, means3D, None, shs, None, scales, rotations, cov3D_precomp, sh_layout)
+    if verify:
+        state.verify()
+    ws = state._live()
     z = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
-    g_means3D, g_means2D, g_op = z(P, 3), z(P, 3), z(P, 1)
-    g_col = z(P, 3) if want_colors_precomp else None
-    g_shs = torch.empty_like(shs) if shs is not None else None
-    g_scales = z(P, 3) if scales is not None else None
-    g_rots = z(P, 4) if rotations is not None else None
-    g_cov = z(P, 6) if cov3D_precomp is not None else None
-    if accumulate_into is not None:
+    if accumulate_into is None:
+        g_means3D, g_means2D, g_op = z(P, 3), z(P, 3), z(P, 1)
+        g_col = z(P, 3) if want_colors_precomp else None
+        g_shs = torch.empty_like(shs) if shs is not None else None
+        g_scales = z(P, 3) if scales is not None else None
+        g_rots = z(P, 4) if rotations is not None else None
+        g_cov = z(P, 6) if cov3D_precomp is not None else None
+    else:
         a = accumulate_into
         g_means3D, g_means2D, g_op = a["means3D"], a["means2D"], a["opacities"]
         g_col = a.get("colors_precomp") if want_colors_precomp else None
         g_shs = a.get("shs") if shs is not None else None
-        if sh_record is not None and shs is not None:
-            if sh_record.shape != (P, 4) or sh_record.dtype != torch.float32 or not sh_record.is_contiguous():
-                raise ValueError("sh_record must be a contiguous float32 [P,4] tensor")
-            g_shs = sh_record
         g_scales = a.get("scales") if scales is not None else None
         g_rots = a.get("rotations") if rotations is not None else None
         g_cov = a.get("cov3D_precomp") if cov3D_precomp is not None else None
-    scratch = torch.empty(lib.dmgs_backward_scratch_bytes(P), dtype=torch.uint8, device=dev)
-    stream = _stream()
-    L.check(lib.dmgs_blend_backward(C.byref(prm), L.ptr(state.geom), L.ptr(state.binning), L.ptr(state.image),
-                                    state.layout_R, L.ptr(grad_color), L.ptr(scratch), stream),
-            "dmgs_blend_backward")
-    if stage_hook is not None:
-        stage_hook("blend_bwd")
-    L.check(lib.dmgs_preprocess_backward(C.byref(prm), L.ptr(means3D), L.ptr(scales), L.ptr(rotations),
-                                         L.ptr(cov3D_precomp), L.ptr(shs), L.ptr(state.radii), L.ptr(state.geom),
-                                         L.ptr(scratch), L.ptr(g_means3D), L.ptr(g_means2D), L.ptr(g_op), L.ptr(g_col),
-                                         L.ptr(g_shs), L.ptr(g_scales), L.ptr(g_rots), L.ptr(g_cov),
-                                         (2 if (sh_record is not None and shs is not None) else 1)
-                                         if accumulate_into is not None else 0, stream),
-            "dmgs_preprocess_backward")
-    if stage_hook is not None:
-        stage_hook("preprocess_bwd")
+        _check("accumulate_into[means3D]", g_means3D, (P, 3), device=dev)
+        _check("accumulate_into[means2D]", g_means2D, (P, 3), device=dev)
+        _check("accumulate_into[opacities]", g_op, None, device=dev)
+        if g_op.numel() != P:
+            raise ValueError("accumulate_into[opacities] must hold P elements")
+        _check("accumulate_into[colors_precomp]", g_col, (P, 3), device=dev)
+        _check("accumulate_into[scales]", g_scales, (P, 3), device=dev)
+        _check("accumulate_into[rotations]", g_rots, (P, 4), device=dev)
+        _check("accumulate_into[cov3D_precomp]", g_cov, (P, 6), device=dev)
+        if shs is not None and g_shs is not None:
+            _check("accumulate_into[shs]", g_shs, tuple(shs.shape), device=dev)
+        if sh_record is not None and shs is not None:
+            _check("sh_record", sh_record, (P, 4), device=dev)
+            g_shs = sh_record
+    with torch.cuda.device(dev):
+        stream = _stream(dev)
+        scratch = ws.ensure_scratch(lib.dmgs_backward_scratch_bytes(P))
+        L.check(lib.dmgs_blend_backward(C.byref(prm), L.ptr(ws.geom), L.ptr(ws.binning), L.ptr(ws.image),
+                                        state.layout_R, L.ptr(grad_color), L.ptr(scratch), stream),
+                "dmgs_blend_backward")
+        if stage_hook is not None:
+            stage_hook("blend_bwd")
+        L.check(lib.dmgs_preprocess_backward(C.byref(prm), L.ptr(means3D), L.ptr(scales), L.ptr(rotations),
+                                             L.ptr(cov3D_precomp), L.ptr(shs), L.ptr(state.radii), L.ptr(ws.geom),
+                                             L.ptr(scratch), L.ptr(g_means3D), L.ptr(g_means2D), L.ptr(g_op), L.ptr(g_col),
+                                             L.ptr(g_shs), L.ptr(g_scales), L.ptr(g_rots), L.ptr(g_cov),
+                                             (2 if (sh_record is not None and shs is not None) else 1)
+                                             if accumulate_into is not None else 0, stream),
+                "dmgs_preprocess_backward")
+        if stage_hook is not None:
+            stage_hook("preprocess_bwd")
     return g_means3D, g_means2D, g_shs, g_col, g_op, g_scales, g_rots, g_cov
 
 
@@ -303,8 +516,20 @@ def sh_grad_expand(records, camera_centers, means3D, shs, sh_degree, out, out_me
     tensors/sequences of 3 floats (the campos of each view's settings, in the same order); shs: the coefficients;
     out: the [P,M,3] (sh_layout 0) or [P,3,M] (1) gradient tensor, overwritten (accumulate=False) or added to;
     out_means3D: [P,3], always added to."""
+    if records.dim() != 3 or records.shape[2] != 4 or records.stride(2) != 1 or records.stride(1) != 4:
+        raise ValueError(f"records: expected [V,P,4] with contiguous [P,4] views, got {tuple(records.shape)} / "
+                         f"{tuple(records.stride())}")
     V, P = int(records.shape[0]), int(records.shape[1])
+    dev = records.device
+    _check("means3D", means3D, (P, 3), device=dev)
+    _check("shs", shs, (P, None, 3) if sh_layout == 0 else (P, 3, None), device=dev)
+    _check("out", out, tuple(shs.shape), device=dev)
+    _check("out_means3D", out_means3D, (P, 3), device=dev)
+    if records.dtype != torch.float32 or not records.is_cuda:
+        raise TypeError("records: expected a float32 CUDA tensor")
     M = int(out.shape[1] if sh_layout == 0 else out.shape[2])
+    if M < (int(sh_degree) + 1) ** 2:
+        raise ValueError(f"out holds {M} coefficients per channel, sh_degree {sh_degree} needs {(int(sh_degree) + 1) ** 2}")
     cams = []
     for c in camera_centers:
         cams.extend(_host_values([c])[0] if isinstance(c, torch.Tensor) else [float(x) for x in c])
@@ -312,9 +537,10 @@ def sh_grad_expand(records, camera_centers, means3D, shs, sh_degree, out, out_me
         raise ValueError("one camera centre per view")
     arr = (C.c_float * (3 * V))(*cams)
     stride = int(records.stride(0)) if V > 1 else P * 4
-    L.check(L.lib().dmgs_sh_grad_expand(P, int(sh_degree), M, int(sh_layout), V, arr, L.ptr(means3D), L.ptr(shs),
-                                        L.ptr(records), stride, L.ptr(out), L.ptr(out_means3D), int(bool(accumulate)),
-                                        _stream()), "dmgs_sh_grad_expand")
+    with torch.cuda.device(dev):
+        L.check(L.lib().dmgs_sh_grad_expand(P, int(sh_degree), M, int(sh_layout), V, arr, L.ptr(means3D), L.ptr(shs),
+                                            L.ptr(records), stride, L.ptr(out), L.ptr(out_means3D), int(bool(accumulate)),
+                                            _stream(dev)), "dmgs_sh_grad_expand")
     return out
 
 
@@ -374,8 +600,9 @@ class GaussianRasterizer(nn.Module):
             if P:
                 view = rs.viewmatrix.float().contiguous()
                 proj = rs.projmatrix.float().contiguous()
-                L.check(L.lib().dmgs_mark_visible(P, L.ptr(pos), L.ptr(view), L.ptr(proj), L.ptr(vis), _stream()),
-                        "dmgs_mark_visible")
+                with torch.cuda.device(positions.device):
+                    L.check(L.lib().dmgs_mark_visible(P, L.ptr(pos), L.ptr(view), L.ptr(proj), L.ptr(vis),
+                                                      _stream(positions.device)), "dmgs_mark_visible")
             return vis.bool()
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,

@@ -33,13 +33,39 @@ def build(force: bool = False) -> str:
     return so
 
 
+def _load(path):
+    l = C.CDLL(path)
+    l.orc_count_instances.restype = C.c_int64
+    l.orc_num_threads.restype = C.c_int
+    return l
+
+
 def lib():
     global _LIB
     if _LIB is None:
-        _LIB = C.CDLL(build())
-        _LIB.orc_count_instances.restype = C.c_int64
-        _LIB.orc_num_threads.restype = C.c_int
+        _LIB = _load(build())
     return _LIB
+
+
+def use_native() -> str:
+    """CPU-baseline timing only (bench.py): rebuild the same source with `-O3 -march=native` ON THE
+    MACHINE THAT RUNS IT (the portable liboracle.so travels to the GPU box prebuilt for x86-64-v3) and
+    switch to it.  Falls back to the portable build if gcc is unavailable.  Returns the flags in use."""
+    global _LIB
+    out_dir = os.path.join(_HERE, "_native")
+    so = os.path.join(out_dir, "liboracle_native.so")
+    src = os.path.join(_HERE, "splat_oracle.c")
+    flags = ["-O3", "-march=native", "-std=c11", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off", "-fno-fast-math"]
+    try:
+        os.makedirs(out_dir, exist_ok=True)
+        tmp = so + f".{os.getpid()}.tmp"
+        subprocess.check_call(["gcc", *flags, "-o", tmp, src, "-lm"], stderr=subprocess.DEVNULL)
+        os.replace(tmp, so)  # always rebuilt: the file may come from another machine's snapshot
+        _LIB = _load(so)
+        return " ".join(flags)
+    except Exception:
+        lib()
+        return "portable build (oracle/Makefile flags); native rebuild failed"
 
 
 def _p(a):

@@ -176,3 +176,42 @@ def test_adam_flat_buffer_split_lr_and_scale_vs_torch():
             assert torch.all((params[k] - tp[k].detach()).abs() <= 2e-6 * (tp[k].detach().abs() + lrs[k])), (k, t)
         ref = torch.cat([dc.detach(), rest.detach()], 1)
         assert torch.all((params["shs"] - ref).abs() <= 2e-6 * (ref.abs() + 0.0025)), t
+
+
+def test_adam_state_dict_round_trip_and_grad_lookup_errors():
+    """torch.optim's checkpoint surface (the reference's capture() stores optimizer.state_dict(), mlp_flex.py:102)
+    and the loud failures of name-keyed gradients."""
+    from dmgs_b200.optim import FusedAdam
+    gen = torch.Generator().manual_seed(4)
+    mk = lambda: {k: torch.randn(1000, w, generator=torch.Generator().manual_seed(7)).cuda() for k, w in (("a", 3), ("b", 4))}
+    pa, pb = mk(), mk()
+    opt_a = FusedAdam([{"params": [pa[k]], "lr": 0.01, "name": k} for k in pa], lr=0.0, eps=1e-15)
+    grads = [{k: torch.randn(v.shape, generator=gen).cuda() for k, v in pa.items()} for _ in range(4)]
+    for g in grads[:2]:
+        opt_a.step(grads={k: v.clone() for k, v in g.items()})
+    sd = opt_a.state_dict()
+    assert set(sd) == {"state", "param_groups"} and sd["param_groups"][0]["params"] == [0] and float(sd["state"][1]["step"]) == 2
+    # torch.optim.Adam accepts the same dict (same layout)
+    tp = [pa["a"].clone().requires_grad_(), pa["b"].clone().requires_grad_()]
+    topt = torch.optim.Adam([{"params": [tp[0]], "lr": 0.01}, {"params": [tp[1]], "lr": 0.01}], lr=0.0, eps=1e-15)
+    topt.load_state_dict({"state": {i: {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in st.items()}
+                                    for i, st in sd["state"].items()},
+                          "param_groups": [{**topt.param_groups[i], "params": [i]} for i in range(2)]})
+    opt_b = FusedAdam([{"params": [pb[k]], "lr": 0.5, "name": k} for k in pb], lr=0.0, eps=1e-15)
+    for k in pb:
+        pb[k].copy_(pa[k])
+    opt_b.load_state_dict(sd)
+    assert opt_b.param_groups[0]["lr"] == 0.01
+    for g in grads[2:]:
+        opt_a.step(grads={k: v.clone() for k, v in g.items()})
+        opt_b.step(grads={k: v.clone() for k, v in g.items()})
+        tp[0].grad, tp[1].grad = g["a"].clone(), g["b"].clone()
+        topt.step()
+    for k, t in zip(pa, tp):
+        assert torch.equal(pa[k], pb[k])
+        assert torch.all((pa[k] - t.detach()).abs() <= 2e-6 * (t.detach().abs() + 0.01))
+    with pytest.raises(KeyError):
+        opt_a.step(grads={"a": grads[0]["a"]})
+    two = FusedAdam([{"params": [pa["a"], pa["b"]], "lr": 0.01, "name": "both"}])
+    with pytest.raises(RuntimeError):
+        two.step(grads={"both": grads[0]["a"]})

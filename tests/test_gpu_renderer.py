@@ -213,8 +213,9 @@ def test_view_batched_training_step_reduces_the_loss():
 
 def test_async_binning_matches_sync_and_reports_overflow():
     """configure(async_binning=True): same image / gradients without the host read-back; a frame whose
-    instance list outgrows the remembered capacity renders as background, check_async() reports it,
-    and the repeated frame is right."""
+    instance list outgrows the remembered capacity is never trusted silently: its backward raises
+    BinningOverflowError (the module path), check_async() reports it (the training-step path, verify=False), and
+    the repeated frame is right."""
     import dmgs_b200
     from dmgs_b200 import GaussianRasterizer
     from dmgs_b200 import rasterizer as RZ
@@ -233,25 +234,40 @@ def test_async_binning_matches_sync_and_reports_overflow():
         img.square().sum().backward()
         return img.detach(), t["means3D"].grad.clone(), ras.last
 
+    def low_level(scales):
+        color, radii, st = RZ.rasterize_forward(rs, d["means3D"], d["opacities"], d["shs"], None, scales, d["rotations"], None)
+        g = RZ.rasterize_backward(st, torch.ones_like(color), d["means3D"], d["shs"], scales, d["rotations"], None, False,
+                                  verify=False)
+        return color, g[0], st
+
     ref_img, ref_g, _ = run(d["scales"])
     big_img, _, _ = run(d["scales"] * 3.0)
     try:
         dmgs_b200.configure(async_binning=True, capacity_slack=1.25)
         RZ._ASYNC["capacity"].clear()
         img0, g0, st0 = run(d["scales"])  # first frame of this shape: synchronous, learns the capacity
-        assert st0._count_dev is None and dmgs_b200.check_async()
+        assert st0.layout_R == st0.num_rendered and dmgs_b200.check_async()
         img1, g1, st1 = run(d["scales"])  # sync-free
-        assert st1._count_dev is not None and st1.layout_R > st1.num_rendered
+        assert st1.layout_R > st1.num_rendered
         assert dmgs_b200.check_async()
         assert torch.equal(img1, ref_img) and torch.equal(img0, ref_img)
         grad_close(g1.cpu().numpy(), ref_g.cpu().numpy(), rtol=2e-4, name="means3D")
-        # 3x larger splats: the instance list no longer fits
-        img2, g2, st2 = run(d["scales"] * 3.0)
-        assert not dmgs_b200.check_async()
-        bgimg = torch.tensor([0.3, 0.2, 0.1], device="cuda").view(3, 1, 1).expand_as(img2)
-        assert torch.equal(img2, bgimg) and g2.abs().sum() == 0
+        # 3x larger splats: the instance list no longer fits -> the module's backward refuses the frame
+        with pytest.raises(RZ.BinningOverflowError):
+            run(d["scales"] * 3.0)
+        dmgs_b200.check_async()
         img3, _, st3 = run(d["scales"] * 3.0)  # repeated with the raised capacity
         assert dmgs_b200.check_async()
         assert torch.equal(img3, big_img)
+        # the training-step path polls once per step instead (verify=False keeps the host running ahead)
+        RZ._ASYNC["capacity"].clear()
+        low_level(d["scales"])
+        assert dmgs_b200.check_async()
+        img4, g4, st4 = low_level(d["scales"] * 3.0)
+        assert not dmgs_b200.check_async()
+        bgimg = torch.tensor([0.3, 0.2, 0.1], device="cuda").view(3, 1, 1).expand_as(img4)
+        assert torch.equal(img4, bgimg) and g4.abs().sum() == 0
+        img5, _, _ = low_level(d["scales"] * 3.0)
+        assert dmgs_b200.check_async() and torch.equal(img5, big_img)
     finally:
         dmgs_b200.configure(async_binning=False)

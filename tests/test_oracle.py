@@ -233,3 +233,39 @@ def test_stage3_oracle_matches_reference_golden():
     for got, name in ((r2.grad, "drotation2d"), (s2.grad, "dscaling2d")):
         ref = g[name]
         assert np.linalg.norm(got.numpy() - ref) <= 1e-4 * np.linalg.norm(ref), name
+
+
+def test_binning_equals_one_stable_sort_of_the_64_bit_keys():
+    """The oracle partitions by tile and merge-sorts every bucket; the result must be THE stable sort of the
+    (tile << 32 | depth bits) keys emitted in ascending Gaussian index, row-major over each rectangle
+     -- checked against numpy's stable argsort of independently emitted keys."""
+    P, W, H = 100_000, 800, 800
+    cl = S.random_cloud(P, seed=0)
+    cam = S.nerf_synthetic_camera(0, W, H)
+    pr = cam_params(cam, P, np.zeros(3, np.float32))
+    g = O.preprocess(pr, cl["means3D"].numpy(), cl["opacities"].numpy(), scales=cl["scales"].numpy(),
+                     rotations=cl["rotations"].numpy(), shs=cl["shs"].numpy())
+    b = O.binning(pr, g)
+    gx, gy = (W + 15) // 16, (H + 15) // 16
+    f32 = np.float32
+    rad, px, py = g["radii"].astype(f32), g["xy"][:, 0], g["xy"][:, 1]
+    cl_ = lambda v, hi: np.minimum(np.maximum(v, f32(0)), f32(hi)).astype(np.int64)
+    x0, x1 = cl_((px - rad) * f32(0.0625), gx), cl_((px + rad + f32(15)) * f32(0.0625), gx)
+    y0, y1 = cl_((py - rad) * f32(0.0625), gy), cl_((py + rad + f32(15)) * f32(0.0625), gy)
+    idx = np.nonzero((g["radii"] > 0) & (g["tiles_touched"] > 0))[0]
+    w, n = (x1 - x0)[idx], ((x1 - x0) * (y1 - y0))[idx]
+    assert np.array_equal(n, g["tiles_touched"][idx].astype(np.int64))
+    rep = np.repeat(idx, n)
+    off = np.arange(n.sum()) - np.repeat(np.cumsum(n) - n, n)
+    ww = np.repeat(w, n)
+    ty, tx = np.repeat(y0[idx], n) + off // ww, np.repeat(x0[idx], n) + off % ww
+    keys = ((ty * gx + tx).astype(np.uint64) << np.uint64(32)) | np.repeat(g["depths"].view(np.uint32)[idx], n).astype(np.uint64)
+    order = np.argsort(keys, kind="stable")
+    assert b["R"] == keys.size
+    assert np.array_equal(keys[order], b["keys"]) and np.array_equal(rep[order].astype(np.uint32), b["vals"])
+    T = gx * gy
+    counts = np.bincount((keys >> np.uint64(32)).astype(np.int64), minlength=T)
+    ends = np.cumsum(counts)
+    ne = counts > 0
+    assert np.array_equal(b["ranges"][ne, 0], (ends - counts)[ne]) and np.array_equal(b["ranges"][ne, 1], ends[ne])
+    assert not b["ranges"][~ne].any()
