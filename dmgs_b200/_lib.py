@@ -49,6 +49,9 @@ _SIGS = {
     "dmgs_mark_visible": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp]),
     "dmgs_bind_forward": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _f, _f, _vp, _i32, _vp, _vp, _vp, _vp]),
     "dmgs_bind_backward": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _f, _f, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dmgs_preprocess_forward_bound": (C.c_int, [C.POINTER(DmgsParams), _i64, _i32, _vp, _vp, _vp, _f, _f, _vp, _i32] + [_vp] * 8),
+    "dmgs_preprocess_backward_bound": (C.c_int, [C.POINTER(DmgsParams), _i64, _i32, _vp, _vp, _vp, _f, _f, _vp, _i32]
+                                       + [_vp] * 10 + [_i32, _vp]),
     "dmgs_sh_grad_expand": (C.c_int, [_i32, _i32, _i32, _i32, _i32, C.POINTER(_f), _vp, _vp, _vp, _i64, _vp, _vp, _i32, _vp]),
     "dmgs_stage3_forward": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp]),
     "dmgs_stage3_backward": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -116,6 +116,77 @@ def renew_gaussian(verts, faces, bc, rad_base, spatial_lr_scale, scale_factor, f
             "verts": verts, "faces": faces}
 
 
+# ------------------------------------------------------------------------------ binding fused into the rasteriser
+class _RasterizeMesh(torch.autograd.Function):
+    """verts, g, features | colors, opacities, means2D -> image, radii (+ detached means): the stage-2 chain
+    renew_gaussian -> get_covariance_dyn -> render_dyn (mlp_flex.py:267-311, :370-385; gaussian_renderer/__init__.py:
+    104-193) with the binding inside the per-Gaussian kernels (dmgs_preprocess_forward_bound / _backward_bound)."""
+
+    @staticmethod
+    def forward(ctx, verts, g, shs, colors_precomp, opacities, means2D, faces, bc, rad_base, thin_z, adaptive, settings,
+                sh_layout, sh_activation, want_xyz, holder):
+        from . import rasterizer as RZ
+        if verts.device.type != "cuda":
+            raise RuntimeError("dmgs_b200 binding needs CUDA tensors; there is no CPU path")
+        if bc.dim() == 3 and bc.shape[0] == 1:
+            bc = bc[0]
+        mesh = RZ.BoundMesh(verts.detach().float().contiguous(), faces.to(torch.int64).contiguous(),
+                            bc.detach().float().contiguous(), float(rad_base), float(thin_z),
+                            None if g is None else g.detach().float().reshape(1).contiguous(), bool(adaptive))
+        P = int(mesh.faces.shape[0]) * int(mesh.bc.shape[0])
+        sh_c, col_c = RZ._f32c(shs), RZ._f32c(colors_precomp)
+        op_c = RZ._f32c(opacities)
+        xyz = torch.empty(P, 3, dtype=torch.float32, device=verts.device) if want_xyz else None
+        color, radii, state = RZ.rasterize_forward(settings, None, op_c, sh_c, col_c, None, None, None, sh_layout,
+                                                   sh_activation, bound=mesh, xyz_out=xyz)
+        ctx.state, ctx.mesh, ctx.has_col, ctx.has_g = state, mesh, col_c is not None, g is not None
+        ctx.save_for_backward(sh_c)
+        if holder is not None:
+            holder.last = state
+        ctx.mark_non_differentiable(radii)
+        if want_xyz:
+            ctx.mark_non_differentiable(xyz)
+            return color, radii, xyz
+        return color, radii
+
+    @staticmethod
+    def backward(ctx, grad_color, *_unused):
+        from . import rasterizer as RZ
+        (sh_c,) = ctx.saved_tensors
+        mesh = ctx.mesh
+        dverts = torch.zeros_like(mesh.verts)
+        dg = torch.zeros(1, dtype=torch.float32, device=dverts.device) if ctx.has_g else None
+        g_means2D, g_shs, g_col, g_op = RZ.rasterize_backward_bound(ctx.state, grad_color.contiguous().float(), mesh, sh_c,
+                                                                    ctx.has_col, dverts, dg)
+        return (dverts, dg, g_shs, g_col, g_op, g_means2D) + (None,) * 10
+
+
+class MeshRasterizer:
+    """Holder mirroring GaussianRasterizer's `.last` for the fused mesh path."""
+
+    last = None
+
+
+def rasterize_mesh(raster_settings, verts, faces, bc, rad_base, thin_z, opacities, features=None, colors_precomp=None,
+                   scale_factor=None, max_scale=2.0, adaptive_cov=True, means2D=None, sh_activation="sigmoid",
+                   sh_layout="P3M", return_xyz=False, holder=None):
+    """Stage-2 render straight from the mesh: -> (image [3,H,W], radii [F*k]) (+ detached gs_xyz [F*k,3] when
+    return_xyz, for the texture MLP).  Same values and gradients as bind_faces(...) followed by
+    GaussianRasterizer(settings, sh_activation, sh_layout)(means3D=gs_xyz, cov3D_precomp=cov, shs=features, ...),
+    without the xyz / cov3D_precomp / dL/dxyz / dL/dcov tensors.  means2D ([F*k,3] zeros with requires_grad, the
+    reference's screenspace_points) receives the viewspace gradient."""
+    if (features is None) == (colors_precomp is None):
+        raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+    g = None if scale_factor is None else torch.tanh(scale_factor) * max_scale  # mlp_flex.py:377
+    P = int(faces.shape[0]) * int(bc.shape[-2])
+    if means2D is None:
+        means2D = torch.zeros(P, 3, dtype=torch.float32, device=verts.device)
+    act = {"clamp": 0, "sigmoid": 1}[sh_activation]
+    lay = {"PM3": 0, "P3M": 1}[sh_layout]
+    return _RasterizeMesh.apply(verts, g, features, colors_precomp, opacities, means2D, faces, bc, rad_base, thin_z,
+                                adaptive_cov, raster_settings, lay, act, return_xyz, holder)
+
+
 # ------------------------------------------------------------------------------ stage 3
 class _Stage3(torch.autograd.Function):
     """(rot_t2w [F,3,3], scaling2d [P,2], rotation2d [P,2]) -> scales / quaternions / cov6 on the device
@@ -178,5 +249,5 @@ def in_frustum(full_proj_transform, points):
     return _f(full_proj_transform, points)
 
 
-__all__ = ["bind_faces", "bind_frame", "face_normals", "renew_gaussian", "stage3_scales_rotations", "stage3_covariance", "in_frustum",
+__all__ = ["bind_faces", "bind_frame", "rasterize_mesh", "MeshRasterizer", "face_normals", "renew_gaussian", "stage3_scales_rotations", "stage3_covariance", "in_frustum",
            "barycentric_layout"]

@@ -5,6 +5,7 @@
 
 #include "common.cuh"
 #include "kernels.cuh"
+#include "bind_math.cuh"
 
 namespace dmgs {
 
@@ -122,16 +123,17 @@ int dmgs_image_layout(int32_t W, int32_t H, int64_t *o)
     return 0;
 }
 
-int dmgs_preprocess_forward(const dmgs_params *prm, const float *means3D, const float *scales, const float *rotations,
-                            const float *cov3D_precomp, const float *opacities, const float *shs,
-                            const float *colors_precomp, int32_t *radii, void *geom, uint32_t *num_rendered,
-                            void *stream)
+static int preprocess_forward_impl(const dmgs_params *prm, const BindSrc *bind, float *xyz_out, const float *means3D,
+                                   const float *scales, const float *rotations,
+                                   const float *cov3D_precomp, const float *opacities, const float *shs,
+                                   const float *colors_precomp, int32_t *radii, void *geom, uint32_t *num_rendered,
+                                   void *stream)
 {
     int rc = validate(prm);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     if ((shs == nullptr) == (colors_precomp == nullptr)) { set_error("provide exactly one of shs / colors_precomp"); return -4; }
-    if (((scales == nullptr) || (rotations == nullptr)) == (cov3D_precomp == nullptr)) {
+    if (!bind && ((scales == nullptr) || (rotations == nullptr)) == (cov3D_precomp == nullptr)) {
         set_error("provide exactly one of (scales, rotations) / cov3D_precomp");
         return -5;
     }
@@ -142,7 +144,7 @@ int dmgs_preprocess_forward(const dmgs_params *prm, const float *means3D, const 
         DMGS_CUDA(cudaMemsetAsync(num_rendered, 0, sizeof(uint32_t), s));
         return 0;
     }
-    if (!means3D || !opacities || !radii || !geom) { set_error("NULL required pointer"); return -6; }
+    if ((!bind && !means3D) || !opacities || !radii || !geom) { set_error("NULL required pointer"); return -6; }
     const GeomLayout L = geom_layout(P);
     // with direct tile placement (place.cu) only the TOTAL of tiles-touched is needed: preprocess reduces
     // it on the fly; the radix tile partition also needs the per-Gaussian offsets (scan below)
@@ -153,8 +155,8 @@ int dmgs_preprocess_forward(const dmgs_params *prm, const float *means3D, const 
         DMGS_CUDA(cudaMemsetAsync(num_rendered, 0, sizeof(uint32_t), s));
         DMGS_CUDA(cudaMemsetAsync(stat, 0, 16, s));
     }
-    rc = launch_preprocess_fwd(prm, means3D, scales, rotations, cov3D_precomp, opacities, shs, colors_precomp, radii,
-                               geom, L, placed ? num_rendered : nullptr, stat, s);
+    rc = launch_preprocess_fwd(prm, bind, xyz_out, means3D, scales, rotations, cov3D_precomp, opacities, shs,
+                               colors_precomp, radii, geom, L, placed ? num_rendered : nullptr, stat, s);
     if (rc) return rc;
     if ((rc = check_stage(prm, s, "preprocess"))) return rc;
     // stable depth sort of the Gaussians: 8-bit LSD passes over (keys_a, order) <-> (keys_b, vals_b).
@@ -172,6 +174,41 @@ int dmgs_preprocess_forward(const dmgs_params *prm, const float *means3D, const 
     rc = exclusive_scan_u32(at<uint32_t>(geom, L.tiles), va, at<uint32_t>(geom, L.offsets), P, num_rendered, tmp, s);
     if (rc) return rc;
     return check_stage(prm, s, "tile scan");
+}
+
+int dmgs_preprocess_forward(const dmgs_params *prm, const float *means3D, const float *scales, const float *rotations,
+                            const float *cov3D_precomp, const float *opacities, const float *shs,
+                            const float *colors_precomp, int32_t *radii, void *geom, uint32_t *num_rendered,
+                            void *stream)
+{
+    return preprocess_forward_impl(prm, nullptr, nullptr, means3D, scales, rotations, cov3D_precomp, opacities, shs,
+                                   colors_precomp, radii, geom, num_rendered, stream);
+}
+
+static int make_bind_src(const dmgs_params *prm, int64_t F, int32_t k, const float *verts, const int64_t *faces,
+                         const float *bc, float rad_base, float thin_z, const float *g, int32_t adaptive, BindSrc *bs)
+{
+    if (!prm) { set_error("params is NULL"); return -1; }
+    if (F < 0 || k <= 0 || F * (int64_t)k != (int64_t)prm->P) {
+        set_error("bound preprocess: P = %d must equal F * k = %lld * %d", prm->P, (long long)F, k);
+        return -2;
+    }
+    if (F > 0 && (!verts || !faces || !bc)) { set_error("bound preprocess: NULL mesh pointer"); return -6; }
+    bs->verts = verts; bs->faces = faces; bs->bc = bc; bs->g_ptr = g;
+    bs->rad_base = rad_base; bs->thin_z = thin_z; bs->k = k; bs->adaptive = adaptive;
+    return 0;
+}
+
+int dmgs_preprocess_forward_bound(const dmgs_params *prm, int64_t F, int32_t k, const float *verts, const int64_t *faces,
+                                  const float *bc, float rad_base, float thin_z, const float *g, int32_t adaptive,
+                                  const float *opacities, const float *shs, const float *colors_precomp, int32_t *radii,
+                                  void *geom, uint32_t *num_rendered, float *xyz_out, void *stream)
+{
+    BindSrc bs;
+    int rc = make_bind_src(prm, F, k, verts, faces, bc, rad_base, thin_z, g, adaptive, &bs);
+    if (rc) return rc;
+    return preprocess_forward_impl(prm, &bs, xyz_out, nullptr, nullptr, nullptr, nullptr, opacities, shs, colors_precomp,
+                                   radii, geom, num_rendered, stream);
 }
 
 static int bin_forward_impl(const dmgs_params *prm, const void *geom, int64_t R, void *binning, uint32_t *overflow,
@@ -302,11 +339,36 @@ int dmgs_preprocess_backward(const dmgs_params *prm, const float *means3D, const
         return -6;
     }
     const GeomLayout GL = geom_layout(P);
-    rc = launch_preprocess_bwd(prm, means3D, scales, rotations, cov3D_precomp, shs, radii, geom, GL,
+    rc = launch_preprocess_bwd(prm, nullptr, means3D, scales, rotations, cov3D_precomp, shs, radii, geom, GL,
                                (const float *)scratch, dL_dmeans3D, dL_dmeans2D, dL_dopacity, dL_dcolors_precomp,
                                dL_dshs, dL_dscales, dL_drotations, dL_dcov3D, accumulate, s);
     if (rc) return rc;
     return check_stage(prm, s, "preprocess backward");
+}
+
+int dmgs_preprocess_backward_bound(const dmgs_params *prm, int64_t F, int32_t k, const float *verts, const int64_t *faces,
+                                   const float *bc, float rad_base, float thin_z, const float *g, int32_t adaptive,
+                                   const float *shs, const int32_t *radii, const void *geom, const void *scratch,
+                                   float *dverts, float *dg, float *dL_dmeans2D, float *dL_dopacity,
+                                   float *dL_dcolors_precomp, float *dL_dshs, int32_t accumulate, void *stream)
+{
+    int rc = validate(prm);
+    if (rc) return rc;
+    BindSrc bs;
+    if ((rc = make_bind_src(prm, F, k, verts, faces, bc, rad_base, thin_z, g, adaptive, &bs))) return rc;
+    if ((rc = validate_sh(prm, shs))) return rc;
+    if (accumulate != 0 && accumulate != 1) { set_error("bound backward: accumulate must be 0 or 1"); return -6; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int P = prm->P;
+    if (P == 0) return 0;
+    if (!radii || !geom || !dverts || !dL_dmeans2D || !dL_dopacity || !scratch) { set_error("NULL required pointer"); return -6; }
+    const GeomLayout GL = geom_layout(P);
+    // in this mode the dL_dmeans3D / dL_dcov3D slots of the kernel carry dverts [V,3] / dg [1] (both accumulated)
+    rc = launch_preprocess_bwd(prm, &bs, nullptr, nullptr, nullptr, nullptr, shs, radii, geom, GL, (const float *)scratch,
+                               dverts, dL_dmeans2D, dL_dopacity, dL_dcolors_precomp, dL_dshs, nullptr, nullptr, dg,
+                               accumulate, s);
+    if (rc) return rc;
+    return check_stage(prm, s, "bound preprocess backward");
 }
 
 int dmgs_backward(const dmgs_params *prm, const float *means3D, const float *scales, const float *rotations,

@@ -73,8 +73,9 @@ blend_fwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
                 if (!done) {
                     const float4 ra = lds128(a_ra + 16u * j), rb = lds128(a_rb + 16u * j);
                     const float dx = ra.x - pxf, dy = ra.y - pyf;
-                    const float q = fma_(rb.x * dy, dy, (ra.z * dx) * dx);
-                    const float power = fma_(-(ra.w * dx), dy, -0.5f * q);
+                    // rounding order of upstream's -0.5f * (A dx dx + C dy dy) - B dx dy under nvcc's contraction
+                    const float q = fma_(dx, ra.z * dx, (rb.x * dy) * dy);
+                    const float power = fma_(q, -0.5f, -((ra.w * dx) * dy));
                     if (power <= 0.0f) {
                         const float alpha = fminf(0.99f, rb.y * dmgs_exp(power));
                         if (alpha >= 1.0f / 255.0f) {

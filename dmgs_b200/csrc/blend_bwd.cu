@@ -128,8 +128,8 @@ blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
                     if (pos < last) {
                         // same power / exp / alpha arithmetic as the forward (explicit _rn operations, immune
                         // to contraction): the contributor set is identical
-                        const float q = fma_(__fmul_rn(rb.x, dy), dy, __fmul_rn(__fmul_rn(ra.z, dx), dx));
-                        const float power = fma_(-__fmul_rn(ra.w, dx), dy, __fmul_rn(-0.5f, q));
+                        const float q = fma_(dx, __fmul_rn(ra.z, dx), __fmul_rn(__fmul_rn(rb.x, dy), dy));
+                        const float power = fma_(q, -0.5f, -__fmul_rn(__fmul_rn(ra.w, dx), dy));
                         if (power <= 0.0f) {
                             const float G = dmgs_exp(power);
                             const float alpha = fminf(0.99f, __fmul_rn(rb.y, G));

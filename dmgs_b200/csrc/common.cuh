@@ -144,9 +144,17 @@ template <typename T> static inline const T *at(const void *base, size_t off)
 // ----------------------------------------------------------------------------- device math
 #ifdef __CUDACC__
 __device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+// a0*b0 + a1*b1 + a2*b2 in the rounding order nvcc's default contraction gives that expression (the upstream
+// rasteriser's GLM products and transformPoint helpers): the SECOND product is rounded on its own, the first and
+// the third are fused -- fma(a2, b2, fma(a0, b0, a1*b1)) (oracle/upstream_arith.cu, scripts/arith_divergence.py)
 __device__ __forceinline__ float dot3(float a0, float b0, float a1, float b1, float a2, float b2)
 {
-    return fma_(a2, b2, fma_(a1, b1, a0 * b0));
+    return fma_(a2, b2, fma_(a0, b0, a1 * b1));
+}
+// ndc2Pix as upstream writes it: ((v + 1.0) * S - 1.0) * 0.5 with DOUBLE literals, rounded to float once
+__device__ __forceinline__ float ndc2pix(float v, int S)
+{
+    return (float)((((double)v + 1.0) * (double)S - 1.0) * 0.5);
 }
 // row r of a column-major 4x4 applied to (x, y, z, 1)
 __device__ __forceinline__ float affine3(const float *m, int r, float x, float y, float z)

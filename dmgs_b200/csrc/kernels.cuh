@@ -7,11 +7,14 @@ namespace dmgs {
 DevParams make_dev_params(const dmgs_params *p);
 
 // preprocess.cu
-int launch_preprocess_fwd(const dmgs_params *prm, const float *means3D, const float *scales, const float *rotations,
+struct BindSrc;  // bind_math.cuh: mesh source of the fused bind + preprocess path (NULL: plain per-Gaussian inputs)
+int launch_preprocess_fwd(const dmgs_params *prm, const BindSrc *bind, float *xyz_out, const float *means3D,
+                          const float *scales, const float *rotations,
                           const float *cov3D_precomp, const float *opacities, const float *shs,
                           const float *colors_precomp, int32_t *radii, void *geom, const GeomLayout &L,
                           uint32_t *total_instances, uint32_t *key_stat, cudaStream_t s);
-int launch_preprocess_bwd(const dmgs_params *prm, const float *means3D, const float *scales, const float *rotations,
+int launch_preprocess_bwd(const dmgs_params *prm, const BindSrc *bind, const float *means3D, const float *scales,
+                          const float *rotations,
                           const float *cov3D_precomp, const float *shs, const int32_t *radii, const void *geom,
                           const GeomLayout &L, const float *grad_blend, float *dL_dmeans3D, float *dL_dmeans2D,
                           float *dL_dopacity, float *dL_dcolprec, float *dL_dshs, float *dL_dscales, float *dL_drots,

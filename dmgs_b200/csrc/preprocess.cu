@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include "sh_stage.cuh"
+#include "bind_math.cuh"
 
 namespace dmgs {
 
@@ -68,15 +69,17 @@ __device__ __forceinline__ int sh_basis(int deg, float x, float y, float z, floa
 __device__ __forceinline__ void quat_to_rot(const float *q, float R[3][3])
 {
     const float r = q[0], x = q[1], y = q[2], z = q[3];
-    R[0][0] = fma_(-2.0f, fma_(z, z, y * y), 1.0f);
-    R[0][1] = 2.0f * fma_(-r, z, x * y);
+    // rounding order = what nvcc (default contraction + CSE of the shared products) emits for upstream's
+    // 1 - 2(yy + zz), 2(xy -+ rz), ... : see oracle/upstream_arith.cu
+    R[0][0] = 1.0f - 2.0f * (y * y + z * z);
+    R[0][1] = 2.0f * fma_(x, y, -(r * z));
     R[0][2] = 2.0f * fma_(r, y, x * z);
-    R[1][0] = 2.0f * fma_(r, z, x * y);
-    R[1][1] = fma_(-2.0f, fma_(z, z, x * x), 1.0f);
-    R[1][2] = 2.0f * fma_(-r, x, y * z);
+    R[1][0] = 2.0f * fma_(x, y, r * z);
+    R[1][1] = 1.0f - 2.0f * fma_(x, x, z * z);
+    R[1][2] = 2.0f * fma_(y, z, -(r * x));
     R[2][0] = 2.0f * fma_(-r, y, x * z);
-    R[2][1] = 2.0f * fma_(r, x, y * z);
-    R[2][2] = fma_(-2.0f, fma_(y, y, x * x), 1.0f);
+    R[2][1] = 2.0f * fma_(y, z, r * x);
+    R[2][2] = 1.0f - 2.0f * fma_(x, x, y * y);
 }
 
 // Shared between forward and backward: T = J * W (2x3), u = Sigma * T^T, cov2D (a,b,c incl. +0.3)
@@ -108,7 +111,7 @@ __device__ __forceinline__ void ewa_project(const DevParams &pr, float x, float 
         e.u1[j] = dot3(S[j][0], e.T1[0], S[j][1], e.T1[1], S[j][2], e.T1[2]);
     }
     e.a = dot3(e.T0[0], e.u0[0], e.T0[1], e.u0[1], e.T0[2], e.u0[2]) + 0.3f;
-    e.b = dot3(e.T1[0], e.u0[0], e.T1[1], e.u0[1], e.T1[2], e.u0[2]);
+    e.b = dot3(e.T0[0], e.u1[0], e.T0[1], e.u1[1], e.T0[2], e.u1[2]);  // cov[0][1] of T^T Vrk^T T
     e.c = dot3(e.T1[0], e.u1[0], e.T1[1], e.u1[1], e.T1[2], e.u1[2]) + 0.3f;
 }
 
@@ -123,9 +126,13 @@ __device__ __forceinline__ float sh_get(const float *__restrict__ shs, const Dev
     return pr.sh_layout == 0 ? __ldg(shs + ((size_t)i * pr.M + k) * 3 + ch) : __ldg(shs + ((size_t)i * 3 + ch) * pr.M + k);
 }
 
-template <int SHMODE>
-__global__ void __launch_bounds__(256, 4)
-preprocess_fwd_kernel(const __grid_constant__ DevParams pr, const float *__restrict__ means3D, const float *__restrict__ scales,
+// BOUND: the Gaussian's mean and covariance are not read from means3D / cov3D_precomp but built in registers
+// from its mesh face (Gaussian i = face i / k, barycentric row i % k; bind_math.cuh) -- the binding fused into
+// preprocess: no xyz[P,3] / cov6[P,6] round trip through HBM (xyz_out, optional, serves the texture MLP).
+template <int SHMODE, bool BOUND>
+__global__ void __launch_bounds__(256, BOUND ? 3 : 4)
+preprocess_fwd_kernel(const __grid_constant__ DevParams pr, const __grid_constant__ BindSrc bs, float *__restrict__ xyz_out,
+                      const float *__restrict__ means3D, const float *__restrict__ scales,
                       const float *__restrict__ rotations, const float *__restrict__ cov3D_precomp,
                       const float *__restrict__ opacities, const float *__restrict__ shs,
                       const float *__restrict__ colors_precomp, int32_t *__restrict__ radii,
@@ -149,8 +156,22 @@ preprocess_fwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
     uint8_t clampbits = 0;
     float c6[6] = {0, 0, 0, 0, 0, 0};
     float x = 0, y = 0, z = 0, tz = 0;
+    float v0[3], v1[3], v2[3];
     if (inb) {
-        x = means3D[3 * i]; y = means3D[3 * i + 1]; z = means3D[3 * i + 2];
+        if (BOUND) {
+            const int64_t f = i / bs.k;
+            const int j = i - (int)f * bs.k;
+            const int64_t i0 = bs.faces[3 * f], i1 = bs.faces[3 * f + 1], i2 = bs.faces[3 * f + 2];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { v0[c] = bs.verts[3 * i0 + c]; v1[c] = bs.verts[3 * i1 + c]; v2[c] = bs.verts[3 * i2 + c]; }
+            const float b0 = __ldg(bs.bc + 3 * j), b1 = __ldg(bs.bc + 3 * j + 1), b2 = __ldg(bs.bc + 3 * j + 2);
+            x = dot3(b0, v0[0], b1, v1[0], b2, v2[0]);
+            y = dot3(b0, v0[1], b1, v1[1], b2, v2[1]);
+            z = dot3(b0, v0[2], b1, v1[2], b2, v2[2]);
+            if (xyz_out) { xyz_out[3 * (size_t)i] = x; xyz_out[3 * (size_t)i + 1] = y; xyz_out[3 * (size_t)i + 2] = z; }
+        } else {
+            x = means3D[3 * i]; y = means3D[3 * i + 1]; z = means3D[3 * i + 2];
+        }
         tz = affine3(pr.V, 2, x, y, z);
     }
     const bool near_ok = inb && tz > DMGS_NEAR;
@@ -161,7 +182,13 @@ preprocess_fwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
         const float hx = affine3(pr.PV, 0, x, y, z), hy = affine3(pr.PV, 1, x, y, z), hw = affine3(pr.PV, 3, x, y, z);
         const float pw = 1.0f / (hw + 1e-7f);
         const float ppx = hx * pw, ppy = hy * pw;
-        if (cov3D_precomp) {
+        if (BOUND) {
+            Frame fr;
+            face_frame(v0, v1, v2, fr);
+            float L00, L01, L11;
+            tri_factor(fr, bs.rad_base, bs.adaptive, L00, L01, L11);
+            bind_cov6(fr, L00, L01, L11, bs.thin_z, bs.g_ptr ? __ldg(bs.g_ptr) : 1.0f, c6);
+        } else if (cov3D_precomp) {
 #pragma unroll
             for (int k = 0; k < 6; ++k) c6[k] = cov3D_precomp[6 * (size_t)i + k];
         } else {
@@ -183,14 +210,13 @@ preprocess_fwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
         }
         Ewa e;
         ewa_project(pr, x, y, z, c6, e);
-        const float det = fma_(-e.b, e.b, e.a * e.c);
+        const float det = fma_(e.a, e.c, -(e.b * e.b));
         if (det != 0.0f) {
             const float det_inv = 1.0f / det;
             const float mid = 0.5f * (e.a + e.c);
             const float sq = sqrtf(fmaxf(0.1f, fma_(mid, mid, -det)));
             const float rf = fminf(ceilf(3.0f * sqrtf(fmaxf(mid + sq, mid - sq))), 1.0e9f);
-            const float px = fma_(ppx + 1.0f, (float)pr.W, -1.0f) * 0.5f;
-            const float py = fma_(ppy + 1.0f, (float)pr.H, -1.0f) * 0.5f;
+            const float px = ndc2pix(ppx, pr.W), py = ndc2pix(ppy, pr.H);
             const int x0 = clampi_f((px - rf) * 0.0625f, pr.gx), x1 = clampi_f((px + rf + 15.0f) * 0.0625f, pr.gx);
             const int y0 = clampi_f((py - rf) * 0.0625f, pr.gy), y1 = clampi_f((py + rf + 15.0f) * 0.0625f, pr.gy);
             const int nt = (x1 - x0) * (y1 - y0);
@@ -294,7 +320,7 @@ preprocess_fwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
     rect[i] = rc;
     sort_key[i] = key;
     sort_val[i] = (uint32_t)i;
-    if (!cov3D_precomp) {
+    if (!cov3D_precomp && !BOUND) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) cov3D[6 * (size_t)i + k] = ntiles ? c6[k] : 0.0f;
     }
@@ -307,7 +333,8 @@ static int sh_mode(const dmgs_params *prm, const float *shs)
     return prm->sh_layout == 0 ? 1 : 2;
 }
 
-int launch_preprocess_fwd(const dmgs_params *prm, const float *means3D, const float *scales, const float *rotations,
+int launch_preprocess_fwd(const dmgs_params *prm, const BindSrc *bind, float *xyz_out, const float *means3D,
+                          const float *scales, const float *rotations,
                           const float *cov3D_precomp, const float *opacities, const float *shs,
                           const float *colors_precomp, int32_t *radii, void *geom, const GeomLayout &L,
                           uint32_t *total_instances, uint32_t *key_stat, cudaStream_t s)
@@ -315,20 +342,31 @@ int launch_preprocess_fwd(const dmgs_params *prm, const float *means3D, const fl
     const int P = prm->P;
     if (P <= 0) return 0;
     if (once_per_device(ONCE_PREPROCESS_FWD)) {
-        DMGS_CUDA(cudaFuncSetAttribute(preprocess_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_STAGE_SMEM));
-        DMGS_CUDA(cudaFuncSetAttribute(preprocess_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_STAGE_SMEM));
+        DMGS_CUDA(cudaFuncSetAttribute(preprocess_fwd_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_STAGE_SMEM));
+        DMGS_CUDA(cudaFuncSetAttribute(preprocess_fwd_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_STAGE_SMEM));
+        DMGS_CUDA(cudaFuncSetAttribute(preprocess_fwd_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_STAGE_SMEM));
+        DMGS_CUDA(cudaFuncSetAttribute(preprocess_fwd_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_STAGE_SMEM));
     }
     const int mode = sh_mode(prm, shs);
     const DevParams dp = make_dev_params(prm);
+    BindSrc bs;
+    memset(&bs, 0, sizeof(bs));
+    if (bind) bs = *bind;
 #define DMGS_FWD_ARGS                                                                                               \
-    dp, means3D, scales, rotations, cov3D_precomp, opacities, shs, colors_precomp, radii, at<float>(geom, L.depths), \
+    dp, bs, xyz_out, means3D, scales, rotations, cov3D_precomp, opacities, shs, colors_precomp, radii, at<float>(geom, L.depths), \
         at<float4>(geom, L.rec), at<float4>(geom, L.rgb), at<uint8_t>(geom, L.clamped), at<float>(geom, L.cov3D),    \
         at<uint32_t>(geom, L.tiles), at<uint2>(geom, L.rect), at<uint32_t>(geom, L.keys_a), at<uint32_t>(geom, L.order), \
         total_instances, key_stat
     const int grid = (P + 255) / 256;
-    if (mode == 1) preprocess_fwd_kernel<1><<<grid, 256, SH_STAGE_SMEM, s>>>(DMGS_FWD_ARGS);
-    else if (mode == 2) preprocess_fwd_kernel<2><<<grid, 256, SH_STAGE_SMEM, s>>>(DMGS_FWD_ARGS);
-    else preprocess_fwd_kernel<0><<<grid, 256, 0, s>>>(DMGS_FWD_ARGS);
+    if (bind) {
+        if (mode == 1) preprocess_fwd_kernel<1, true><<<grid, 256, SH_STAGE_SMEM, s>>>(DMGS_FWD_ARGS);
+        else if (mode == 2) preprocess_fwd_kernel<2, true><<<grid, 256, SH_STAGE_SMEM, s>>>(DMGS_FWD_ARGS);
+        else preprocess_fwd_kernel<0, true><<<grid, 256, 0, s>>>(DMGS_FWD_ARGS);
+    } else {
+        if (mode == 1) preprocess_fwd_kernel<1, false><<<grid, 256, SH_STAGE_SMEM, s>>>(DMGS_FWD_ARGS);
+        else if (mode == 2) preprocess_fwd_kernel<2, false><<<grid, 256, SH_STAGE_SMEM, s>>>(DMGS_FWD_ARGS);
+        else preprocess_fwd_kernel<0, false><<<grid, 256, 0, s>>>(DMGS_FWD_ARGS);
+    }
 #undef DMGS_FWD_ARGS
     DMGS_CUDA(cudaGetLastError());
     count_launches(1);
@@ -371,9 +409,13 @@ __device__ __forceinline__ void sh_dir_grad(int deg, const float *h, float ox, f
 // grad_blend: per Gaussian 12 floats {dmean2D.x, dmean2D.y, dconic.a, dconic.b(half), dconic.c,
 // dopacity, dcolor.r, dcolor.g, dcolor.b, pad x3} accumulated by the blend backward.
 // SHMODE 3 = deferred SH gradient (accumulate == 2): no SH row is read or written, only the 16-byte record
-template <int SHMODE>
-__global__ void __launch_bounds__(256, SHMODE == 3 ? 4 : 3)
-preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restrict__ means3D, const float *__restrict__ scales,
+// BOUND: mean and covariance are rebuilt from the mesh face, and dL/dmean, dL/dSigma go straight through the
+// binding adjoint (the reference's truncated gradient: cov3D_L constant) to dverts / dg with atomics -- no
+// dL/dxyz[P,3] / dL/dcov6[P,6] is materialised.  dL_dmeans3D = dverts [V,3], dL_dcov3D = dg [1] in that mode.
+template <int SHMODE, bool BOUND>
+__global__ void __launch_bounds__(256, BOUND ? 2 : (SHMODE == 3 ? 4 : 3))
+preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const __grid_constant__ BindSrc bs,
+                      const float *__restrict__ means3D, const float *__restrict__ scales,
                       const float *__restrict__ rotations, const float *__restrict__ cov3D_precomp,
                       const float *__restrict__ shs, const int32_t *__restrict__ radii,
                       const float *__restrict__ cov3D_state, const uint8_t *__restrict__ clamped,
@@ -399,6 +441,10 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
     float d2x = 0, d2y = 0, dop = 0, dcol[3] = {0, 0, 0};
     float x = 0, y = 0, z = 0;
     const int M = pr.M;
+    // BOUND: the face of this Gaussian
+    float v0[3], v1[3], v2[3], bcw[3] = {0, 0, 0}, L00 = 0, L01 = 0, L11 = 0, gscale = 1.0f;
+    int64_t vi[3] = {0, 0, 0};
+    Frame fr;
 
     if (vis) {
         const float4 ga = grad_blend[3 * (size_t)i], gb = grad_blend[3 * (size_t)i + 1], gc = grad_blend[3 * (size_t)i + 2];
@@ -407,11 +453,27 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
         dop = gb.y;
         dcol[0] = gb.z; dcol[1] = gb.w; dcol[2] = gc.x;
 
-        x = means3D[3 * i]; y = means3D[3 * i + 1]; z = means3D[3 * i + 2];
         float c6[6];
-        const float *csrc = cov3D_precomp ? cov3D_precomp : cov3D_state;
+        if (BOUND) {
+            const int64_t f = i / bs.k;
+            const int j = i - (int)f * bs.k;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) c6[k] = csrc[6 * (size_t)i + k];
+            for (int c = 0; c < 3; ++c) { vi[c] = bs.faces[3 * f + c]; bcw[c] = __ldg(bs.bc + 3 * j + c); }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { v0[c] = bs.verts[3 * vi[0] + c]; v1[c] = bs.verts[3 * vi[1] + c]; v2[c] = bs.verts[3 * vi[2] + c]; }
+            x = dot3(bcw[0], v0[0], bcw[1], v1[0], bcw[2], v2[0]);
+            y = dot3(bcw[0], v0[1], bcw[1], v1[1], bcw[2], v2[1]);
+            z = dot3(bcw[0], v0[2], bcw[1], v1[2], bcw[2], v2[2]);
+            face_frame(v0, v1, v2, fr);
+            tri_factor(fr, bs.rad_base, bs.adaptive, L00, L01, L11);
+            gscale = bs.g_ptr ? __ldg(bs.g_ptr) : 1.0f;
+            bind_cov6(fr, L00, L01, L11, bs.thin_z, gscale, c6);
+        } else {
+            x = means3D[3 * i]; y = means3D[3 * i + 1]; z = means3D[3 * i + 2];
+            const float *csrc = cov3D_precomp ? cov3D_precomp : cov3D_state;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) c6[k] = csrc[6 * (size_t)i + k];
+        }
         Ewa e;
         ewa_project(pr, x, y, z, c6, e);
         const float a = e.a, b = e.b, c = e.c;
@@ -570,7 +632,59 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
         }
     }
 
-    if (inb) {
+    if (BOUND) {
+        // binding adjoint of this Gaussian: dL/dmean through its barycentric row, dL/dSigma through R (and g),
+        // R through the frame to the three vertices; nine reductions into dverts, dg block-reduced
+        float dg_local = 0.0f;
+        if (vis) {
+            float dv[3][3], dR[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+            for (int m = 0; m < 3; ++m)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) dv[m][c] = bcw[m] * gm[c];
+            bind_cov_adjoint(fr, L00, L01, L11, bs.thin_z, gscale, g6, dR, dg_local);
+            frame_adjoint(fr, dR, dv);
+#pragma unroll
+            for (int m = 0; m < 3; ++m)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) atomicAdd(dL_dmeans3D + 3 * vi[m] + c, dv[m][c]);
+        }
+        if (dL_dcov3D) {
+            __shared__ float red[8];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) dg_local += __shfl_xor_sync(0xffffffffu, dg_local, d);
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dg_local;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                float t = 0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) t += red[w];
+                if (t != 0.0f) atomicAdd(dL_dcov3D, t);
+            }
+        }
+        if (inb) {
+            if (accumulate) {
+                if (vis) {
+                    dL_dmeans2D[3 * (size_t)i] += d2x;
+                    dL_dmeans2D[3 * (size_t)i + 1] += d2y;
+                    dL_dopacity[i] += dop;
+                    if (dL_dcolprec) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) dL_dcolprec[3 * (size_t)i + k] += dcol[k];
+                    }
+                }
+            } else {
+                dL_dmeans2D[3 * (size_t)i] = d2x;
+                dL_dmeans2D[3 * (size_t)i + 1] = d2y;
+                dL_dmeans2D[3 * (size_t)i + 2] = 0.0f;
+                dL_dopacity[i] = dop;
+                if (dL_dcolprec) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) dL_dcolprec[3 * (size_t)i + k] = dcol[k];
+                }
+            }
+        }
+    } else if (inb) {
         if (accumulate) {
             if (vis) {
 #pragma unroll
@@ -620,7 +734,8 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const float *__restr
     if (STAGED) stage.flush();  // shared rows must stay valid until the bulk stores have read them
 }
 
-int launch_preprocess_bwd(const dmgs_params *prm, const float *means3D, const float *scales, const float *rotations,
+int launch_preprocess_bwd(const dmgs_params *prm, const BindSrc *bind, const float *means3D, const float *scales,
+                          const float *rotations,
                           const float *cov3D_precomp, const float *shs, const int32_t *radii, const void *geom,
                           const GeomLayout &L, const float *grad_blend, float *dL_dmeans3D, float *dL_dmeans2D,
                           float *dL_dopacity, float *dL_dcolprec, float *dL_dshs, float *dL_dscales, float *dL_drots,
@@ -629,24 +744,34 @@ int launch_preprocess_bwd(const dmgs_params *prm, const float *means3D, const fl
     const int P = prm->P;
     if (P <= 0) return 0;
     if (once_per_device(ONCE_PREPROCESS_BWD)) {
-        DMGS_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_STAGE_SMEM));
-        DMGS_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_STAGE_SMEM));
+        DMGS_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_STAGE_SMEM));
+        DMGS_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_STAGE_SMEM));
+        DMGS_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_STAGE_SMEM));
+        DMGS_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_STAGE_SMEM));
     }
     int mode = (dL_dshs && !(reinterpret_cast<uintptr_t>(dL_dshs) & 15)) ? sh_mode(prm, shs) : 0;
     if (accumulate == 2) {
         if (!dL_dshs || !shs || (reinterpret_cast<uintptr_t>(dL_dshs) & 15)) { set_error("accumulate = 2 needs shs and a 16-byte aligned record array"); return -6; }
+        if (bind) { set_error("the fused binding backward does not support the deferred SH gradient (accumulate = 2)"); return -6; }
         mode = 3;
     }
     const DevParams dp = make_dev_params(prm);
+    BindSrc bs;
+    memset(&bs, 0, sizeof(bs));
+    if (bind) bs = *bind;
 #define DMGS_BWD_ARGS                                                                                                  \
-    dp, means3D, scales, rotations, cov3D_precomp, shs, radii, at<float>(geom, L.cov3D), at<uint8_t>(geom, L.clamped), \
+    dp, bs, means3D, scales, rotations, cov3D_precomp, shs, radii, at<float>(geom, L.cov3D), at<uint8_t>(geom, L.clamped), \
         at<float4>(geom, L.rgb), reinterpret_cast<const float4 *>(grad_blend), dL_dmeans3D, dL_dmeans2D, dL_dopacity,   \
         dL_dcolprec, dL_dshs, dL_dscales, dL_drots, dL_dcov3D, accumulate
     const int grid = (P + 255) / 256;
-    if (mode == 1) preprocess_bwd_kernel<1><<<grid, 256, SH_STAGE_SMEM, s>>>(DMGS_BWD_ARGS);
-    else if (mode == 2) preprocess_bwd_kernel<2><<<grid, 256, SH_STAGE_SMEM, s>>>(DMGS_BWD_ARGS);
-    else if (mode == 3) preprocess_bwd_kernel<3><<<grid, 256, 0, s>>>(DMGS_BWD_ARGS);
-    else preprocess_bwd_kernel<0><<<grid, 256, 0, s>>>(DMGS_BWD_ARGS);
+    if (bind) {
+        if (mode == 1) preprocess_bwd_kernel<1, true><<<grid, 256, SH_STAGE_SMEM, s>>>(DMGS_BWD_ARGS);
+        else if (mode == 2) preprocess_bwd_kernel<2, true><<<grid, 256, SH_STAGE_SMEM, s>>>(DMGS_BWD_ARGS);
+        else preprocess_bwd_kernel<0, true><<<grid, 256, 0, s>>>(DMGS_BWD_ARGS);
+    } else if (mode == 1) preprocess_bwd_kernel<1, false><<<grid, 256, SH_STAGE_SMEM, s>>>(DMGS_BWD_ARGS);
+    else if (mode == 2) preprocess_bwd_kernel<2, false><<<grid, 256, SH_STAGE_SMEM, s>>>(DMGS_BWD_ARGS);
+    else if (mode == 3) preprocess_bwd_kernel<3, false><<<grid, 256, 0, s>>>(DMGS_BWD_ARGS);
+    else preprocess_bwd_kernel<0, false><<<grid, 256, 0, s>>>(DMGS_BWD_ARGS);
 #undef DMGS_BWD_ARGS
     DMGS_CUDA(cudaGetLastError());
     count_launches(1);

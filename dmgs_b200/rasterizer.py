@@ -369,18 +369,52 @@ class RasterState:
         return keys[:R]
 
 
+class BoundMesh(NamedTuple):
+    """Mesh source of the fused bind + preprocess path (dmgs_preprocess_forward_bound): Gaussian i = face i // k,
+    barycentric row i % k.  verts [V,3] f32, faces [F,3] int64, bc [k,3] f32, g: 1-element f32 tensor
+    (tanh(scale_factor) * max_scale) or None."""
+    verts: torch.Tensor
+    faces: torch.Tensor
+    bc: torch.Tensor
+    rad_base: float
+    thin_z: float
+    g: Optional[torch.Tensor]
+    adaptive: bool = True
+
+
+def _check_mesh(m: BoundMesh):
+    dev = m.verts.device
+    _check("verts", m.verts, (None, 3), device=dev)
+    _check("faces", m.faces, (None, 3), dtype=torch.int64, device=dev)
+    _check("bc", m.bc, (None, 3), device=dev)
+    if m.g is not None:
+        _check("g", m.g, (1,), device=dev)
+    return dev, int(m.faces.shape[0]), int(m.bc.shape[0])
+
+
 def rasterize_forward(settings, means3D, opacities, shs, colors_precomp, scales, rotations, cov3D_precomp,
-                      sh_layout=0, sh_activation=0, stage_hook=None):
+                      sh_layout=0, sh_activation=0, stage_hook=None, bound: Optional[BoundMesh] = None, xyz_out=None):
     """Runs the three forward stages; returns (color [3,H,W], radii [P] int32, RasterState).
     Inputs: contiguous float32 CUDA tensors on one device (checked); work is enqueued on that device's current
-    stream."""
-    dev = means3D.device
+    stream.  bound: build mean + covariance from the mesh inside preprocess instead of reading means3D /
+    cov3D_precomp (which must then be None); xyz_out [F*k,3] optionally receives the means."""
+    if bound is not None:
+        if means3D is not None or scales is not None or rotations is not None or cov3D_precomp is not None:
+            raise ValueError("bound mesh source: means3D / scales / rotations / cov3D_precomp must be None")
+        dev, F_, k_ = _check_mesh(bound)
+        P = F_ * k_
+        _check("xyz_out", xyz_out, (P, 3), device=dev)
+    else:
+        dev = means3D.device
+        P = int(means3D.shape[0])
     if dev.type != "cuda":
         raise RuntimeError("dmgs_b200 rasteriser needs CUDA tensors; there is no CPU path")
     lib = L.lib()
-    P = int(means3D.shape[0])
     H, W = int(settings.image_height), int(settings.image_width)
-    _check_inputs(P, dev, means3D, opacities, shs, colors_precomp, scales, rotations, cov3D_precomp, sh_layout)
+    if bound is None:
+        _check_inputs(P, dev, means3D, opacities, shs, colors_precomp, scales, rotations, cov3D_precomp, sh_layout)
+    else:
+        _check_inputs(P, dev, None, opacities, shs, colors_precomp, None, None, None, sh_layout)
     M = 0
     if shs is not None:
         M = int(shs.shape[1] if sh_layout == 0 else shs.shape[2])
@@ -395,9 +429,16 @@ def rasterize_forward(settings, means3D, opacities, shs, colors_precomp, scales,
         color = torch.empty(3, H, W, dtype=torch.float32, device=dev)
         ws = _acquire(dev, cur.cuda_stream, P, W, H)
         nr, flag = ws.meta[0:1], ws.meta[1:2]
-        L.check(lib.dmgs_preprocess_forward(C.byref(prm), L.ptr(means3D), L.ptr(scales), L.ptr(rotations),
-                                            L.ptr(cov3D_precomp), L.ptr(opacities), L.ptr(shs), L.ptr(colors_precomp),
-                                            L.ptr(radii), L.ptr(ws.geom), L.ptr(nr), stream), "dmgs_preprocess_forward")
+        if bound is None:
+            L.check(lib.dmgs_preprocess_forward(C.byref(prm), L.ptr(means3D), L.ptr(scales), L.ptr(rotations),
+                                                L.ptr(cov3D_precomp), L.ptr(opacities), L.ptr(shs), L.ptr(colors_precomp),
+                                                L.ptr(radii), L.ptr(ws.geom), L.ptr(nr), stream), "dmgs_preprocess_forward")
+        else:
+            L.check(lib.dmgs_preprocess_forward_bound(C.byref(prm), F_, k_, L.ptr(bound.verts), L.ptr(bound.faces),
+                                                      L.ptr(bound.bc), float(bound.rad_base), float(bound.thin_z),
+                                                      L.ptr(bound.g), int(bool(bound.adaptive)), L.ptr(opacities), L.ptr(shs),
+                                                      L.ptr(colors_precomp), L.ptr(radii), L.ptr(ws.geom), L.ptr(nr),
+                                                      L.ptr(xyz_out), stream), "dmgs_preprocess_forward_bound")
         if stage_hook is not None:
             stage_hook("preprocess_sort_scan")
         key = (dev.index, P, W, H)
@@ -440,6 +481,40 @@ def rasterize_forward(settings, means3D, opacities, shs, colors_precomp, scales,
         if stage_hook is not None:
             stage_hook("blend_fwd")
     return color, radii, state
+
+
+def rasterize_backward_bound(state: RasterState, grad_color, bound: BoundMesh, shs, want_colors_precomp, dverts, dg,
+                             verify=True):
+    """Backward of a frame rendered with `rasterize_forward(..., bound=mesh)`: blend backward, then the per-Gaussian
+    backward with the binding adjoint fused in (dmgs_preprocess_backward_bound).  dverts [V,3] and dg [1] (or None)
+    are ADDED to (the caller zeroes them).  Returns (dL/dmeans2D [P,3], dL/dshs | None, dL/dcolors_precomp | None,
+    dL/dopacities [P,1])."""
+    lib = L.lib()
+    prm, P = state.prm, state.prm.P
+    dev, F_, k_ = _check_mesh(bound)
+    _check("grad_color", grad_color, (3, prm.image_height, prm.image_width), device=dev)
+    _check("shs", shs, (P, None, 3) if prm.sh_layout == 0 else (P, 3, None), device=dev)
+    _check("dverts", dverts, tuple(bound.verts.shape), device=dev)
+    _check("dg", dg, (1,), device=dev)
+    if verify:
+        state.verify()
+    ws = state._live()
+    z = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+    g_means2D, g_op = z(P, 3), z(P, 1)
+    g_col = z(P, 3) if want_colors_precomp else None
+    g_shs = torch.empty_like(shs) if shs is not None else None
+    with torch.cuda.device(dev):
+        stream = _stream(dev)
+        scratch = ws.ensure_scratch(lib.dmgs_backward_scratch_bytes(P))
+        L.check(lib.dmgs_blend_backward(C.byref(prm), L.ptr(ws.geom), L.ptr(ws.binning), L.ptr(ws.image),
+                                        state.layout_R, L.ptr(grad_color), L.ptr(scratch), stream), "dmgs_blend_backward")
+        L.check(lib.dmgs_preprocess_backward_bound(C.byref(prm), F_, k_, L.ptr(bound.verts), L.ptr(bound.faces),
+                                                   L.ptr(bound.bc), float(bound.rad_base), float(bound.thin_z),
+                                                   L.ptr(bound.g), int(bool(bound.adaptive)), L.ptr(shs), L.ptr(state.radii),
+                                                   L.ptr(ws.geom), L.ptr(scratch), L.ptr(dverts), L.ptr(dg), L.ptr(g_means2D),
+                                                   L.ptr(g_op), L.ptr(g_col), L.ptr(g_shs), 0, stream),
+                "dmgs_preprocess_backward_bound")
+    return g_means2D, g_shs, g_col, g_op
 
 
 def rasterize_backward(state: RasterState, grad_color, means3D, shs, scales, rotations, cov3D_precomp,

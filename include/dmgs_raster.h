@@ -145,6 +145,27 @@ int dmgs_bind_backward(int64_t F, int32_t k, const float *verts, const int64_t *
                        float rad_base, float thin_z, const float *g, int32_t adaptive, const float *dL_dxyz,
                        const float *dL_dcov6, const float *dL_drot, float *dverts, float *dg, void *stream);
 
+/* ---- binding FUSED INTO preprocess (stage-2 mode; SURVEY.md K1 "fused bind+preprocess", K8/K9 "scatter to verts"):
+ *      scene/gaussian_geo_model_mlp_flex.py:267-311 + :370-385 feeding gaussian_renderer/__init__.py:178-186 in ONE
+ *      pass per direction.  Gaussian i = face i / k, barycentric row i % k (face-major, as the reference);
+ *      prm->P must equal F * k.  The mean and Sigma are built in registers (same arithmetic, same bits as
+ *      dmgs_bind_forward) and go straight into the EWA projection + SH colour: no xyz[P,3] / cov6[P,6] round trip.
+ * forward: everything dmgs_preprocess_forward does (state in `geom`, radii, num_rendered; then dmgs_bin_forward /
+ *      dmgs_blend_forward as usual); xyz_out [P,3] optional (the texture MLP consumes the means).
+ * backward (after dmgs_blend_backward filled `scratch`): dL/dmean and dL/dSigma never reach memory: they pass through
+ *      the binding adjoint (the reference's truncated gradient: cov3D_L constant) and are ADDED with reductions to
+ *      dverts [V,3] and dg [1] (dg may be NULL; the caller zeroes both).  dL_dmeans2D [P,3], dL_dopacity [P],
+ *      dL_dcolors_precomp [P,3] / dL_dshs (layout of shs) as dmgs_preprocess_backward (accumulate 0: store, 1: add). */
+int dmgs_preprocess_forward_bound(const dmgs_params *prm, int64_t F, int32_t k, const float *verts, const int64_t *faces,
+                                  const float *bc, float rad_base, float thin_z, const float *g, int32_t adaptive,
+                                  const float *opacities, const float *shs, const float *colors_precomp, int32_t *radii,
+                                  void *geom, uint32_t *num_rendered, float *xyz_out, void *stream);
+int dmgs_preprocess_backward_bound(const dmgs_params *prm, int64_t F, int32_t k, const float *verts, const int64_t *faces,
+                                   const float *bc, float rad_base, float thin_z, const float *g, int32_t adaptive,
+                                   const float *shs, const int32_t *radii, const void *geom, const void *scratch,
+                                   float *dverts, float *dg, float *dL_dmeans2D, float *dL_dopacity,
+                                   float *dL_dcolors_precomp, float *dL_dshs, int32_t accumulate, void *stream);
+
 /* ---- stage-3 binding, per-Gaussian part (scene/gaussian_geo_model_finetune.py:446-453 get_scaling,
  *      :456-463 get_rotation, :465-482 get_rot_matrix, :501-516 get_covariance).
  * rot_t2w [F,9]: the face frames (dmgs_bind_forward's rot_t2w output); rotation2d, scaling2d [F*k,2]:

@@ -134,15 +134,20 @@ def blend_forward(pr: OrcParams, geom: dict, bins: dict) -> dict:
     return out
 
 
-def blend_backward(pr: OrcParams, geom: dict, bins: dict, img: dict, dL_dpix) -> dict:
+def blend_backward(pr: OrcParams, geom: dict, bins: dict, img: dict, dL_dpix, abs_sums: bool = False) -> dict:
+    """abs_sums: also return "abs9" [P,9] (order mean2D.xy, conic.abc, opacity, colour.rgb): the sum of the magnitudes
+    of the terms of every gradient sum (its conditioning; see orc_blend_backward)."""
     P = pr.P
     dL_dpix = _f32(dL_dpix)
     out = {"dL_dmean2D": np.empty((P, 2), np.float32), "dL_dconic": np.empty((P, 3), np.float32),
            "dL_dopacity": np.empty(P, np.float32), "dL_dcolor": np.empty((P, 3), np.float32)}
+    if abs_sums:
+        out["abs9"] = np.empty((P, 9), np.float32)
     vals = bins["vals"] if bins["R"] > 0 else np.zeros(1, np.uint32)
     lib().orc_blend_backward(C.byref(pr), _p(bins["ranges"]), _p(vals), _p(geom["xy"]), _p(geom["conic_opacity"]),
                              _p(geom["rgb"]), _p(img["final_T"]), _p(img["n_contrib"]), _p(dL_dpix),
-                             _p(out["dL_dmean2D"]), _p(out["dL_dconic"]), _p(out["dL_dopacity"]), _p(out["dL_dcolor"]))
+                             _p(out["dL_dmean2D"]), _p(out["dL_dconic"]), _p(out["dL_dopacity"]), _p(out["dL_dcolor"]),
+                             _p(out.get("abs9")))
     return out
 
 
@@ -174,8 +179,8 @@ def render_forward(pr: OrcParams, means3D, opacities, **kw) -> dict:
 
 
 def render_backward(pr: OrcParams, fwd: dict, dL_dpix, means3D, scales=None, rotations=None, shs=None,
-                    precomp_color=False) -> dict:
-    bg = blend_backward(pr, fwd["geom"], fwd["bins"], fwd["img"], dL_dpix)
+                    precomp_color=False, abs_sums: bool = False) -> dict:
+    bg = blend_backward(pr, fwd["geom"], fwd["bins"], fwd["img"], dL_dpix, abs_sums)
     pg = preprocess_backward(pr, fwd["geom"], bg, means3D, scales, rotations, shs, precomp_color)
     pg.update(bg)
     return pg

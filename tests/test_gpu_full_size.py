@@ -127,19 +127,47 @@ def _oracle_parity(name, backward):
         return
     dL = torch.randn(3, H, W, generator=torch.Generator().manual_seed(5))
     bw = O.render_backward(pr, ref, dL.numpy(), cl["means3D"].numpy(), scales=npin["scales"], rotations=npin["rotations"],
-                           shs=npin["shs"])
+                           shs=npin["shs"], abs_sums=True)
     d = {k: torch.tensor(v).cuda() for k, v in npin.items()}
     g = rasterize_backward(st, dL.cuda(), cl["means3D"].cuda(), d["shs"], d["scales"], d["rotations"], None, False)
     torch.cuda.synchronize()
-    g_means3D, g_means2D, g_shs, _, g_op, g_scales, g_rots, _ = [None if t is None else t.cpu().numpy() for t in g]
-    grad_close(g_means3D, bw["dL_dmeans3D"], name="means3D")
-    grad_close(g_means2D[:, :2], bw["dL_dmean2D"], name="means2D")
-    grad_close(g_op[:, 0], bw["dL_dopacity"], name="opacity")
-    grad_close(g_shs, bw["dL_dshs"], name="shs")
-    grad_close(g_scales, bw["dL_dscales"], name="scales")
-    grad_close(g_rots, bw["dL_drotations"], name="rotations")
-    for t in (g_means3D, g_means2D, g_op, g_shs, g_scales, g_rots):
-        assert np.isfinite(t).all()
+    got = dict(zip(["means3D", "means2D", "shs", "col", "opacity", "scales", "rotations", "cov"],
+                   [None if t is None else t.cpu().numpy() for t in g]))
+    # (1) the blend backward (K7), element by element with NO outliers allowed.  Every one of its outputs is a sum
+    #     over up to thousands of (pixel, Gaussian) terms of mixed sign, accumulated in fp32 in an order that differs
+    #     from the oracle's (and from run to run: atomics) -- so the bar is 1e-4 relative to the gradient plus 1e-5 of
+    #     the sum of the MAGNITUDES of its terms (oracle: abs9), i.e. plain 1e-4 relative unless the sum cancels >10x
+    gb = st.ws.scratch[:P * 48].view(torch.float32).view(P, 12).cpu().numpy().astype(np.float64)
+    ref9 = np.concatenate([bw["dL_dmean2D"], bw["dL_dconic"], bw["dL_dopacity"][:, None], bw["dL_dcolor"]], 1).astype(np.float64)
+    err9 = np.abs(gb[:, :9] - ref9)
+    bound9 = 1e-4 * np.abs(ref9) + 1e-5 * bw["abs9"].astype(np.float64) + 1e-30
+    worst = float((err9 / bound9).max())
+    assert worst <= 1.0, f"blend backward: worst error / bound = {worst:.3f} at {np.unravel_index(np.argmax(err9 / bound9), err9.shape)}"
+    # (2) the per-Gaussian backward (K8 + K9) on ITS inputs: the oracle's per-Gaussian backward fed with the blend
+    #     gradients the GPU produced must give the GPU's final gradients (no accumulation-order freedom left)
+    gpu_blend = {"dL_dmean2D": gb[:, 0:2].astype(np.float32), "dL_dconic": gb[:, 2:5].astype(np.float32),
+                 "dL_dopacity": gb[:, 5].astype(np.float32), "dL_dcolor": gb[:, 6:9].astype(np.float32)}
+    pg = O.preprocess_backward(pr, ref["geom"], gpu_blend, cl["means3D"].numpy(), npin["scales"], npin["rotations"], npin["shs"])
+    grad_close(got["means3D"], pg["dL_dmeans3D"], name="means3D | gpu blend grads")
+    grad_close(got["shs"], pg["dL_dshs"], name="shs | gpu blend grads")
+    grad_close(got["scales"], pg["dL_dscales"], name="scales | gpu blend grads")
+    grad_close(got["rotations"], pg["dL_drotations"], name="rotations | gpu blend grads")
+    assert np.array_equal(got["means2D"][:, :2], gpu_blend["dL_dmean2D"]) and (got["means2D"][:, 2] == 0).all()
+    assert np.array_equal(got["opacity"][:, 0], gpu_blend["dL_dopacity"])
+    # (3) end to end against the oracle: norm-wise 1e-5 (ten times inside the 1e-4 bar), and element-wise at the
+    #     row-scaled 1e-4 bar of tests/util.py for all but a 1e-4 fraction of the elements (the ill-conditioned sums of (1))
+    pairs = [("means3D", bw["dL_dmeans3D"]), ("means2D", np.concatenate([bw["dL_dmean2D"], np.zeros((P, 1), np.float32)], 1)),
+             ("opacity", bw["dL_dopacity"][:, None]), ("shs", bw["dL_dshs"]), ("scales", bw["dL_dscales"]),
+             ("rotations", bw["dL_drotations"])]
+    for name_, r in pairs:
+        a_, r_ = got[name_].astype(np.float64).reshape(P, -1), r.astype(np.float64).reshape(P, -1)
+        assert np.isfinite(a_).all(), name_
+        rel = np.linalg.norm(a_ - r_) / np.linalg.norm(r_)
+        assert rel <= 1e-5, f"{name_}: norm-wise relative error {rel:.2e}"
+        floor = 1e-3 * np.sqrt(np.mean(r_ ** 2))
+        scale = np.maximum(np.abs(r_).max(axis=1, keepdims=True), floor)
+        frac = float((np.abs(a_ - r_) > 1e-4 * scale).mean())
+        assert frac <= 1e-4, f"{name_}: {frac:.2e} of the elements miss the row-scaled 1e-4 bar"
 
 
 @pytest.mark.parametrize("name", ["h0", "c3"])
@@ -153,56 +181,111 @@ def test_full_size_forward_vs_oracle_1080p():
     _oracle_parity("c5_1080p", backward=False)
 
 
-def test_c2_stage2_chain_vs_oracle():
-    """BASELINE.json configs[1] as a CHAIN against the oracle chain: mesh (F ~ 82 k, k = 6 -> P ~ 490 k) -> binding
-    -> sigmoid-SH colour inside preprocess + cov3D_precomp render (opacity 0.9999: alpha saturates at 0.99) ->
-    0.8 L1 + 0.2 (1 - SSIM) -> backward -> dL/dverts, dL/dscale_factor, dL/dfeatures."""
+_C2 = {}
+
+
+def _c2_oracle_chain():
+    """The C2 inputs and the oracle's chain on them (computed once per session): binding -> render (sigmoid SH in
+    preprocess, cov3D_precomp, opacity 0.9999) -> 0.8 L1 + 0.2 (1 - SSIM) -> backward -> dverts, dg, dfeatures."""
+    if _C2:
+        return _C2
     import numpy as np
     from oracle import next_rows as NR, oracle as O
-    from test_gpu_parity import assert_forward_parity
-    from util import cam_params, grad_close
-    from gpu_util import settings_for, state_numpy
-    from dmgs_b200 import GaussianRasterizer
-    from dmgs_b200.binding import bind_faces
-    from dmgs_b200.loss_utils import l1_ssim_loss
+    from util import cam_params
     m = S.mesh_bound_inputs(50_000, k=6, seed=1)
     W = H = 800
     cam = S.nerf_synthetic_camera(2, W, H)
     bg = (1.0, 1.0, 1.0)
     thin_z = m["spatial_lr_scale"] * 1e-6
     gt = torch.rand(3, H, W, generator=torch.Generator().manual_seed(11))
-    # ---- CUDA chain (autograd through the product's ops)
-    v = m["verts"].cuda().requires_grad_()
-    sf = torch.tensor([m["scale_factor"]], device="cuda", requires_grad=True)
-    feats = m["features"].cuda().requires_grad_()
-    xyz, cov6 = bind_faces(v, m["faces"].cuda(), m["bc"].cuda(), m["rad_base"], thin_z, sf, max_scale=2.0)
-    ras = GaussianRasterizer(settings_for(cam, bg), sh_activation="sigmoid", sh_layout="P3M")
-    op = m["opacities"].cuda()
-    img, radii = ras(means3D=xyz, means2D=torch.zeros_like(xyz), shs=feats, colors_precomp=None, opacities=op,
-                     scales=None, rotations=None, cov3D_precomp=cov6)
-    loss = l1_ssim_loss(img, gt.cuda(), lambda_dssim=0.2)
-    loss.backward()
-    torch.cuda.synchronize()
-    # ---- oracle chain
-    g = float((torch.tanh(sf.detach()) * 2.0).item())
+    sf = torch.tensor([m["scale_factor"]], device="cuda")
+    g = float((torch.tanh(sf) * 2.0).item())  # the fp32 value the kernels read
     ob = O.bind_forward(m["verts"].numpy(), m["faces"].numpy(), m["bc"].numpy(), m["rad_base"], thin_z, g, True)
-    assert np.array_equal(xyz.detach().cpu().numpy().view(np.uint32), ob["xyz"].view(np.uint32))
-    assert np.array_equal(cov6.detach().cpu().numpy().view(np.uint32), ob["cov6"].view(np.uint32))
     P = ob["xyz"].shape[0]
     pr = cam_params(cam, P, np.array(bg, np.float32), sh_layout=1, sh_act=1, sh_degree=3)
     ref = O.render_forward(pr, ob["xyz"], m["opacities"].numpy(), cov3D_precomp=ob["cov6"], shs=m["features"].numpy())
-    assert_forward_parity(ref, img.detach(), radii, ras.last, state_numpy(ras.last))
     l1, ssim, dl1, dssim = NR.l1_ssim(ref["img"]["color"], gt.numpy())
-    ref_loss = 0.8 * l1 + 0.2 * (1.0 - ssim)
-    assert abs(loss.item() - ref_loss) <= 1e-5
     dL = (0.8 * dl1 - 0.2 * dssim).astype(np.float32)
     bw = O.render_backward(pr, ref, dL, ob["xyz"], shs=m["features"].numpy())
-    grad_close(feats.grad.cpu().numpy().reshape(P, -1), bw["dL_dshs"].reshape(P, -1), name="features")
     ov = O.bind_backward(m["verts"].numpy(), m["faces"].numpy(), m["bc"].numpy(), m["rad_base"], thin_z, g,
                          bw["dL_dmeans3D"], bw["dL_dcov3D"], True)
-    grad_close(v.grad.cpu().numpy(), ov["dverts"], rtol=2e-4, name="dverts")
-    dsf = ov["dg"] * 2.0 * (1.0 - math.tanh(m["scale_factor"]) ** 2)
-    assert abs(sf.grad.item() - dsf) <= 2e-4 * abs(dsf) + 1e-12
+    _C2.update(m=m, cam=cam, bg=bg, thin_z=thin_z, gt=gt, g=g, ob=ob, P=P, pr=pr, ref=ref, bw=bw, ov=ov,
+               loss=0.8 * l1 + 0.2 * (1.0 - ssim),
+               dsf=ov["dg"] * 2.0 * (1.0 - math.tanh(m["scale_factor"]) ** 2))
+    return _C2
+
+
+def _c2_check(c, loss, img, radii, state, v, sf, feats):
+    import numpy as np
+    from test_gpu_parity import assert_forward_parity
+    from util import grad_close
+    from gpu_util import state_numpy
+    assert_forward_parity(c["ref"], img.detach(), radii, state, state_numpy(state))
+    assert abs(loss.item() - c["loss"]) <= 1e-5
+    P = c["P"]
+    grad_close(feats.grad.cpu().numpy().reshape(P, -1), c["bw"]["dL_dshs"].reshape(P, -1), name="features")
+    grad_close(v.grad.cpu().numpy(), c["ov"]["dverts"], rtol=2e-4, name="dverts")
+    assert abs(sf.grad.item() - c["dsf"]) <= 2e-4 * abs(c["dsf"]) + 1e-12
+    assert np.isfinite(v.grad.cpu().numpy()).all()
+
+
+def test_c2_stage2_chain_vs_oracle():
+    """BASELINE.json configs[1] as a CHAIN against the oracle chain: mesh (F ~ 82 k, k = 6 -> P ~ 490 k) -> binding
+    -> sigmoid-SH colour inside preprocess + cov3D_precomp render (opacity 0.9999: alpha saturates at 0.99) ->
+    0.8 L1 + 0.2 (1 - SSIM) -> backward -> dL/dverts, dL/dscale_factor, dL/dfeatures."""
+    import numpy as np
+    from gpu_util import settings_for
+    from dmgs_b200 import GaussianRasterizer
+    from dmgs_b200.binding import bind_faces
+    from dmgs_b200.loss_utils import l1_ssim_loss
+    c = _c2_oracle_chain()
+    m = c["m"]
+    v = m["verts"].cuda().requires_grad_()
+    sf = torch.tensor([m["scale_factor"]], device="cuda", requires_grad=True)
+    feats = m["features"].cuda().requires_grad_()
+    xyz, cov6 = bind_faces(v, m["faces"].cuda(), m["bc"].cuda(), m["rad_base"], c["thin_z"], sf, max_scale=2.0)
+    assert np.array_equal(xyz.detach().cpu().numpy().view(np.uint32), c["ob"]["xyz"].view(np.uint32))
+    assert np.array_equal(cov6.detach().cpu().numpy().view(np.uint32), c["ob"]["cov6"].view(np.uint32))
+    ras = GaussianRasterizer(settings_for(c["cam"], c["bg"]), sh_activation="sigmoid", sh_layout="P3M")
+    img, radii = ras(means3D=xyz, means2D=torch.zeros_like(xyz), shs=feats, colors_precomp=None,
+                     opacities=m["opacities"].cuda(), scales=None, rotations=None, cov3D_precomp=cov6)
+    loss = l1_ssim_loss(img, c["gt"].cuda(), lambda_dssim=0.2)
+    loss.backward()
+    torch.cuda.synchronize()
+    _c2_check(c, loss, img, radii, ras.last, v, sf, feats)
+
+
+def test_c2_fused_bind_preprocess_vs_oracle():
+    """The same chain with the binding fused INTO the per-Gaussian kernels (dmgs_preprocess_forward_bound /
+    dmgs_preprocess_backward_bound via binding.rasterize_mesh): no xyz / cov3D_precomp / dL/dxyz / dL/dcov tensors.
+    Forward bit-exact against the oracle chain, gradients (the reference's truncated binding gradient) within the bar."""
+    import numpy as np
+    from gpu_util import settings_for
+    from dmgs_b200.binding import MeshRasterizer, rasterize_mesh
+    from dmgs_b200.loss_utils import l1_ssim_loss
+    c = _c2_oracle_chain()
+    m = c["m"]
+    v = m["verts"].cuda().requires_grad_()
+    sf = torch.tensor([m["scale_factor"]], device="cuda", requires_grad=True)
+    feats = m["features"].cuda().requires_grad_()
+    holder = MeshRasterizer()
+    m2d = torch.zeros(c["P"], 3, device="cuda", requires_grad=True)
+    img, radii, xyz = rasterize_mesh(settings_for(c["cam"], c["bg"]), v, m["faces"].cuda(), m["bc"].cuda(), m["rad_base"],
+                                     c["thin_z"], m["opacities"].cuda(), features=feats, scale_factor=sf, max_scale=2.0,
+                                     means2D=m2d, return_xyz=True, holder=holder)
+    assert np.array_equal(xyz.cpu().numpy().view(np.uint32), c["ob"]["xyz"].view(np.uint32))
+    loss = l1_ssim_loss(img, c["gt"].cuda(), lambda_dssim=0.2)
+    loss.backward()
+    torch.cuda.synchronize()
+    _c2_check(c, loss, img, radii, holder.last, v, sf, feats)
+    assert m2d.grad.shape == (c["P"], 3) and torch.all(m2d.grad[:, 2] == 0) and m2d.grad.abs().sum() > 0
+    # the COLMAP variant (no scale factor, mlp_flex_colmap.py:500-504) and precomputed colours run too
+    col = torch.rand(c["P"], 3, device="cuda", requires_grad=True)
+    v2 = m["verts"].cuda().requires_grad_()
+    img2, radii2 = rasterize_mesh(settings_for(c["cam"], c["bg"]), v2, m["faces"].cuda(), m["bc"].cuda(), m["rad_base"],
+                                  c["thin_z"], m["opacities"].cuda(), colors_precomp=col)
+    img2.square().mean().backward()
+    assert torch.isfinite(v2.grad).all() and v2.grad.abs().sum() > 0 and col.grad.abs().sum() > 0
 
 
 def test_arith_divergence_script_small():
