@@ -20,7 +20,7 @@
 
 namespace dmgs {
 
-__global__ void __launch_bounds__(BLK)
+__global__ void __launch_bounds__(BLK, 4)
 blend_fwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ ranges,
                  const uint32_t *__restrict__ gidx, const float4 *__restrict__ rec, const float4 *__restrict__ rgb4,
                  float *__restrict__ out_color, float *__restrict__ final_T, uint32_t *__restrict__ n_contrib)
@@ -28,6 +28,7 @@ blend_fwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
     __shared__ float4 s_ra[BLK];   // x, y, conA, conB
     __shared__ float4 s_rb[BLK];   // conC, opacity, cut, -
     __shared__ float4 s_rgb[BLK];
+    __shared__ __align__(16) unsigned char s_cw[(BLK / 32) * CW_WARP_BYTES];  // per-warp compacted survivors
 
     const int lane = threadIdx.x & 31;
     int px0, py0;
@@ -35,6 +36,7 @@ blend_fwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
     const int px = px0 + (lane & 7), py = py0 + (lane >> 3);
     const bool inside = px < a.W && py < a.H;
     const float pxf = (float)px, pyf = (float)py;
+    const f32x2 npx = pk2(-pxf, -pxf), npy = pk2(-pyf, -pyf);
     const float rx0 = (float)px0, rx1 = (float)(px0 + 7), ry0 = (float)py0, ry1 = (float)(py0 + 3);
     const uint2 rng = ranges[blockIdx.y * a.gx + blockIdx.x];
     const int total = (int)(rng.y - rng.x);
@@ -44,6 +46,8 @@ blend_fwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
     float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f;
     uint32_t last = 0;
     const uint32_t a_ra = smem_addr(s_ra), a_rb = smem_addr(s_rb), a_rgb = smem_addr(s_rgb);
+    const uint32_t a_cw = smem_addr(s_cw) + (uint32_t)(threadIdx.x >> 5) * CW_WARP_BYTES;
+    const uint32_t lt_mask = (1u << lane) - 1u;
 
     for (int r = 0; r < rounds; ++r) {
         if (__syncthreads_count(done) == BLK) break;
@@ -58,42 +62,69 @@ blend_fwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
         const int nb = min(BLK, total - r * BLK);
         if (__all_sync(0xffffffffu, done)) continue;  // this warp's pixels are finished; keep staging
         for (int s0 = 0; s0 < nb; s0 += 32) {
-            // lane <-> entry: which of these 32 entries can touch the warp's rectangle?
+            // lane <-> entry: which of these 32 entries can touch the warp's rectangle?  Survivors are compacted,
+            // in list order, into the warp's structure-of-arrays buffer.
             const int e = s0 + lane;
             bool keep = false;
+            float4 ra, rb;
             if (e < nb) {
-                const float4 ra = lds128(a_ra + 16u * e), rb = lds128(a_rb + 16u * e);
+                ra = lds128(a_ra + 16u * e);
+                rb = lds128(a_rb + 16u * e);
                 keep = !cull_rect(ra.x, ra.y, ra.z, ra.w, rb.x, rb.z, rx0, rx1, ry0, ry1);
             }
-            uint32_t m = __ballot_sync(0xffffffffu, keep);
-            // lane <-> pixel over the surviving entries, in list order
-            while (m) {
-                const int j = s0 + __ffs(m) - 1;
-                m &= m - 1;
-                if (!done) {
-                    const float4 ra = lds128(a_ra + 16u * j), rb = lds128(a_rb + 16u * j);
-                    const float dx = ra.x - pxf, dy = ra.y - pyf;
-                    // rounding order of upstream's -0.5f * (A dx dx + C dy dy) - B dx dy under nvcc's contraction
-                    const float q = fma_(dx, ra.z * dx, (rb.x * dy) * dy);
-                    const float power = fma_(q, -0.5f, -((ra.w * dx) * dy));
-                    if (power <= 0.0f) {
-                        const float alpha = fminf(0.99f, rb.y * dmgs_exp(power));
-                        if (alpha >= 1.0f / 255.0f) {
-                            const float test_T = T * (1.0f - alpha);
-                            if (test_T < 0.0001f) {
-                                done = true;
-                            } else {
-                                const float4 c = lds128(a_rgb + 16u * j);
-                                C0 = fma_(c.x * alpha, T, C0);
-                                C1 = fma_(c.y * alpha, T, C1);
-                                C2 = fma_(c.z * alpha, T, C2);
-                                T = test_T;
-                                last = (uint32_t)(r * BLK + j + 1);
-                            }
-                        }
+            const uint32_t m = __ballot_sync(0xffffffffu, keep);
+            if (!m) continue;
+            const int n = __popc(m);
+            if (keep) {
+                const uint32_t w = a_cw + 4u * (uint32_t)__popc(m & lt_mask);
+                sts32(w, ra.x); sts32(w + CW_STRIDE, ra.y); sts32(w + 2 * CW_STRIDE, ra.z); sts32(w + 3 * CW_STRIDE, -ra.w);
+                sts32(w + 4 * CW_STRIDE, rb.x); sts32(w + 5 * CW_STRIDE, rb.y); sts32u(w + 6 * CW_STRIDE, (uint32_t)e);
+            }
+            if (lane == 0 && (n & 1)) {  // sentinel pads an odd count: opacity 0 -> alpha 0 -> never a contributor
+                const uint32_t w = a_cw + 4u * (uint32_t)n;
+                sts32(w, 0.0f); sts32(w + CW_STRIDE, 0.0f); sts32(w + 2 * CW_STRIDE, 0.0f); sts32(w + 3 * CW_STRIDE, 0.0f);
+                sts32(w + 4 * CW_STRIDE, 0.0f); sts32(w + 5 * CW_STRIDE, 0.0f); sts32u(w + 6 * CW_STRIDE, 0u);
+            }
+            __syncwarp();
+            // lane <-> pixel over the survivors, two per iteration (packed FP32), in list order
+            for (int t = 0; t < n; t += 2) {
+                const uint32_t cw = a_cw + 4u * (uint32_t)t;
+                f32x2 power, alpha, dx, dy, G;
+                alpha_pair(cw, npx, npy, power, alpha, dx, dy, G);
+                float p0, p1, a0, a1;
+                upk2(power, p0, p1);
+                upk2(alpha, a0, a1);
+                const bool h0 = p0 <= 0.0f && a0 >= 1.0f / 255.0f, h1 = p1 <= 0.0f && a1 >= 1.0f / 255.0f;
+                if (!done && h0) {
+                    const float test_T = T * (1.0f - a0);
+                    if (test_T < 0.0001f) {
+                        done = true;
+                    } else {
+                        const uint32_t j = lds32(cw + 6 * CW_STRIDE);
+                        const float4 c = lds128(a_rgb + 16u * j);
+                        C0 = fma_(c.x * a0, T, C0);
+                        C1 = fma_(c.y * a0, T, C1);
+                        C2 = fma_(c.z * a0, T, C2);
+                        T = test_T;
+                        last = (uint32_t)(r * BLK) + j + 1u;
+                    }
+                }
+                if (!done && h1) {
+                    const float test_T = T * (1.0f - a1);
+                    if (test_T < 0.0001f) {
+                        done = true;
+                    } else {
+                        const uint32_t j = lds32(cw + 6 * CW_STRIDE + 4u);
+                        const float4 c = lds128(a_rgb + 16u * j);
+                        C0 = fma_(c.x * a1, T, C0);
+                        C1 = fma_(c.y * a1, T, C1);
+                        C2 = fma_(c.z * a1, T, C2);
+                        T = test_T;
+                        last = (uint32_t)(r * BLK) + j + 1u;
                     }
                 }
             }
+            __syncwarp();  // the buffer is rewritten by the next group
             if (__all_sync(0xffffffffu, done)) break;
         }
     }

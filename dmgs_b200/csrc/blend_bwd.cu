@@ -57,6 +57,7 @@ blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
     __shared__ float4 s_rgb[BLK];
     __shared__ float4 s_acc[BLK * 3];  // per staged entry: the 9 (+3 pad) gradient sums of this tile
     __shared__ uint32_t s_id[BLK];
+    __shared__ __align__(16) unsigned char s_cw[(BLK / 32) * CW_WARP_BYTES];  // per-warp compacted survivors
     __shared__ int s_max;
 
     const int lane = threadIdx.x & 31;
@@ -65,6 +66,7 @@ blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
     const int px = px0 + (lane & 7), py = py0 + (lane >> 3);
     const bool inside = px < a.W && py < a.H;
     const float pxf = (float)px, pyf = (float)py;
+    const f32x2 npx = pk2(-pxf, -pxf), npy = pk2(-pyf, -pyf);
     const float rx0 = (float)px0, rx1 = (float)(px0 + 7), ry0 = (float)py0, ry1 = (float)(py0 + 3);
     const uint2 rng = ranges[blockIdx.y * a.gx + blockIdx.x];
     const size_t pix = (size_t)py * a.W + px, HW = (size_t)a.H * a.W;
@@ -79,6 +81,8 @@ blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
     const bool owner = slot >= 0 && !(lane & 1);
     const uint32_t a_ra = smem_addr(s_ra), a_rb = smem_addr(s_rb), a_rgb = smem_addr(s_rgb);
     const uint32_t a_acc = smem_addr(s_acc) + 4u * (uint32_t)(slot < 0 ? 0 : slot);
+    const uint32_t a_cw = smem_addr(s_cw) + (uint32_t)(threadIdx.x >> 5) * CW_WARP_BYTES;
+    const uint32_t lt_mask = (1u << lane) - 1u;
 
     // only the first max(n_contrib) entries of the list matter: per tile for staging, per warp for work
     if (threadIdx.x == 0) s_max = 0;
@@ -106,60 +110,78 @@ blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
         __syncthreads();
         if (r * BLK < wmax) {  // else nothing in this round is a contributor for this warp
             const int nb = min(BLK, min(count, wmax) - r * BLK);
+            const int lim = last - r * BLK;  // staged entries j < lim lie before this pixel's last contributor
             for (int s0 = ((nb - 1) / 32) * 32; s0 >= 0; s0 -= 32) {
                 const int e = s0 + lane;
                 bool keep = false;
+                float4 ra, rb;
                 if (e < nb) {
-                    const float4 ra = lds128(a_ra + 16u * e), rb = lds128(a_rb + 16u * e);
+                    ra = lds128(a_ra + 16u * e);
+                    rb = lds128(a_rb + 16u * e);
                     keep = !cull_rect(ra.x, ra.y, ra.z, ra.w, rb.x, rb.z, rx0, rx1, ry0, ry1);
                 }
-                uint32_t m = __ballot_sync(0xffffffffu, keep);
-                while (m) {
-                    const int jb = 31 - __clz(m);  // back to front
-                    m &= ~(1u << jb);
-                    const int j = s0 + jb;
-                    const int pos = r * BLK + j;  // 0-based list position
-                    // per-pixel work stops at cg = G * dL/dalpha and w = alpha * T; lanes that do not
-                    // contribute keep both at zero, so the products below need no other masking
-                    float cg = 0.0f, w = 0.0f;
-                    bool hit = false;
-                    const float4 ra = lds128(a_ra + 16u * j), rb = lds128(a_rb + 16u * j);
-                    const float dx = ra.x - pxf, dy = ra.y - pyf;
-                    if (pos < last) {
-                        // same power / exp / alpha arithmetic as the forward (explicit _rn operations, immune
-                        // to contraction): the contributor set is identical
-                        const float q = fma_(dx, __fmul_rn(ra.z, dx), __fmul_rn(__fmul_rn(rb.x, dy), dy));
-                        const float power = fma_(q, -0.5f, -__fmul_rn(__fmul_rn(ra.w, dx), dy));
-                        if (power <= 0.0f) {
-                            const float G = dmgs_exp(power);
-                            const float alpha = fminf(0.99f, __fmul_rn(rb.y, G));
-                            if (alpha >= 1.0f / 255.0f) {
-                                hit = true;
-                                // one refined reciprocal replaces two IEEE divisions by (1 - alpha) (no FCHK /
-                                // slow-path branches; operands are in [0.01, 1] so no special cases exist)
-                                const float oma = 1.0f - alpha;
-                                const float inv = rcp_nr(oma);
-                                const float t0 = T * inv;  // T / (1 - alpha), residual-corrected: the error must
-                                T = fma_(fma_(-t0, oma, T), inv, t0);  // not accumulate along the list
-                                w = alpha * T;
-                                const float4 c = lds128(a_rgb + 16u * j);
-                                // colour behind this entry enters only through its dot product with dL/dpixel
-                                const float cd = fma_(c.z, dp2, fma_(c.y, dp1, c.x * dp0));
-                                behind = fma_(last_alpha, last_cd, (1.0f - last_alpha) * behind);
-                                last_cd = cd;
-                                last_alpha = alpha;
-                                cg = G * fma_(bgT, inv, (cd - behind) * T);
-                            }
-                        }
-                    }
-                    if (!__any_sync(0xffffffffu, hit)) continue;
-                    // moments of cg about the Gaussian's centre (the flush below turns the tile's sums into
-                    // dL/dmean2D and dL/dconic) and the colour gradient
-                    const float cgx = cg * dx, cgy = cg * dy;
-                    float v[9] = {cgx, cgy, cgx * dx, cgx * dy, cgy * dy, cg, w * dp0, w * dp1, w * dp2};
-                    tr_reduce<9, 16>(v, lane);
-                    if (owner) reds_add(a_acc + 48u * j, v[0]);
+                const uint32_t m = __ballot_sync(0xffffffffu, keep);
+                if (!m) continue;
+                const int n = __popc(m);
+                if (keep) {  // compact the survivors in list order (see blend.cu)
+                    const uint32_t w = a_cw + 4u * (uint32_t)__popc(m & lt_mask);
+                    sts32(w, ra.x); sts32(w + CW_STRIDE, ra.y); sts32(w + 2 * CW_STRIDE, ra.z); sts32(w + 3 * CW_STRIDE, -ra.w);
+                    sts32(w + 4 * CW_STRIDE, rb.x); sts32(w + 5 * CW_STRIDE, rb.y); sts32u(w + 6 * CW_STRIDE, (uint32_t)e);
                 }
+                if (lane == 0 && (n & 1)) {  // sentinel: opacity 0 -> alpha 0 -> never a contributor
+                    const uint32_t w = a_cw + 4u * (uint32_t)n;
+                    sts32(w, 0.0f); sts32(w + CW_STRIDE, 0.0f); sts32(w + 2 * CW_STRIDE, 0.0f); sts32(w + 3 * CW_STRIDE, 0.0f);
+                    sts32(w + 4 * CW_STRIDE, 0.0f); sts32(w + 5 * CW_STRIDE, 0.0f); sts32u(w + 6 * CW_STRIDE, 0u);
+                }
+                __syncwarp();
+                // back to front over the survivors, two per iteration: the alpha arithmetic (the forward's, so the
+                // contributor set is identical) runs packed for both, the recurrences and reductions one by one
+                for (int t = (n - 1) & ~1; t >= 0; t -= 2) {
+                    const uint32_t cw = a_cw + 4u * (uint32_t)t;
+                    f32x2 power2, alpha2, dx2, dy2, G2;
+                    alpha_pair(cw, npx, npy, power2, alpha2, dx2, dy2, G2);
+                    float pw[2], al[2], dxs[2], dys[2], Gs[2];
+                    upk2(power2, pw[0], pw[1]);
+                    upk2(alpha2, al[0], al[1]);
+                    upk2(dx2, dxs[0], dxs[1]);
+                    upk2(dy2, dys[0], dys[1]);
+                    upk2(G2, Gs[0], Gs[1]);
+                    const f32x2 jj = lds64(cw + 6 * CW_STRIDE);
+                    const int js[2] = {(int)(uint32_t)(jj & 0xffffffffull), (int)(uint32_t)(jj >> 32)};
+#pragma unroll
+                    for (int h = 1; h >= 0; --h) {
+                        const int j = js[h];
+                        const float alpha = al[h], dx = dxs[h], dy = dys[h];
+                        // per-pixel work stops at cg = G * dL/dalpha and w = alpha * T; lanes that do not
+                        // contribute keep both at zero, so the products below need no other masking
+                        float cg = 0.0f, w = 0.0f;
+                        const bool hit = j < lim && pw[h] <= 0.0f && alpha >= 1.0f / 255.0f;
+                        if (hit) {
+                            // one refined reciprocal replaces two IEEE divisions by (1 - alpha) (no FCHK /
+                            // slow-path branches; operands are in [0.01, 1] so no special cases exist)
+                            const float oma = 1.0f - alpha;
+                            const float inv = rcp_nr(oma);
+                            const float t0 = T * inv;  // T / (1 - alpha), residual-corrected: the error must
+                            T = fma_(fma_(-t0, oma, T), inv, t0);  // not accumulate along the list
+                            w = alpha * T;
+                            const float4 c = lds128(a_rgb + 16u * j);
+                            // colour behind this entry enters only through its dot product with dL/dpixel
+                            const float cd = fma_(c.z, dp2, fma_(c.y, dp1, c.x * dp0));
+                            behind = fma_(last_alpha, last_cd, (1.0f - last_alpha) * behind);
+                            last_cd = cd;
+                            last_alpha = alpha;
+                            cg = Gs[h] * fma_(bgT, inv, (cd - behind) * T);
+                        }
+                        if (!__any_sync(0xffffffffu, hit)) continue;
+                        // moments of cg about the Gaussian's centre (the flush below turns the tile's sums into
+                        // dL/dmean2D and dL/dconic) and the colour gradient
+                        const float cgx = cg * dx, cgy = cg * dy;
+                        float v[9] = {cgx, cgy, cgx * dx, cgx * dy, cgy * dy, cg, w * dp0, w * dp1, w * dp2};
+                        tr_reduce<9, 16>(v, lane);
+                        if (owner) reds_add(a_acc + 48u * j, v[0]);
+                    }
+                }
+                __syncwarp();  // the buffer is rewritten by the next group
             }
         }
         __syncthreads();

@@ -7,7 +7,7 @@ namespace dmgs {
 
 constexpr int BLK = 256;
 #ifndef BWD_MIN_BLOCKS
-#define BWD_MIN_BLOCKS 5
+#define BWD_MIN_BLOCKS 4
 #endif
 
 struct BlendArgs {
@@ -50,6 +50,99 @@ __device__ __forceinline__ float rcp_nr(float x)
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return fma_(r, fma_(-x, r, 1.0f), r);
+}
+
+// ---- packed FP32 (sm_100: FFMA2 / FMUL2 / FADD2, two IEEE round-to-nearest results per instruction).  The blend
+// kernels are bound by instruction ISSUE, not by the FP32 pipes (ncu: issue 80 %, fma pipe 40 %), so evaluating two
+// list entries per instruction cuts the time.  Element-wise the results are those of the scalar operations, which
+// keeps every forward decision bit-identical.  NOTE: never write mul2 followed by add2 where the contract wants two
+// roundings -- ptxas 12.9 contracts that pair into FFMA2 even with -fmad=false; use fma2 (and say so in the contract).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
+{
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 lds64(uint32_t a)
+{
+    f32x2 v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts32u(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// Per-warp compacted survivor list of one 32-entry group, structure of arrays so that ONE 8-byte shared load
+// fetches the same field of two consecutive survivors: x, y, A, -B, C, opacity, staged index.  34 slots: up to 32
+// survivors + a sentinel (opacity 0: alpha = 0 fails the 1/255 test) that pads an odd count to a pair.
+constexpr int CW_SLOTS = 34, CW_FIELDS = 7;
+constexpr uint32_t CW_STRIDE = CW_SLOTS * 4u;             // bytes between two fields
+constexpr uint32_t CW_WARP_BYTES = CW_FIELDS * CW_STRIDE;  // 952 B per warp
+
+// alpha of two list entries for one pixel, in the arithmetic contract, element-wise:
+//   dx = x - px, dy = y - py;  q = fma(dx, A dx, (C dy) dy);  power = fma(q, -0.5, (-B dx) dy)
+//   G = dmgs_exp(power) (for power <= 0 only max(power, -80) of its clamp can act);  alpha = min(0.99, opacity G)
+// npx, npy: (-px, -px), (-py, -py).  Returns power and alpha pairs (alpha meaningless where power > 0).
+__device__ __forceinline__ void alpha_pair(uint32_t cw, f32x2 npx, f32x2 npy, f32x2 &power, f32x2 &alpha, f32x2 &dxo, f32x2 &dyo,
+                                           f32x2 &Go)
+{
+    const f32x2 X = lds64(cw), Y = lds64(cw + CW_STRIDE), A = lds64(cw + 2 * CW_STRIDE), NB = lds64(cw + 3 * CW_STRIDE);
+    const f32x2 Cc = lds64(cw + 4 * CW_STRIDE), OP = lds64(cw + 5 * CW_STRIDE);
+    const f32x2 dx = add2(X, npx), dy = add2(Y, npy);
+    const f32x2 t1 = mul2(A, dx);
+    const f32x2 t2 = mul2(mul2(Cc, dy), dy);
+    const f32x2 t3 = mul2(mul2(NB, dx), dy);
+    const f32x2 q = fma2(dx, t1, t2);
+    power = fma2(q, pk2(-0.5f, -0.5f), t3);
+    float p0, p1;
+    upk2(power, p0, p1);
+    const f32x2 xc = pk2(fmaxf(p0, -80.0f), fmaxf(p1, -80.0f));
+    const f32x2 r = fma2(xc, pk2(1.44269502162933349609375f, 1.44269502162933349609375f), pk2(12582912.0f, 12582912.0f));
+    const f32x2 jf = add2(r, pk2(-12582912.0f, -12582912.0f));
+    f32x2 f = fma2(jf, pk2(-0.693145751953125f, -0.693145751953125f), xc);
+    f = fma2(jf, pk2(-1.42860682030941723212e-6f, -1.42860682030941723212e-6f), f);
+    f32x2 p = fma2(pk2(0x1.6d8360p-10f, 0x1.6d8360p-10f), f, pk2(0x1.127dd8p-7f, 0x1.127dd8p-7f));
+    p = fma2(p, f, pk2(0x1.55549ep-5f, 0x1.55549ep-5f));
+    p = fma2(p, f, pk2(0x1.5553e8p-3f, 0x1.5553e8p-3f));
+    p = fma2(p, f, pk2(0.5f, 0.5f));
+    p = fma2(p, f, pk2(1.0f, 1.0f));
+    p = fma2(p, f, pk2(1.0f, 1.0f));
+    float r0, r1, e0, e1;
+    upk2(r, r0, r1);
+    upk2(p, e0, e1);
+    // exponent insert: bits(p) + (j << 23), j = bits(r) - 0x4B400000 (whose low 23 bits are zero: the shift drops it)
+    e0 = __int_as_float(__float_as_int(e0) + (__float_as_int(r0) << 23));
+    e1 = __int_as_float(__float_as_int(e1) + (__float_as_int(r1) << 23));
+    Go = pk2(e0, e1);
+    const f32x2 a = mul2(OP, Go);
+    float a0, a1;
+    upk2(a, a0, a1);
+    alpha = pk2(fminf(0.99f, a0), fminf(0.99f, a1));
+    dxo = dx;
+    dyo = dy;
 }
 
 // exact minimum over the pixel rectangle [x0,x1]x[y0,y1] of q(d) = A dx^2 + 2 B dx dy + C dy^2,

@@ -167,8 +167,10 @@ __device__ __forceinline__ float dmgs_exp(float x)
 {
     // explicit _rn operations: never contracted, whatever -fmad says for the translation unit
     x = fminf(fmaxf(x, -80.0f), 80.0f);
-    const float t = __fmul_rn(x, 1.44269502162933349609375f);
-    const float r = __fadd_rn(t, 12582912.0f);
+    // round(x * log2 e) by the magic-number trick, the product and the add FUSED: the packed-FP32 blend kernels
+    // evaluate the same sequence with fma.rn.f32x2 (a separate mul.rn.f32x2 + add.rn.f32x2 pair is contracted by
+    // ptxas 12.9 even under -fmad=false, so the contract makes the fusion explicit)
+    const float r = fma_(x, 1.44269502162933349609375f, 12582912.0f);
     const float jf = __fadd_rn(r, -12582912.0f);
     const int j = __float_as_int(r) - 0x4B400000;
     float f = fma_(jf, -0.693145751953125f, x);
