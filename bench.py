@@ -404,8 +404,9 @@ def run_ours(args):
         finally:
             dmgs_b200.configure(async_binning=not args.sync_binning)
 
-    value_dropin = time_dropin(False) if world == 1 else None          # default settings: upstream's host read-back
-    value_dropin_syncfree = time_dropin(True) if world == 1 else None  # configure(async_binning=True)
+    full = not args.quick  # --quick (kernel-variant experiments): `value` and the stage times only
+    value_dropin = time_dropin(False) if world == 1 and full else None          # default settings: upstream's host read-back
+    value_dropin_syncfree = time_dropin(True) if world == 1 and full else None  # configure(async_binning=True)
 
     # ---- end-to-end with HOST inputs (rank-local; max over ranks).  Every step copies all inputs from
     # pinned host memory (double-buffered on a copy stream, so the copy of step i+1 overlaps the kernels
@@ -488,8 +489,8 @@ def run_ours(args):
             dt = float(tm.item())
         return (views_per_rank * world * Ke) / dt
 
-    e2e_module = time_e2e(e2e_step_module)
-    e2e_training = time_e2e(e2e_step_training)
+    e2e_module = time_e2e(e2e_step_module) if full else None
+    e2e_training = time_e2e(e2e_step_training) if full else None
     h2d = staged.bytes_per_step
 
     if rank != 0:
@@ -552,7 +553,7 @@ def run_ours(args):
         roofline = hbm_roof(dom)
     hbm_dom = max(["preprocess_bwd"], key=lambda k: stage_ms.get(k, 0.0))
     cb = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and full:
         cb, _ = cpu_baseline(args.workload, 3)
     wl = {"h0": "H0", "c1": "C1", "c3": "C3", "c4": "C4"}[args.workload]
     line = {
@@ -659,6 +660,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("DMGS_BENCH_WORKLOAD", "h0"), choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="experiments: skip the drop-in, end-to-end and CPU legs "
+                    "(the line then carries nulls there and is NOT a bench result)")
     ap.add_argument("--sync-binning", action="store_true",
                     help="read the instance count back every frame (upstream behaviour) instead of sync-free binning")
     args = ap.parse_args()

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdmgs_raster.so")
+# DMGS_RASTER_LIB: another build of the same library (kernel-variant experiments, scripts/variants.sh)
+LIB_PATH = os.environ.get("DMGS_RASTER_LIB") or os.path.join(_HERE, "libdmgs_raster.so")
 
 
 class DmgsParams(C.Structure):

@@ -52,30 +52,36 @@ blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
                  const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
                  const float *__restrict__ dL_dpix, float *__restrict__ grad_blend)
 {
-    __shared__ float4 s_ra[BLK];
-    __shared__ float4 s_rb[BLK];
-    __shared__ float4 s_rgb[BLK];
-    __shared__ float4 s_acc[BLK * 3];  // per staged entry: the 9 (+3 pad) gradient sums of this tile
-    __shared__ uint32_t s_id[BLK];
+    __shared__ float4 s_ra[ROUND];
+    __shared__ float4 s_rb[ROUND];
+    __shared__ float4 s_rgb[ROUND];
+    __shared__ float4 s_acc[ROUND * 3];  // per staged entry: the 9 (+3 pad) gradient sums of this tile
+    __shared__ uint32_t s_id[ROUND];
     __shared__ __align__(16) unsigned char s_cw[(BLK / 32) * CW_WARP_BYTES];  // per-warp compacted survivors
     __shared__ int s_max;
 
     const int lane = threadIdx.x & 31;
     int px0, py0;
     warp_rect(px0, py0);
-    const int px = px0 + (lane & 7), py = py0 + (lane >> 3);
-    const bool inside = px < a.W && py < a.H;
-    const float pxf = (float)px, pyf = (float)py;
-    const f32x2 npx = pk2(-pxf, -pxf), npy = pk2(-pyf, -pyf);
-    const float rx0 = (float)px0, rx1 = (float)(px0 + 7), ry0 = (float)py0, ry1 = (float)(py0 + 3);
+    const int px = px0 + (lane & 7), pya = py0 + (lane >> 3), pyb = pya + 4;
+    const bool in_a = px < a.W && pya < a.H, in_b = px < a.W && pyb < a.H;
+    const float pxf = (float)px;
+    const f32x2 npx = pk2(-pxf, -pxf), npy = pk2(-(float)pya, -(float)pyb);
+    const float rx0 = (float)px0, rx1 = (float)(px0 + 7), ry0 = (float)py0, ry1 = (float)(py0 + 7);
     const uint2 rng = ranges[blockIdx.y * a.gx + blockIdx.x];
-    const size_t pix = (size_t)py * a.W + px, HW = (size_t)a.H * a.W;
+    const size_t pix_a = (size_t)pya * a.W + px, pix_b = (size_t)pyb * a.W + px, HW = (size_t)a.H * a.W;
 
-    const float T_final = inside ? final_T[pix] : 0.0f;
-    const int last = inside ? (int)n_contrib[pix] : 0;
-    float dp0 = 0, dp1 = 0, dp2 = 0;
-    if (inside) { dp0 = dL_dpix[pix]; dp1 = dL_dpix[HW + pix]; dp2 = dL_dpix[2 * HW + pix]; }
-    const float bgT = -T_final * dot3(a.bg[0], dp0, a.bg[1], dp1, a.bg[2], dp2);
+    // per pixel: T (transmittance in front of the entry being visited), `behind` = (colour blended behind that
+    // entry) . dL/dpixel, normalised by the transmittance behind it, and the background's share bgT
+    float Ta = in_a ? final_T[pix_a] : 0.0f, Tb = in_b ? final_T[pix_b] : 0.0f;
+    const int last_a = in_a ? (int)n_contrib[pix_a] : 0, last_b = in_b ? (int)n_contrib[pix_b] : 0;
+    float da0 = 0, da1 = 0, da2 = 0, db0 = 0, db1 = 0, db2 = 0;
+    if (in_a) { da0 = dL_dpix[pix_a]; da1 = dL_dpix[HW + pix_a]; da2 = dL_dpix[2 * HW + pix_a]; }
+    if (in_b) { db0 = dL_dpix[pix_b]; db1 = dL_dpix[HW + pix_b]; db2 = dL_dpix[2 * HW + pix_b]; }
+    const float bgTa = -Ta * dot3(a.bg[0], da0, a.bg[1], da1, a.bg[2], da2);
+    const float bgTb = -Tb * dot3(a.bg[0], db0, a.bg[1], db1, a.bg[2], db2);
+    float bha = 0.0f, bhb = 0.0f;
+    const f32x2 dp0 = pk2(da0, db0), dp1 = pk2(da1, db1), dp2 = pk2(da2, db2);
     const float ddelx_dx = 0.5f * (float)a.W, ddely_dy = 0.5f * (float)a.H;
     const int slot = tr_slot9(lane);
     const bool owner = slot >= 0 && !(lane & 1);
@@ -86,31 +92,32 @@ blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
 
     // only the first max(n_contrib) entries of the list matter: per tile for staging, per warp for work
     if (threadIdx.x == 0) s_max = 0;
-    s_acc[threadIdx.x] = make_float4(0, 0, 0, 0);
-    s_acc[BLK + threadIdx.x] = make_float4(0, 0, 0, 0);
-    s_acc[2 * BLK + threadIdx.x] = make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int i = threadIdx.x; i < ROUND * 3; i += BLK) s_acc[i] = make_float4(0, 0, 0, 0);
     __syncthreads();
-    const int wmax = __reduce_max_sync(0xffffffffu, last);
+    const int wmax = __reduce_max_sync(0xffffffffu, max(last_a, last_b));
     if (lane == 0) atomicMax(&s_max, wmax);
     __syncthreads();
     const int count = s_max;
     if (count == 0) return;
 
-    float T = T_final, behind = 0, last_cd = 0, last_alpha = 0;
-    const int rounds = (count + BLK - 1) / BLK;
+    const int rounds = (count + ROUND - 1) / ROUND;
     for (int r = rounds - 1; r >= 0; --r) {
-        const int idx = r * BLK + threadIdx.x;
-        if (idx < count) {
-            const uint32_t g = gidx[rng.x + idx];
-            s_id[threadIdx.x] = g;
-            s_ra[threadIdx.x] = rec[2 * (size_t)g];
-            s_rb[threadIdx.x] = rec[2 * (size_t)g + 1];
-            s_rgb[threadIdx.x] = rgb4[g];
+#pragma unroll
+        for (int h = 0; h < ROUND / BLK; ++h) {
+            const int st = h * BLK + threadIdx.x, idx = r * ROUND + st;
+            if (idx < count) {
+                const uint32_t g = gidx[rng.x + idx];
+                s_id[st] = g;
+                s_ra[st] = rec[2 * (size_t)g];
+                s_rb[st] = rec[2 * (size_t)g + 1];
+                s_rgb[st] = rgb4[g];
+            }
         }
         __syncthreads();
-        if (r * BLK < wmax) {  // else nothing in this round is a contributor for this warp
-            const int nb = min(BLK, min(count, wmax) - r * BLK);
-            const int lim = last - r * BLK;  // staged entries j < lim lie before this pixel's last contributor
+        if (r * ROUND < wmax) {  // else nothing in this round is a contributor for this warp
+            const int nb = min(ROUND, min(count, wmax) - r * ROUND);
+            const int lim_a = last_a - r * ROUND, lim_b = last_b - r * ROUND;  // staged j < lim: before the last contributor
             for (int s0 = ((nb - 1) / 32) * 32; s0 >= 0; s0 -= 32) {
                 const int e = s0 + lane;
                 bool keep = false;
@@ -123,89 +130,94 @@ blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
                 const uint32_t m = __ballot_sync(0xffffffffu, keep);
                 if (!m) continue;
                 const int n = __popc(m);
-                if (keep) {  // compact the survivors in list order (see blend.cu)
-                    const uint32_t w = a_cw + 4u * (uint32_t)__popc(m & lt_mask);
-                    sts32(w, ra.x); sts32(w + CW_STRIDE, ra.y); sts32(w + 2 * CW_STRIDE, ra.z); sts32(w + 3 * CW_STRIDE, -ra.w);
-                    sts32(w + 4 * CW_STRIDE, rb.x); sts32(w + 5 * CW_STRIDE, rb.y); sts32u(w + 6 * CW_STRIDE, (uint32_t)e);
-                }
-                if (lane == 0 && (n & 1)) {  // sentinel: opacity 0 -> alpha 0 -> never a contributor
-                    const uint32_t w = a_cw + 4u * (uint32_t)n;
-                    sts32(w, 0.0f); sts32(w + CW_STRIDE, 0.0f); sts32(w + 2 * CW_STRIDE, 0.0f); sts32(w + 3 * CW_STRIDE, 0.0f);
-                    sts32(w + 4 * CW_STRIDE, 0.0f); sts32(w + 5 * CW_STRIDE, 0.0f); sts32u(w + 6 * CW_STRIDE, 0u);
-                }
+                if (keep) cw_store(a_cw, __popc(m & lt_mask), ra, rb, e);  // compact the survivors in list order
                 __syncwarp();
-                // back to front over the survivors, two per iteration: the alpha arithmetic (the forward's, so the
-                // contributor set is identical) runs packed for both, the recurrences and reductions one by one
-                for (int t = (n - 1) & ~1; t >= 0; t -= 2) {
-                    const uint32_t cw = a_cw + 4u * (uint32_t)t;
+                // back to front over the survivors: the alpha arithmetic (the forward's, so the contributor set is
+                // identical) runs packed for the lane's two pixels, the recurrences one by one
+                for (int t = n - 1; t >= 0; --t) {
+                    const uint32_t cw = a_cw + CW_REC * (uint32_t)t;
                     f32x2 power2, alpha2, dx2, dy2, G2;
-                    alpha_pair(cw, npx, npy, power2, alpha2, dx2, dy2, G2);
-                    float pw[2], al[2], dxs[2], dys[2], Gs[2];
-                    upk2(power2, pw[0], pw[1]);
-                    upk2(alpha2, al[0], al[1]);
-                    upk2(dx2, dxs[0], dxs[1]);
-                    upk2(dy2, dys[0], dys[1]);
-                    upk2(G2, Gs[0], Gs[1]);
-                    const f32x2 jj = lds64(cw + 6 * CW_STRIDE);
-                    const int js[2] = {(int)(uint32_t)(jj & 0xffffffffull), (int)(uint32_t)(jj >> 32)};
-#pragma unroll
-                    for (int h = 1; h >= 0; --h) {
-                        const int j = js[h];
-                        const float alpha = al[h], dx = dxs[h], dy = dys[h];
-                        // per-pixel work stops at cg = G * dL/dalpha and w = alpha * T; lanes that do not
-                        // contribute keep both at zero, so the products below need no other masking
-                        float cg = 0.0f, w = 0.0f;
-                        const bool hit = j < lim && pw[h] <= 0.0f && alpha >= 1.0f / 255.0f;
-                        if (hit) {
-                            // one refined reciprocal replaces two IEEE divisions by (1 - alpha) (no FCHK /
-                            // slow-path branches; operands are in [0.01, 1] so no special cases exist)
-                            const float oma = 1.0f - alpha;
-                            const float inv = rcp_nr(oma);
-                            const float t0 = T * inv;  // T / (1 - alpha), residual-corrected: the error must
-                            T = fma_(fma_(-t0, oma, T), inv, t0);  // not accumulate along the list
-                            w = alpha * T;
-                            const float4 c = lds128(a_rgb + 16u * j);
-                            // colour behind this entry enters only through its dot product with dL/dpixel
-                            const float cd = fma_(c.z, dp2, fma_(c.y, dp1, c.x * dp0));
-                            behind = fma_(last_alpha, last_cd, (1.0f - last_alpha) * behind);
-                            last_cd = cd;
-                            last_alpha = alpha;
-                            cg = Gs[h] * fma_(bgT, inv, (cd - behind) * T);
-                        }
-                        if (!__any_sync(0xffffffffu, hit)) continue;
-                        // moments of cg about the Gaussian's centre (the flush below turns the tile's sums into
-                        // dL/dmean2D and dL/dconic) and the colour gradient
-                        const float cgx = cg * dx, cgy = cg * dy;
-                        float v[9] = {cgx, cgy, cgx * dx, cgx * dy, cgy * dy, cg, w * dp0, w * dp1, w * dp2};
-                        tr_reduce<9, 16>(v, lane);
-                        if (owner) reds_add(a_acc + 48u * j, v[0]);
+                    alpha_two(cw, npx, npy, power2, alpha2, dx2, dy2, G2);
+                    float pw0, pw1, al0, al1, G0, G1;
+                    upk2(power2, pw0, pw1);
+                    upk2(alpha2, al0, al1);
+                    upk2(G2, G0, G1);
+                    const int j = (int)lds32(cw + 48u);
+                    const bool hit_a = j < lim_a && pw0 <= 0.0f && al0 >= 1.0f / 255.0f;
+                    const bool hit_b = j < lim_b && pw1 <= 0.0f && al1 >= 1.0f / 255.0f;
+                    if (!__any_sync(0xffffffffu, hit_a || hit_b)) continue;
+                    // per-pixel work stops at cg = G * dL/dalpha and w = alpha * T; pixels that do not contribute keep
+                    // both at zero, so the products below need no other masking
+                    float cga = 0.0f, wa = 0.0f, cgb = 0.0f, wb = 0.0f;
+                    const float4 c = lds128(a_rgb + 16u * j);
+                    if (hit_a) {
+                        // one refined reciprocal replaces the IEEE divisions by (1 - alpha) (no FCHK / slow-path
+                        // branches; operands are in [0.01, 1] so no special cases exist)
+                        const float oma = 1.0f - al0;
+                        const float inv = rcp_nr(oma);
+                        const float t0 = Ta * inv;  // T / (1 - alpha), residual-corrected: the error must not
+                        Ta = fma_(fma_(-t0, oma, Ta), inv, t0);  // accumulate along the list
+                        wa = al0 * Ta;
+                        const float cd = fma_(c.z, da2, fma_(c.y, da1, c.x * da0));
+                        // the colour behind this entry enters only through its dot product with dL/dpixel
+                        cga = G0 * fma_(bgTa, inv, (cd - bha) * Ta);
+                        bha = fma_(al0, cd, oma * bha);
                     }
+                    if (hit_b) {
+                        const float oma = 1.0f - al1;
+                        const float inv = rcp_nr(oma);
+                        const float t0 = Tb * inv;
+                        Tb = fma_(fma_(-t0, oma, Tb), inv, t0);
+                        wb = al1 * Tb;
+                        const float cd = fma_(c.z, db2, fma_(c.y, db1, c.x * db0));
+                        cgb = G1 * fma_(bgTb, inv, (cd - bhb) * Tb);
+                        bhb = fma_(al1, cd, oma * bhb);
+                    }
+                    // moments of cg about the Gaussian's centre (the flush below turns the tile's sums into
+                    // dL/dmean2D and dL/dconic) and the colour gradient: packed over the two pixels, then added
+                    const f32x2 cg2 = pk2(cga, cgb), w2 = pk2(wa, wb);
+                    const f32x2 cgx = mul2(cg2, dx2), cgy = mul2(cg2, dy2);
+                    const f32x2 q[9] = {cgx, cgy, mul2(cgx, dx2), mul2(cgx, dy2), mul2(cgy, dy2), cg2,
+                                        mul2(w2, dp0), mul2(w2, dp1), mul2(w2, dp2)};
+                    float v[9];
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) {
+                        float lo, hi;
+                        upk2(q[i], lo, hi);
+                        v[i] = lo + hi;
+                    }
+                    tr_reduce<9, 16>(v, lane);
+                    if (owner) reds_add(a_acc + 48u * j, v[0]);
                 }
                 __syncwarp();  // the buffer is rewritten by the next group
             }
         }
         __syncthreads();
         // flush the round's tile-level sums: three 16-byte vector reductions per touched Gaussian
-        if (idx < count) {
-            float4 g0 = s_acc[3 * threadIdx.x], g1 = s_acc[3 * threadIdx.x + 1];
-            const float4 g2 = s_acc[3 * threadIdx.x + 2];
-            const bool nz = g0.x != 0.0f || g0.y != 0.0f || g0.z != 0.0f || g0.w != 0.0f || g1.x != 0.0f || g1.y != 0.0f ||
-                            g1.z != 0.0f || g1.w != 0.0f || g2.x != 0.0f;
-            if (nz) {
-                // moments -> gradients: dG/ddelta = -G (A dx + B dy, B dx + C dy), dG/dconic = -0.5 G (dx^2, dx dy, dy^2)
-                const float4 ra = s_ra[threadIdx.x], rb = s_rb[threadIdx.x];
-                const float opx = -rb.y * ddelx_dx, opy = -rb.y * ddely_dy, oph = -0.5f * rb.y;
-                const float mx = g0.x, my = g0.y;
-                g0.x = opx * fma_(ra.w, my, ra.z * mx);
-                g0.y = opy * fma_(rb.x, my, ra.w * mx);
-                g0.z *= oph; g0.w *= oph; g1.x *= oph;
-                float *dst = grad_blend + 12 * (size_t)s_id[threadIdx.x];
-                red_global_v4(dst, g0);
-                red_global_v4(dst + 4, g1);
-                red_global_v4(dst + 8, g2);
-                s_acc[3 * threadIdx.x] = make_float4(0, 0, 0, 0);
-                s_acc[3 * threadIdx.x + 1] = make_float4(0, 0, 0, 0);
-                s_acc[3 * threadIdx.x + 2] = make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int h = 0; h < ROUND / BLK; ++h) {
+            const int st = h * BLK + threadIdx.x, idx = r * ROUND + st;
+            if (idx < count) {
+                float4 g0 = s_acc[3 * st], g1 = s_acc[3 * st + 1];
+                const float4 g2 = s_acc[3 * st + 2];
+                const bool nz = g0.x != 0.0f || g0.y != 0.0f || g0.z != 0.0f || g0.w != 0.0f || g1.x != 0.0f ||
+                                g1.y != 0.0f || g1.z != 0.0f || g1.w != 0.0f || g2.x != 0.0f;
+                if (nz) {
+                    // moments -> gradients: dG/ddelta = -G (A dx + B dy, B dx + C dy), dG/dconic = -0.5 G (dx^2, dx dy, dy^2)
+                    const float4 ra = s_ra[st], rb = s_rb[st];
+                    const float opx = -rb.y * ddelx_dx, opy = -rb.y * ddely_dy, oph = -0.5f * rb.y;
+                    const float mx = g0.x, my = g0.y;
+                    g0.x = opx * fma_(ra.w, my, ra.z * mx);
+                    g0.y = opy * fma_(rb.x, my, ra.w * mx);
+                    g0.z *= oph; g0.w *= oph; g1.x *= oph;
+                    float *dst = grad_blend + 12 * (size_t)s_id[st];
+                    red_global_v4(dst, g0);
+                    red_global_v4(dst + 4, g1);
+                    red_global_v4(dst + 8, g2);
+                    s_acc[3 * st] = make_float4(0, 0, 0, 0);
+                    s_acc[3 * st + 1] = make_float4(0, 0, 0, 0);
+                    s_acc[3 * st + 2] = make_float4(0, 0, 0, 0);
+                }
             }
         }
         __syncthreads();

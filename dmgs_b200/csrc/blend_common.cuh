@@ -5,9 +5,16 @@
 
 namespace dmgs {
 
-constexpr int BLK = 256;
+constexpr int BLK = 128;    // 4 warps per 16x16 tile, two pixels per lane
+#ifndef BLEND_ROUND
+#define BLEND_ROUND 128
+#endif
+constexpr int ROUND = BLEND_ROUND;  // entries staged per round (ROUND / BLK per thread)
+#ifndef FWD_MIN_BLOCKS
+#define FWD_MIN_BLOCKS 8
+#endif
 #ifndef BWD_MIN_BLOCKS
-#define BWD_MIN_BLOCKS 4
+#define BWD_MIN_BLOCKS 8
 #endif
 
 struct BlendArgs {
@@ -95,22 +102,43 @@ __device__ __forceinline__ f32x2 lds64(uint32_t a)
 __device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void sts32u(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
-// Per-warp compacted survivor list of one 32-entry group, structure of arrays so that ONE 8-byte shared load
-// fetches the same field of two consecutive survivors: x, y, A, -B, C, opacity, staged index.  34 slots: up to 32
-// survivors + a sentinel (opacity 0: alpha = 0 fails the 1/255 test) that pads an odd count to a pair.
-constexpr int CW_SLOTS = 34, CW_FIELDS = 7;
-constexpr uint32_t CW_STRIDE = CW_SLOTS * 4u;             // bytes between two fields
-constexpr uint32_t CW_WARP_BYTES = CW_FIELDS * CW_STRIDE;  // 952 B per warp
+// Per-warp compacted survivor list of one 32-entry group.  A lane owns TWO pixels (same column, rows v and v + 4 of
+// the warp's 8x8 rectangle) and evaluates both with packed FP32, so every field is stored twice: one broadcast
+// 16-byte shared load yields two ready-made register pairs.  64 bytes per survivor:
+//   {x, x, y, y} {A, A, -B, -B} {C, C, opacity, opacity} {staged index, -, -, -}
+constexpr uint32_t CW_REC = 64u;
+constexpr uint32_t CW_WARP_BYTES = 32u * CW_REC;  // 2 KB per warp
 
-// alpha of two list entries for one pixel, in the arithmetic contract, element-wise:
+__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void lds128x2(uint32_t a, f32x2 &lo, f32x2 &hi)
+{
+    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(a));
+}
+// survivor `slot` of the warp's list <- staged entry e (ra = x, y, A, B; rb = C, opacity, cut, -)
+__device__ __forceinline__ void cw_store(uint32_t a_cw, int slot, const float4 &ra, const float4 &rb, int e)
+{
+    const uint32_t w = a_cw + CW_REC * (uint32_t)slot;
+    sts128(w, ra.x, ra.x, ra.y, ra.y);
+    sts128(w + 16u, ra.z, ra.z, -ra.w, -ra.w);
+    sts128(w + 32u, rb.x, rb.x, rb.y, rb.y);
+    sts32u(w + 48u, (uint32_t)e);
+}
+
+// alpha of ONE list entry for the lane's TWO pixels, in the arithmetic contract, element-wise:
 //   dx = x - px, dy = y - py;  q = fma(dx, A dx, (C dy) dy);  power = fma(q, -0.5, (-B dx) dy)
 //   G = dmgs_exp(power) (for power <= 0 only max(power, -80) of its clamp can act);  alpha = min(0.99, opacity G)
-// npx, npy: (-px, -px), (-py, -py).  Returns power and alpha pairs (alpha meaningless where power > 0).
-__device__ __forceinline__ void alpha_pair(uint32_t cw, f32x2 npx, f32x2 npy, f32x2 &power, f32x2 &alpha, f32x2 &dxo, f32x2 &dyo,
-                                           f32x2 &Go)
+// cw: shared address of the survivor record; npx, npy: (-px, -px), (-py_a, -py_b).  alpha is meaningless where
+// power > 0.
+__device__ __forceinline__ void alpha_two(uint32_t cw, f32x2 npx, f32x2 npy, f32x2 &power, f32x2 &alpha, f32x2 &dxo, f32x2 &dyo,
+                                          f32x2 &Go)
 {
-    const f32x2 X = lds64(cw), Y = lds64(cw + CW_STRIDE), A = lds64(cw + 2 * CW_STRIDE), NB = lds64(cw + 3 * CW_STRIDE);
-    const f32x2 Cc = lds64(cw + 4 * CW_STRIDE), OP = lds64(cw + 5 * CW_STRIDE);
+    f32x2 X, Y, A, NB, Cc, OP;
+    lds128x2(cw, X, Y);
+    lds128x2(cw + 16u, A, NB);
+    lds128x2(cw + 32u, Cc, OP);
     const f32x2 dx = add2(X, npx), dy = add2(Y, npy);
     const f32x2 t1 = mul2(A, dx);
     const f32x2 t2 = mul2(mul2(Cc, dy), dy);
@@ -177,11 +205,12 @@ __device__ __forceinline__ bool cull_rect(float gx, float gy, float A, float B, 
     return 0.5f * qmin > cut + 1.0e-5f * mag + 1.0e-3f;
 }
 
+// warp w of a tile's four owns the 8x8 pixel square (w & 1, w >> 1); lane -> column lane & 7, rows lane >> 3 and + 4
 __device__ __forceinline__ void warp_rect(int &px0, int &py0)
 {
     const int w = threadIdx.x >> 5;
     px0 = blockIdx.x * DMGS_TILE + (w & 1) * 8;
-    py0 = blockIdx.y * DMGS_TILE + (w >> 1) * 4;
+    py0 = blockIdx.y * DMGS_TILE + (w >> 1) * 8;
 }
 
 }  // namespace dmgs

@@ -11,7 +11,7 @@ import torch
 
 from dmgs_b200 import synthetic as S
 from oracle import oracle as O
-from util import cam_params, cov6_from_scale_rot, grad_close, small_scene
+from util import cam_params, cov6_from_scale_rot, grad_close, grad_close_conditioned, small_scene
 
 pytestmark = pytest.mark.gpu
 
@@ -125,7 +125,8 @@ def test_backward_parity(mode):
     H, W = cam.image_height, cam.image_width
     dL = torch.randn(3, H, W, generator=torch.Generator().manual_seed(5))
     bw = O.render_backward(pr, ref, dL.numpy(), cl["means3D"].numpy(), scales=npin.get("scales"),
-                           rotations=npin.get("rotations"), shs=npin.get("shs"), precomp_color="colors_precomp" in npin)
+                           rotations=npin.get("rotations"), shs=npin.get("shs"), precomp_color="colors_precomp" in npin,
+                           abs_sums=True)
     d = lambda k: None if k not in npin else torch.tensor(npin[k]).cuda()
     g = rasterize_backward(st, dL.cuda(), cl["means3D"].cuda(), d("shs"), d("scales"), d("rotations"),
                            d("cov3D_precomp"), "colors_precomp" in npin)
@@ -134,7 +135,9 @@ def test_backward_parity(mode):
     grad_close(g_means3D, bw["dL_dmeans3D"], name="means3D")
     grad_close(g_means2D[:, :2], bw["dL_dmean2D"], name="means2D")
     assert (g_means2D[:, 2] == 0).all()
-    grad_close(g_op[:, 0], bw["dL_dopacity"], name="opacity")
+    # the two pure blend-backward outputs, element by element against their conditioning (tests/util.py)
+    grad_close_conditioned(g_op[:, 0], bw["dL_dopacity"], bw["abs9"][:, 5], name="opacity")
+    grad_close_conditioned(g_means2D[:, :2], bw["dL_dmean2D"], bw["abs9"][:, 0:2], name="means2D (conditioned)")
     if g_shs is not None:
         grad_close(g_shs, bw["dL_dshs"], name="shs")
     if g_col is not None:

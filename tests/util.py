@@ -62,3 +62,17 @@ def grad_close(got, ref, rtol=1e-4, name=""):
         i, j = np.unravel_index(np.argmax(err / scale), err.shape)
         raise AssertionError(f"{name}: {bad.sum()} / {bad.size} elements off; worst row {i}: got {g2[i]} ref {r2[i]} "
                              f"(err {err[i, j]:.3e}, scale {scale[i, 0]:.3e})")
+
+
+def grad_close_conditioned(got, ref, abs_sums, rtol=1e-4, ctol=1e-5, name=""):
+    """Element-wise bar for gradients that are sums of many mixed-sign fp32 terms accumulated in an order that
+    differs from the oracle's (and from run to run: atomics): |got - ref| <= rtol |ref| + ctol * (sum of the
+    MAGNITUDES of the element's terms, the oracle's `abs9`), i.e. plain 1e-4 relative unless the sum cancels by
+    more than 10x; no row scaling, no floor, no outliers."""
+    got, ref, ab = (np.asarray(x, np.float64) for x in (got, ref, abs_sums))
+    assert got.shape == ref.shape == ab.shape, f"{name}: shapes {got.shape} {ref.shape} {ab.shape}"
+    err = np.abs(got - ref)
+    bound = rtol * np.abs(ref) + ctol * ab + 1e-30
+    worst = float((err / bound).max()) if err.size else 0.0
+    assert worst <= 1.0, (f"{name}: worst error / bound = {worst:.3f} at "
+                          f"{np.unravel_index(np.argmax(err / bound), err.shape)}")
