@@ -5,11 +5,7 @@
 
 namespace dmgs {
 
-constexpr int BLK = 128;    // 4 warps per 16x16 tile, two pixels per lane
-#ifndef BLEND_ROUND
-#define BLEND_ROUND 128
-#endif
-constexpr int ROUND = BLEND_ROUND;  // entries staged per round (ROUND / BLK per thread)
+constexpr int BLK = 128;    // 4 warps per 16x16 tile, two pixels per lane; the warps never synchronise with each other
 #ifndef FWD_MIN_BLOCKS
 #define FWD_MIN_BLOCKS 8
 #endif
@@ -60,9 +56,9 @@ __device__ __forceinline__ float rcp_nr(float x)
 }
 
 // ---- packed FP32 (sm_100: FFMA2 / FMUL2 / FADD2, two IEEE round-to-nearest results per instruction).  The blend
-// kernels are bound by instruction ISSUE, not by the FP32 pipes (ncu: issue 80 %, fma pipe 40 %), so evaluating two
-// list entries per instruction cuts the time.  Element-wise the results are those of the scalar operations, which
-// keeps every forward decision bit-identical.  NOTE: never write mul2 followed by add2 where the contract wants two
+// kernels are bound by instruction ISSUE, not by the FP32 pipes (ncu: issue 70-80 %, fma pipe 40-48 %), so evaluating
+// a lane's two pixels per instruction cuts the time.  Element-wise the results are those of the scalar operations,
+// which keeps every forward decision bit-identical.  NOTE: never write mul2 followed by add2 where the contract wants two
 // roundings -- ptxas 12.9 contracts that pair into FFMA2 even with -fmad=false; use fma2 (and say so in the contract).
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pk2(float lo, float hi)
@@ -103,9 +99,9 @@ __device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.sh
 __device__ __forceinline__ void sts32u(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
 // Per-warp compacted survivor list of one 32-entry group.  A lane owns TWO pixels (same column, rows v and v + 4 of
-// the warp's 8x8 rectangle) and evaluates both with packed FP32, so every field is stored twice: one broadcast
-// 16-byte shared load yields two ready-made register pairs.  64 bytes per survivor:
-//   {x, x, y, y} {A, A, -B, -B} {C, C, opacity, opacity} {staged index, -, -, -}
+// the warp's 8x8 square) and evaluates both with packed FP32, so every geometric field is stored twice: one
+// broadcast 16-byte shared load yields two ready-made register pairs.  64 bytes per survivor:
+//   {x, x, y, y} {A, A, -B, -B} {C, C, opacity, opacity} {r, g, b, position in the tile's list (u32 bits)}
 constexpr uint32_t CW_REC = 64u;
 constexpr uint32_t CW_WARP_BYTES = 32u * CW_REC;  // 2 KB per warp
 
@@ -117,15 +113,18 @@ __device__ __forceinline__ void lds128x2(uint32_t a, f32x2 &lo, f32x2 &hi)
 {
     asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(a));
 }
-// survivor `slot` of the warp's list <- staged entry e (ra = x, y, A, B; rb = C, opacity, cut, -)
-__device__ __forceinline__ void cw_store(uint32_t a_cw, int slot, const float4 &ra, const float4 &rb, int e)
+// survivor `slot` of the warp's list <- list entry number `pos` (ra = x, y, A, B; rb = C, opacity, cut, -; colour)
+__device__ __forceinline__ void cw_store(uint32_t a_cw, int slot, const float4 &ra, const float4 &rb, const float4 &col,
+                                         uint32_t pos)
 {
     const uint32_t w = a_cw + CW_REC * (uint32_t)slot;
     sts128(w, ra.x, ra.x, ra.y, ra.y);
     sts128(w + 16u, ra.z, ra.z, -ra.w, -ra.w);
     sts128(w + 32u, rb.x, rb.x, rb.y, rb.y);
-    sts32u(w + 48u, (uint32_t)e);
+    sts128(w + 48u, col.x, col.y, col.z, __uint_as_float(pos));
 }
+// read-only 16-byte gather (records and colours are written by preprocess, a different kernel)
+__device__ __forceinline__ float4 ldg128(const float4 *p) { return __ldg(p); }
 
 // alpha of ONE list entry for the lane's TWO pixels, in the arithmetic contract, element-wise:
 //   dx = x - px, dy = y - py;  q = fma(dx, A dx, (C dy) dy);  power = fma(q, -0.5, (-B dx) dy)
