@@ -28,15 +28,15 @@ blend_fwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
     __shared__ __align__(16) unsigned char s_cw[(BLK / 32) * CW_WARP_BYTES];  // per-warp compacted survivors
 
     const int lane = threadIdx.x & 31;
-    int px0, py0;
-    warp_rect(px0, py0);
+    int tile, px0, py0;
+    if (!warp_square(a, tile, px0, py0)) return;
     const int px = px0 + (lane & 7), pya = py0 + (lane >> 3), pyb = pya + 4;
     const bool in_a = px < a.W && pya < a.H, in_b = px < a.W && pyb < a.H;
     if (!__any_sync(0xffffffffu, in_a)) return;  // the whole square lies outside the image
     const float pxf = (float)px;
     const f32x2 npx = pk2(-pxf, -pxf), npy = pk2(-(float)pya, -(float)pyb);
     const float rx0 = (float)px0, rx1 = (float)(px0 + 7), ry0 = (float)py0, ry1 = (float)(py0 + 7);
-    const uint2 rng = ranges[blockIdx.y * a.gx + blockIdx.x];
+    const uint2 rng = ranges[tile];
     const int total = (int)(rng.y - rng.x);
     const uint32_t *__restrict__ list = gidx + rng.x;
 
@@ -140,7 +140,7 @@ int launch_blend_fwd(const dmgs_params *prm, const void *geom, const GeomLayout 
     a.gx = (a.W + DMGS_TILE - 1) / DMGS_TILE; a.gy = (a.H + DMGS_TILE - 1) / DMGS_TILE;
     for (int i = 0; i < 3; ++i) a.bg[i] = prm->bg[i];
     if (a.W <= 0 || a.H <= 0) return 0;
-    blend_fwd_kernel<<<dim3(a.gx, a.gy), BLK, 0, s>>>(a, at<uint2>(binning, BL.ranges), at<uint32_t>(binning, BL.gidx),
+    blend_fwd_kernel<<<blend_grid(a), BLK, 0, s>>>(a, at<uint2>(binning, BL.ranges), at<uint32_t>(binning, BL.gidx),
                                                       at<float4>(geom, GL.rec), at<float4>(geom, GL.rgb), out_color,
                                                       at<float>(image, IL.final_T), at<uint32_t>(image, IL.n_contrib));
     DMGS_CUDA(cudaGetLastError());

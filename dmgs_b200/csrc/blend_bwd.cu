@@ -59,8 +59,8 @@ blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
     __shared__ __align__(16) unsigned char s_acc[(BLK / 32) * ACC_WARP_BYTES];  // per-warp sums of the current group
 
     const int lane = threadIdx.x & 31;
-    int px0, py0;
-    warp_rect(px0, py0);
+    int tile, px0, py0;
+    if (!warp_square(a, tile, px0, py0)) return;
     const int px = px0 + (lane & 7), pya = py0 + (lane >> 3), pyb = pya + 4;
     const bool in_a = px < a.W && pya < a.H, in_b = px < a.W && pyb < a.H;
     const size_t pix_a = (size_t)pya * a.W + px, pix_b = (size_t)pyb * a.W + px, HW = (size_t)a.H * a.W;
@@ -72,7 +72,7 @@ blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
     const float pxf = (float)px;
     const f32x2 npx = pk2(-pxf, -pxf), npy = pk2(-(float)pya, -(float)pyb);
     const float rx0 = (float)px0, rx1 = (float)(px0 + 7), ry0 = (float)py0, ry1 = (float)(py0 + 7);
-    const uint32_t *__restrict__ list = gidx + ranges[blockIdx.y * a.gx + blockIdx.x].x;
+    const uint32_t *__restrict__ list = gidx + ranges[tile].x;
 
     // per pixel: T (transmittance in front of the entry being visited), `behind` = (colour blended behind that
     // entry) . dL/dpixel, normalised by the transmittance behind it, and the background's share bgT
@@ -219,7 +219,7 @@ int launch_blend_bwd(const dmgs_params *prm, const void *geom, const GeomLayout 
     a.gx = (a.W + DMGS_TILE - 1) / DMGS_TILE; a.gy = (a.H + DMGS_TILE - 1) / DMGS_TILE;
     for (int i = 0; i < 3; ++i) a.bg[i] = prm->bg[i];
     if (a.W <= 0 || a.H <= 0) return 0;
-    blend_bwd_kernel<<<dim3(a.gx, a.gy), BLK, 0, s>>>(a, at<uint2>(binning, BL.ranges), at<uint32_t>(binning, BL.gidx),
+    blend_bwd_kernel<<<blend_grid(a), BLK, 0, s>>>(a, at<uint2>(binning, BL.ranges), at<uint32_t>(binning, BL.gidx),
                                                       at<float4>(geom, GL.rec), at<float4>(geom, GL.rgb),
                                                       at<float>(image, IL.final_T), at<uint32_t>(image, IL.n_contrib),
                                                       dL_dpix, grad_blend);

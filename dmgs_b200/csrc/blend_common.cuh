@@ -5,7 +5,13 @@
 
 namespace dmgs {
 
-constexpr int BLK = 128;    // 4 warps per 16x16 tile, two pixels per lane; the warps never synchronise with each other
+// A 16x16 tile is four 8x8 squares, one per warp, two pixels per lane.  The warps never synchronise with each
+// other, so the CTA size only decides how soon a finished warp gives its slot back (and how the four squares of a
+// tile share L1): squares are numbered 4 * tile + quadrant and dealt to the warps of a 1-D grid.
+#ifndef BLEND_BLK
+#define BLEND_BLK 128
+#endif
+constexpr int BLK = BLEND_BLK;
 #ifndef FWD_MIN_BLOCKS
 #define FWD_MIN_BLOCKS 8
 #endif
@@ -204,12 +210,18 @@ __device__ __forceinline__ bool cull_rect(float gx, float gy, float A, float B, 
     return 0.5f * qmin > cut + 1.0e-5f * mag + 1.0e-3f;
 }
 
-// warp w of a tile's four owns the 8x8 pixel square (w & 1, w >> 1); lane -> column lane & 7, rows lane >> 3 and + 4
-__device__ __forceinline__ void warp_rect(int &px0, int &py0)
+// square sq = 4 * tile + q owns the 8x8 pixels (q & 1, q >> 1) of its tile; lane -> column lane & 7, rows lane >> 3
+// and + 4.  Returns false for the padding warps of the last CTA.
+__device__ __forceinline__ bool warp_square(const BlendArgs &a, int &tile, int &px0, int &py0)
 {
-    const int w = threadIdx.x >> 5;
-    px0 = blockIdx.x * DMGS_TILE + (w & 1) * 8;
-    py0 = blockIdx.y * DMGS_TILE + (w >> 1) * 8;
+    const int sq = blockIdx.x * (BLK / 32) + (threadIdx.x >> 5);
+    tile = sq >> 2;
+    if (tile >= a.gx * a.gy) return false;
+    const int ty = tile / a.gx, tx = tile - ty * a.gx, q = sq & 3;
+    px0 = tx * DMGS_TILE + (q & 1) * 8;
+    py0 = ty * DMGS_TILE + (q >> 1) * 8;
+    return true;
 }
+__host__ inline int blend_grid(const BlendArgs &a) { return (4 * a.gx * a.gy + BLK / 32 - 1) / (BLK / 32); }
 
 }  // namespace dmgs

@@ -227,19 +227,38 @@ tile_place_kernel(int P, int T, int gx, int seg, int nseg, const uint4 *__restri
     const int sg = blockIdx.x * wpb + w;
     uint32_t *cur = s_cur + (size_t)w * T;
     if (sg < nseg) {
+        // eight independent loads in flight per lane (the plain loop was one L2 round trip per 32 tiles)
         const uint32_t *row = table + (size_t)sg * T;
-        for (int t = lane; t < T; t += 32) cur[t] = row[t];
+        int t = lane;
+        for (; t + 7 * 32 < T; t += 8 * 32) {
+            uint32_t v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = row[t + 32 * u];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) cur[t + 32 * u] = v[u];
+        }
+        for (; t < T; t += 32) cur[t] = row[t];
     } else {
         for (int t = lane; t < T; t += 32) cur[t] = 0;
     }
     __syncthreads();
     const uint32_t *grow = gsum + (size_t)blockIdx.x * T;
-    for (int t = threadIdx.x; t < T; t += blockDim.x) {
-        uint32_t run = tile_start[t] + grow[t];
-        for (int k = 0; k < wpb; ++k) {
-            const uint32_t c = s_cur[(size_t)k * T + t];
-            s_cur[(size_t)k * T + t] = run;
-            run += c;
+    for (int t0 = threadIdx.x; t0 < T; t0 += 4 * blockDim.x) {
+        uint32_t run[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = t0 + u * blockDim.x;
+            run[u] = t < T ? tile_start[t] + grow[t] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = t0 + u * blockDim.x;
+            if (t < T)
+                for (int k = 0; k < wpb; ++k) {
+                    const uint32_t c = s_cur[(size_t)k * T + t];
+                    s_cur[(size_t)k * T + t] = run[u];
+                    run[u] += c;
+                }
         }
     }
     __syncthreads();

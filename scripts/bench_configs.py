@@ -125,3 +125,29 @@ if "c5" in which:
                 print(json.dumps({"config": f"c5: forward-only, {P} Gaussians SH-3, {W}x{H}", "ms_per_frame": round(ms, 4),
                                   "frames_per_s": round(1e3 / ms, 1), "R": st.num_rendered, "binning_fit": ok}), flush=True)
                 del cl
+
+if "4k" in which:
+    # > 16384 tiles: the direct placement path does not apply, binning falls back to emission in depth order + a
+    # stable radix partition by tile id (sort.cu) -- timed per stage on a real 3840x2160 image (32 400 tiles)
+    W, H = 3840, 2160
+    cam = S.nerf_synthetic_camera(0, W, H)
+    rs = settings(cam, torch.zeros(3, device=dev))
+    dL = torch.randn(3, H, W, generator=torch.Generator().manual_seed(1)).to(dev)
+    for P in [1_000_000, 3_000_000]:
+        cl = {k: v.to(dev) for k, v in S.random_cloud(P, seed=0, extent=1.3, log_scale_mean=math.log(0.01)).items()}
+        acc, n = {}, 10
+        for it in range(n + 3):
+            marks = [("start", ev())]
+            hook = lambda name: marks.append((name, ev()))
+            color, radii, st = rasterize_forward(rs, cl["means3D"], cl["opacities"], cl["shs"], None, cl["scales"],
+                                                 cl["rotations"], None, stage_hook=hook)
+            rasterize_backward(st, dL, cl["means3D"], cl["shs"], cl["scales"], cl["rotations"], None, False, stage_hook=hook)
+            torch.cuda.synchronize()
+            if it >= 3:
+                for (n0, a), (n1, b) in zip(marks[:-1], marks[1:]):
+                    acc[n1] = acc.get(n1, 0.0) + a.elapsed_time(b) / n
+        print(json.dumps({"config": f"4k: fwd+bwd, {P} Gaussians SH-3, {W}x{H} = {((W + 15) // 16) * ((H + 15) // 16)} tiles "
+                          "(radix tile partition, synchronous instance count)", "R": st.num_rendered,
+                          "stage_ms": {k: round(v, 4) for k, v in acc.items()},
+                          "ms_per_frame": round(sum(acc.values()), 4)}), flush=True)
+        del cl
