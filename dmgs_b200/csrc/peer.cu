@@ -14,6 +14,8 @@
 // symmetric-memory signal pads (all accumulators complete before, all slices delivered after).
 // NVLink traffic per rank: (N-1)/N * n * 4 B in each direction with peer loads/stores, n/N * 4 B in
 // each direction with multimem -- against 2 (N-1)/N * n * 4 B each way for a ring all-reduce.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -76,22 +78,39 @@ __device__ __forceinline__ void mm_st(float *p, float4 v)
                  ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-__global__ void __launch_bounds__(256)
+// U 16-byte groups per thread and iteration: all U in-switch reductions are issued before the first multicast store
+template <int U>
+__global__ void __launch_bounds__(1024)
 allreduce_multimem_kernel(float *mc, long long begin4, long long end4, float scale)
 {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long q = begin4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; q < end4; q += 4 * stride) {
-        float4 v[4];
+    for (long long q = begin4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; q < end4; q += U * stride) {
+        float4 v[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < U; ++u)
             if (q + u * stride < end4) v[u] = mm_ld_reduce(mc + 4 * (q + u * stride));
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < U; ++u)
             if (q + u * stride < end4) {
                 v[u].x *= scale; v[u].y *= scale; v[u].z *= scale; v[u].w *= scale;
                 mm_st(mc + 4 * (q + u * stride), v[u]);
             }
     }
+}
+
+// launch shape of the multimem kernel: {CTAs per SM, threads per CTA, groups in flight per thread}.  Measured on one
+// 8 x B200 box (profiles/r2_allreduce_sweep.jsonl): the exchange is bound by what the fabric sustains (0.60-0.66 ms
+// for 248 MB whatever the shape; running peer loads/stores beside the switch reduction on a share of the buffer
+// does not help either), a small grid with eight reductions in flight per thread is the best of them.
+// DMGS_AR_SHAPE="ctas,threads,unroll" overrides (experiments)
+static void ar_shape(int *ctas_per_sm, int *threads, int *unroll)
+{
+    int cc = 1, tt = 256, uu = 8;
+    if (const char *e = getenv("DMGS_AR_SHAPE")) sscanf(e, "%d,%d,%d", &cc, &tt, &uu);
+    if (cc < 1) cc = 1;
+    if (tt < 32 || tt > 1024 || (tt & 31)) tt = 256;
+    if (uu != 1 && uu != 2 && uu != 4 && uu != 8) uu = 4;
+    *ctas_per_sm = cc; *threads = tt; *unroll = uu;
 }
 
 int launch_allreduce_peer(int64_t n, int world, int rank, const void *const *peer_ptrs_host, void *multicast_ptr,
@@ -102,11 +121,23 @@ int launch_allreduce_peer(int64_t n, int world, int rank, const void *const *pee
     const long long n4 = n / 4, per = (n4 + world - 1) / world;
     const long long begin4 = (long long)rank * per, end4 = begin4 + per < n4 ? begin4 + per : n4;
     if (end4 <= begin4) return 0;
+    int cps, threads, unroll;
+    ar_shape(&cps, &threads, &unroll);
     long long blocks = (end4 - begin4 + 255) / 256;
-    const long long cap = (long long)num_sms() * 8;
+    long long cap = (long long)num_sms() * 8;
     if (blocks > cap) blocks = cap;
     if (multicast_ptr) {
-        allreduce_multimem_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<float *>(multicast_ptr), begin4, end4, scale);
+        float *mc = reinterpret_cast<float *>(multicast_ptr);
+        blocks = (end4 - begin4 + threads - 1) / threads;
+        cap = (long long)num_sms() * cps;
+        if (blocks > cap) blocks = cap;
+        const unsigned g = (unsigned)blocks;
+        switch (unroll) {
+        case 1: allreduce_multimem_kernel<1><<<g, threads, 0, s>>>(mc, begin4, end4, scale); break;
+        case 2: allreduce_multimem_kernel<2><<<g, threads, 0, s>>>(mc, begin4, end4, scale); break;
+        case 8: allreduce_multimem_kernel<8><<<g, threads, 0, s>>>(mc, begin4, end4, scale); break;
+        default: allreduce_multimem_kernel<4><<<g, threads, 0, s>>>(mc, begin4, end4, scale); break;
+        }
     } else {
         PeerPtrs pp;
         for (int k = 0; k < DMGS_MAX_PEERS; ++k) {

@@ -26,6 +26,15 @@ def timed(fn, iters=20):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t)
 
+if "--sweep" in sys.argv:  # launch shapes of the multimem kernel (DMGS_AR_SHAPE: CTAs per SM, threads, groups in flight)
+    for shape in ["8,256,4", "2,512,8", "1,1024,8", "4,512,4", "2,1024,4", "16,256,2", "1,512,8", "4,256,8", "1,256,8", "2,256,8"]:
+        os.environ["DMGS_AR_SHAPE"] = shape
+        ms = timed(lambda: vs.peer.all_reduce_(1.0, use_multicast=True), iters=10)
+        if rank == 0:
+            print(json.dumps({"world": world, "shape": shape, "multimem_ms": round(ms, 4),
+                              "algbw_GBps": round(flat.numel() * 4 / ms / 1e6, 1)}), flush=True)
+    dist.destroy_process_group()
+    sys.exit(0)
 res = {"world": world, "bytes": flat.numel() * 4, "peer_error": vs.peer_error}
 res["nccl_ms"] = timed(lambda: dist.all_reduce(other))
 if vs.peer is not None:
