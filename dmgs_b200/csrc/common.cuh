@@ -185,6 +185,14 @@ __device__ __forceinline__ float dmgs_exp(float x)
     return __int_as_float(__float_as_int(p) + (j << 23));
 }
 
+// 16-byte vector reduction into global memory (REDG.E.ADD.F32x4): fire-and-forget, resolved in L2.  The accumulate
+// modes of the per-Gaussian backward use reductions (not load-add-store) so that the views of a step running on
+// different CUDA streams can add into ONE gradient buffer.
+__device__ __forceinline__ void red_add_v4(float *p, float4 v)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 __device__ __forceinline__ int clampi_f(float v, int hi) { return (int)fminf(fmaxf(v, 0.0f), (float)hi); }
 
 // per-launch constants shared by the per-Gaussian kernels

@@ -601,7 +601,8 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const __grid_constan
                         const size_t idx = pr.sh_layout == 0 ? ((size_t)i * M + k) * 3 + ch : ((size_t)i * 3 + ch) * M + k;
                         if (k < nb) {
                             h[k] = fma_(__ldg(shs + idx), g[ch], h[k]);
-                            dL_dshs[idx] = accumulate ? dL_dshs[idx] + bas[k] * g[ch] : bas[k] * g[ch];
+                            if (accumulate) atomicAdd(&dL_dshs[idx], bas[k] * g[ch]);
+                            else dL_dshs[idx] = bas[k] * g[ch];
                         } else if (k < M && !accumulate) {
                             dL_dshs[idx] = 0.0f;
                         }
@@ -665,12 +666,12 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const __grid_constan
         if (inb) {
             if (accumulate) {
                 if (vis) {
-                    dL_dmeans2D[3 * (size_t)i] += d2x;
-                    dL_dmeans2D[3 * (size_t)i + 1] += d2y;
-                    dL_dopacity[i] += dop;
+                    atomicAdd(&dL_dmeans2D[3 * (size_t)i], d2x);
+                    atomicAdd(&dL_dmeans2D[3 * (size_t)i + 1], d2y);
+                    atomicAdd(&dL_dopacity[i], dop);
                     if (dL_dcolprec) {
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) dL_dcolprec[3 * (size_t)i + k] += dcol[k];
+                        for (int k = 0; k < 3; ++k) atomicAdd(&dL_dcolprec[3 * (size_t)i + k], dcol[k]);
                     }
                 }
             } else {
@@ -688,25 +689,24 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const __grid_constan
         if (accumulate) {
             if (vis) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) dL_dmeans3D[3 * (size_t)i + k] += gm[k];
-                dL_dmeans2D[3 * (size_t)i] += d2x;
-                dL_dmeans2D[3 * (size_t)i + 1] += d2y;
-                dL_dopacity[i] += dop;
+                for (int k = 0; k < 3; ++k) atomicAdd(&dL_dmeans3D[3 * (size_t)i + k], gm[k]);
+                atomicAdd(&dL_dmeans2D[3 * (size_t)i], d2x);
+                atomicAdd(&dL_dmeans2D[3 * (size_t)i + 1], d2y);
+                atomicAdd(&dL_dopacity[i], dop);
                 if (dL_dcolprec) {
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) dL_dcolprec[3 * (size_t)i + k] += dcol[k];
+                    for (int k = 0; k < 3; ++k) atomicAdd(&dL_dcolprec[3 * (size_t)i + k], dcol[k]);
                 }
                 if (dL_dcov3D) {
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) dL_dcov3D[6 * (size_t)i + k] += g6[k];
+                    for (int k = 0; k < 6; ++k) atomicAdd(&dL_dcov3D[6 * (size_t)i + k], g6[k]);
                 }
                 if (dL_dscales) {
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) dL_dscales[3 * (size_t)i + k] += gs[k];
+                    for (int k = 0; k < 3; ++k) atomicAdd(&dL_dscales[3 * (size_t)i + k], gs[k]);
                 }
                 if (dL_drots) {
-                    float4 o = reinterpret_cast<float4 *>(dL_drots)[i];
-                    reinterpret_cast<float4 *>(dL_drots)[i] = make_float4(o.x + gq[0], o.y + gq[1], o.z + gq[2], o.w + gq[3]);
+                    red_add_v4(dL_drots + 4 * (size_t)i, make_float4(gq[0], gq[1], gq[2], gq[3]));
                 }
             }
         } else {

@@ -161,15 +161,15 @@ class PeerAllReduce:
 
 
 class ViewStreams:
-    """Renders the local views of a step on `n` CUDA streams, round-robin, each stream accumulating into
-    its own FlatGradBuffer; `finish()` joins the streams and sums the buffers into the first one.
+    """Renders the local views of a step on `n` CUDA streams, round-robin, all of them accumulating into ONE
+    FlatGradBuffer; `finish()` joins the streams (and, in deferred-SH mode, forms the SH rows).
 
     Why: the stages of one view alternate between latency-bound kernels (depth sort, tile placement:
-    < 50 % issue utilisation, little HBM traffic) and issue-bound ones (the blend kernels: ~80 % issue
+    < 50 % issue utilisation, little HBM traffic) and issue-bound ones (the blend kernels: ~75 % issue
     utilisation, ~1 % of the HBM bandwidth).  Views of a step are independent given identical
-    Gaussians, so two views in flight let the SMs fill one view's stalls with the other's work.  The
-    per-Gaussian accumulators are read-modify-written without atomics by the per-Gaussian backward
-    (one thread owns one row), hence one buffer per stream rather than one shared buffer."""
+    Gaussians, so several views in flight let the SMs fill one view's stalls with the other's work.  The
+    accumulate modes of the per-Gaussian backward add with global reductions (red.global.add / TMA reduce-add,
+    resolved in L2), so concurrent views can share the buffer: no per-stream accumulators, no sums at the end."""
 
     def __init__(self, P: int, widths: Dict[str, Tuple[int, ...]], device, n: int = 2, peer_group=None,
                  deferred_sh_views: int = 0, sh_key: str = "shs"):
@@ -198,7 +198,7 @@ class ViewStreams:
                 raise
             self.peer, self.peer_error = None, f"{type(e).__name__}: {e}"
             first = FlatGradBuffer(P, widths, device)
-        self.bufs = [first] + [FlatGradBuffer(P, widths, device) for _ in range(n - 1)]
+        self.bufs = [first]
         self.sh_key, self.P = sh_key, int(P)
         self.records = (torch.zeros(int(deferred_sh_views), int(P), 4, dtype=torch.float32, device=device)
                         if deferred_sh_views > 0 and sh_key in widths else None)
@@ -217,25 +217,24 @@ class ViewStreams:
         return self.bufs[0]
 
     def begin(self):
-        """Zeroes the accumulators; the side streams start after everything queued on the current stream."""
+        """Zeroes the accumulator; the side streams start after everything queued on the current stream."""
         cur = torch.cuda.current_stream(self.device)
         self._campos, self._used = {}, 0
-        zero = (lambda b: b.flat[:self._dense].zero_()) if self.records is not None else (lambda b: b.zero_())
-        for b, st in zip(self.bufs, self.streams):
-            if st is None:
-                zero(b)
-                continue
-            st.wait_stream(cur)
-            with torch.cuda.stream(st):
-                zero(b)
+        if self.records is not None:
+            self.bufs[0].flat[:self._dense].zero_()
+        else:
+            self.bufs[0].zero_()
+        for st in self.streams:
+            if st is not None:
+                st.wait_stream(cur)
 
     def run(self, i: int, fn: Callable[[Dict[str, torch.Tensor]], object]):
         """Calls fn(acc_views) for the i-th local view on stream i mod n."""
         k = i % len(self.streams)
         if self.streams[k] is None:
-            return fn(self.bufs[k].views)
+            return fn(self.bufs[0].views)
         with torch.cuda.stream(self.streams[k]):
-            return fn(self.bufs[k].views)
+            return fn(self.bufs[0].views)
 
     def sh_record(self, i: int, campos) -> Optional[torch.Tensor]:
         """Record array [P,4] of the i-th local view of the step (deferred SH mode; None otherwise); campos is
@@ -258,11 +257,7 @@ class ViewStreams:
             if st is not None:
                 cur.wait_stream(st)
         if self.records is None:
-            for b in self.bufs[1:]:
-                self.bufs[0].flat.add_(b.flat)
             return self.bufs[0]
-        for b in self.bufs[1:]:
-            self.bufs[0].flat[:self._dense].add_(b.flat[:self._dense])
         if means3D is None or shs is None:
             raise ValueError("deferred SH mode: finish(means3D, shs, sh_degree) forms the SH gradient rows")
         if sorted(self._campos) != list(range(self._used)):
