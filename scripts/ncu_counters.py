@@ -67,6 +67,15 @@ def main():
             med[k] = statistics.median(vs) if vs else None
         med["launches_in_capture"] = len(launches)
         table[f] = med
+    # (warp square, list entry) pairs that survive the culling = trips of the blend kernels' inner loops
+    # (scripts/blend_stats.py, backward range; the forward walks a little further, to each square's saturation)
+    stats = os.path.join(os.path.dirname(out), "r2_blend_stats.json")
+    if os.path.exists(stats):
+        with open(stats) as fh:
+            st = json.load(fh).get(workload)
+        if st and "blend_bwd" in table:
+            table["blend_bwd"]["warp_entry_pairs"] = st["8x8"]["survivors"]
+            table["blend_bwd"]["pixel_entry_hits"] = st["8x8"]["pixel_hits"]
     doc = {"source": None, "workloads": {}}
     if os.path.exists(out):
         with open(out) as fh:
