@@ -153,7 +153,7 @@ static int preprocess_forward_impl(const dmgs_params *prm, const BindSrc *bind, 
     uint32_t *stat = placed ? at<uint32_t>(geom, L.stat) : nullptr;
     if (placed) {
         DMGS_CUDA(cudaMemsetAsync(num_rendered, 0, sizeof(uint32_t), s));
-        DMGS_CUDA(cudaMemsetAsync(stat, 0, 16, s));
+        DMGS_CUDA(cudaMemsetAsync(stat, 0, L.os_status - L.stat, s));  // key range, tile counters, digit histograms
     }
     rc = launch_preprocess_fwd(prm, bind, xyz_out, means3D, scales, rotations, cov3D_precomp, opacities, shs,
                                colors_precomp, radii, geom, L, placed ? num_rendered : nullptr, stat, s);
@@ -164,11 +164,10 @@ static int preprocess_forward_impl(const dmgs_params *prm, const BindSrc *bind, 
     // skipped on the device, typically the top byte); otherwise all four run and the result is in A.
     uint32_t *ka = at<uint32_t>(geom, L.keys_a), *kb = at<uint32_t>(geom, L.keys_b);
     uint32_t *va = at<uint32_t>(geom, L.order), *vb = at<uint32_t>(geom, L.vals_b);
-    uint32_t *hist = at<uint32_t>(geom, L.hist), *tmp = at<uint32_t>(geom, L.scan_tmp);
-    for (int pass = 0; pass < 4; ++pass) {
-        rc = radix_pass(ka, va, kb, vb, P, pass, 8 * pass, 8, hist, stat, s);
-        if (rc) return rc;
-    }
+    uint32_t *tmp = at<uint32_t>(geom, L.scan_tmp);
+    rc = depth_sort_onesweep(ka, va, kb, vb, P, at<uint32_t>(geom, L.os_ghist), at<uint32_t>(geom, L.stat) + 4,
+                             at<uint32_t>(geom, L.os_status), stat, s);
+    if (rc) return rc;
     if ((rc = check_stage(prm, s, "depth sort"))) return rc;
     if (placed) return 0;
     rc = exclusive_scan_u32(at<uint32_t>(geom, L.tiles), va, at<uint32_t>(geom, L.offsets), P, num_rendered, tmp, s);

@@ -46,8 +46,8 @@ static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a
 
 struct GeomLayout {
     size_t depths, rec, rgb, clamped, cov3D, tiles, rect, order, offsets;  // inspection arrays
-    size_t keys_a, keys_b, vals_b, hist, scan_tmp, stat, total;
-    int sort_blocks;
+    size_t keys_a, keys_b, vals_b, hist, scan_tmp, stat, os_ghist, os_status, total;
+    int sort_blocks, os_tiles;
 };
 struct BinLayout {
     size_t tiles, gidx, ranges;  // inspection arrays (final sorted list)
@@ -69,6 +69,7 @@ struct ImgLayout {
 constexpr int SORT_MIN_ITEMS_PER_BLOCK = 1024;  // 256 threads x 4 rounds (8 rounds above RADIX_SMALL_N items)
 constexpr int64_t RADIX_SMALL_N = 2 * 1024 * 1024;
 constexpr int SORT_MAX_BINS = 256;
+constexpr int ONESWEEP_ITEMS = 2048;  // keys per tile of the depth sort (256 threads x 8)
 
 static inline size_t scan_tmp_bytes(size_t n) { return align_up((n / 2048 + 2) * sizeof(uint32_t) * 2); }
 
@@ -93,7 +94,12 @@ static inline GeomLayout geom_layout(int32_t P)
     L.hist = o;    o += align_up(hist_n * 4);
     size_t big = hist_n > n ? hist_n : n;
     L.scan_tmp = o; o += scan_tmp_bytes(big);
-    L.stat = o;    o += 256;  // {max of ~key, max of key over the live depth keys, -, -}
+    // {max of ~key, max of key over the live depth keys, -, -, tile counters of the four onesweep passes}, then the
+    // four global digit histograms: ONE memset clears both before preprocess
+    L.stat = o;    o += 256;
+    L.os_ghist = o; o += 4 * SORT_MAX_BINS * 4;
+    L.os_tiles = (int)((n + ONESWEEP_ITEMS - 1) / ONESWEEP_ITEMS);
+    L.os_status = o; o += align_up((size_t)4 * L.os_tiles * SORT_MAX_BINS * 4);  // decoupled look-back words
     L.total = o;
     return L;
 }

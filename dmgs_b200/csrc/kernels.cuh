@@ -28,6 +28,13 @@ int launch_exp_array(const float *x, float *y, int64_t n, cudaStream_t s);
 // depth sort that skips digits which do not vary (sort.cu).
 int radix_pass(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b, int64_t n, int pass, int shift,
                int bits, uint32_t *hist, const uint32_t *stat, cudaStream_t s);
+// Stable depth sort of n (key, value) pairs, 8-bit digits, onesweep: one histogram kernel + one kernel per digit
+// with decoupled look-back between the tiles (sort.cu).  ghist (4 x 256 words) and counters (4 words) must be zero
+// on entry (stat != NULL: the caller clears them together with stat before the keys are produced; stat == NULL:
+// cleared here).  Result in (keys_a, vals_a) after an even number of executed passes, else in (keys_b, vals_b);
+// without stat all four passes run (result in A).
+int depth_sort_onesweep(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b, int64_t n,
+                        uint32_t *ghist, uint32_t *counters, uint32_t *status, const uint32_t *stat, cudaStream_t s);
 // out[i] = sum_{j<i} in[gather ? gather[j] : j]; *total = sum of all (may be NULL)
 int exclusive_scan_u32(const uint32_t *in, const uint32_t *gather, uint32_t *out, int64_t n, uint32_t *total,
                        uint32_t *scan_tmp, cudaStream_t s);

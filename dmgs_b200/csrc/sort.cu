@@ -365,6 +365,179 @@ int radix_pass(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *v
     return 0;
 }
 
+// ------------------------------------------------------------------------------ onesweep depth sort
+// The depth sort of the P Gaussians is launch-latency bound (8 MB of keys per pass): three kernels per digit were
+// 9-12 small launches per frame.  Onesweep: ONE kernel builds the global histograms of all four digits (and clears
+// the look-back words), then ONE kernel per digit ranks a 2048-key tile exactly like radix_scatter_kernel and gets
+// the number of equal-digit keys in earlier tiles by decoupled look-back: every tile publishes its per-digit count
+// (AGG) as soon as it is known, then walks back over its predecessors' words until it meets an inclusive PREFIX,
+// and publishes its own.  Tiles are numbered by an atomic counter in the order their blocks START, so every
+// predecessor a block waits for is already running: the spin cannot dead-lock.
+constexpr uint32_t OS_AGG = 1u << 30, OS_PREFIX = 2u << 30, OS_VALUE = (1u << 30) - 1u;
+
+__global__ void __launch_bounds__(RP_THREADS)
+depth_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, const uint32_t *__restrict__ stat,
+                  uint32_t *__restrict__ ghist, uint32_t *__restrict__ status, int ntiles)
+{
+    __shared__ uint32_t h[4][SORT_MAX_BINS];
+    for (int p = 0; p < 4; ++p) {
+        h[p][threadIdx.x] = 0;
+        status[((size_t)p * ntiles + blockIdx.x) * SORT_MAX_BINS + threadIdx.x] = 0;
+    }
+    const uint32_t kmin = stat ? ~stat[0] : 0u;
+    const int64_t base = (int64_t)blockIdx.x * ONESWEEP_ITEMS;
+    uint32_t k[ONESWEEP_ITEMS / RP_THREADS];
+#pragma unroll
+    for (int r = 0; r < ONESWEEP_ITEMS / RP_THREADS; ++r) {
+        const int64_t i = base + (int64_t)r * RP_THREADS + threadIdx.x;
+        k[r] = i < n ? keys[i] : 0xFFFFFFFFu;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < ONESWEEP_ITEMS / RP_THREADS; ++r) {
+        if (base + (int64_t)r * RP_THREADS + threadIdx.x < n) {
+            const uint32_t v = k[r] - kmin;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) atomicAdd(&h[p][(v >> (8 * p)) & 255u], 1u);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const uint32_t c = h[p][threadIdx.x];
+        if (c) atomicAdd(&ghist[p * SORT_MAX_BINS + threadIdx.x], c);
+    }
+}
+
+__global__ void __launch_bounds__(RP_THREADS, SCATTER_MIN_BLOCKS)
+onesweep_pass_kernel(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b, int64_t n, int pass,
+                     int ntiles, const uint32_t *__restrict__ ghist, uint32_t *status, uint32_t *counters,
+                     const uint32_t *__restrict__ stat)
+{
+    const int shift = 8 * pass;
+    const PassSel ps = pass_select(stat, pass, shift);
+    if (!ps.active) return;
+    const uint32_t *__restrict__ keys_in = ps.src ? keys_b : keys_a, *__restrict__ vals_in = ps.src ? vals_b : vals_a;
+    uint32_t *__restrict__ keys_out = ps.src ? keys_a : keys_b, *__restrict__ vals_out = ps.src ? vals_a : vals_b;
+    constexpr int BINS = SORT_MAX_BINS, ROUNDS = ONESWEEP_ITEMS / RP_THREADS, ITEMS = ONESWEEP_ITEMS;
+    __shared__ uint32_t wh[RP_WARPS][BINS];
+    __shared__ uint32_t bin_local[BINS];   // first slot of digit d inside the tile's reordered chunk
+    __shared__ uint32_t bin_global[BINS];  // global position of that slot
+    __shared__ uint32_t skeys[ITEMS];
+    __shared__ uint32_t svals[ITEMS];
+    __shared__ uint32_t s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(&counters[pass], 1u);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int d = threadIdx.x; d < RP_WARPS * BINS; d += RP_THREADS) (&wh[0][0])[d] = 0;
+    __syncthreads();
+    const int tile = (int)s_tile;
+    const uint32_t lt = (1u << lane) - 1u;
+    const int64_t bbase = (int64_t)tile * ITEMS;
+    const int64_t wbase = bbase + (int64_t)w * (ROUNDS * 32) + lane;
+    uint32_t key[ROUNDS], val[ROUNDS], rank[ROUNDS];
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const int64_t i = wbase + r * 32;
+        key[r] = i < n ? keys_in[i] : 0xFFFFFFFFu;
+    }
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const int64_t i = wbase + r * 32;
+        val[r] = i < n ? vals_in[i] : 0u;
+    }
+    // stable rank of every key among the warp's keys with the same digit (see radix_scatter_kernel)
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const bool valid = wbase + r * 32 < n;
+        const uint32_t act = __ballot_sync(0xffffffffu, valid);
+        const uint32_t d = ((key[r] - ps.kmin) >> shift) & 255u;
+        const uint32_t peers = digit_peers<8>(d, act);
+        uint32_t old = 0;
+        if (valid && (peers & lt) == 0) old = atomicAdd(&wh[w][d], (uint32_t)__popc(peers));
+        old = __shfl_sync(0xffffffffu, old, peers ? __ffs(peers) - 1 : 0);
+        rank[r] = old + __popc(peers & lt);
+    }
+    __syncthreads();
+    {
+        const int d = threadIdx.x;  // one digit per thread (RP_THREADS == BINS)
+        uint32_t tot = 0;
+#pragma unroll
+        for (int k = 0; k < RP_WARPS; ++k) {
+            const uint32_t t = wh[k][d];
+            wh[k][d] = tot;
+            tot += t;
+        }
+        // publish, then look back
+        volatile uint32_t *st = status + (size_t)pass * ntiles * BINS;
+        st[(size_t)tile * BINS + d] = (tile == 0 ? OS_PREFIX : OS_AGG) | tot;
+        const uint32_t gtot = ghist[pass * BINS + d];
+        uint32_t dummy;
+        const uint32_t lex = block_excl_scan(tot, &dummy);
+        const uint32_t gex = block_excl_scan(gtot, &dummy);
+        uint32_t excl = 0;
+        if (tile > 0) {
+            // eight predecessors per round trip: all tiles of a small sort start together, so the walk back to the
+            // first inclusive prefix is long and its latency, not its traffic, is what a pass costs
+            bool found = false;
+            for (int t = tile - 1; !found; t -= 8) {
+                uint32_t v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = t - u >= 0 ? (uint32_t)st[(size_t)(t - u) * BINS + d] : (uint32_t)(2u << 30);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (found) break;
+                    uint32_t x = v[u];
+                    while ((x & (OS_AGG | OS_PREFIX)) == 0) x = st[(size_t)(t - u) * BINS + d];
+                    excl += x & OS_VALUE;
+                    found = (x & OS_PREFIX) != 0;
+                }
+            }
+            st[(size_t)tile * BINS + d] = OS_PREFIX | (excl + tot);
+        }
+        bin_local[d] = lex;
+        bin_global[d] = gex + excl;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        if (wbase + r * 32 < n) {
+            const uint32_t d = ((key[r] - ps.kmin) >> shift) & 255u;
+            const uint32_t pos = bin_local[d] + wh[w][d] + rank[r];
+            skeys[pos] = key[r];
+            svals[pos] = val[r];
+        }
+    }
+    __syncthreads();
+    const int count = (int)min((int64_t)ITEMS, n - bbase);
+#pragma unroll 4
+    for (int j = threadIdx.x; j < count; j += RP_THREADS) {
+        const uint32_t k = skeys[j];
+        const uint32_t d = ((k - ps.kmin) >> shift) & 255u;
+        const uint32_t out = bin_global[d] + ((uint32_t)j - bin_local[d]);
+        keys_out[out] = k;
+        vals_out[out] = svals[j];
+    }
+}
+
+int depth_sort_onesweep(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b, int64_t n,
+                        uint32_t *ghist, uint32_t *counters, uint32_t *status, const uint32_t *stat, cudaStream_t s)
+{
+    if (n <= 0) return 0;
+    static_assert(RP_THREADS == SORT_MAX_BINS, "one digit per thread");
+    const int ntiles = (int)((n + ONESWEEP_ITEMS - 1) / ONESWEEP_ITEMS);
+    if (!stat) {
+        DMGS_CUDA(cudaMemsetAsync(ghist, 0, 4 * SORT_MAX_BINS * sizeof(uint32_t), s));
+        DMGS_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(uint32_t), s));
+    }
+    depth_hist_kernel<<<ntiles, RP_THREADS, 0, s>>>(keys_a, n, stat, ghist, status, ntiles);
+    for (int pass = 0; pass < 4; ++pass)
+        onesweep_pass_kernel<<<ntiles, RP_THREADS, 0, s>>>(keys_a, vals_a, keys_b, vals_b, n, pass, ntiles, ghist, status,
+                                                           counters, stat);
+    DMGS_CUDA(cudaGetLastError());
+    count_launches(5);
+    return 0;
+}
+
 // ------------------------------------------------------------------------------ instance emission
 // Load-balanced emission: a warp takes 32 depth-ordered Gaussians whose instances occupy one
 // contiguous output range; lanes walk that range with stride 32 (fully coalesced stores) and find
