@@ -230,7 +230,8 @@ static int bin_forward_impl(const dmgs_params *prm, const void *geom, int64_t R,
                                        at<uint32_t>(geom, GL.stat), at<uint2>(geom, GL.rect),
                                        at<uint4>(binning, BL.srec), at<uint32_t>(binning, BL.table),
                                        at<uint32_t>(binning, BL.gsum), at<uint32_t>(binning, BL.tile_start),
-                                       at<uint2>(binning, BL.ranges), at<uint32_t>(binning, BL.gidx), R, overflow, s);
+                                       at<uint2>(binning, BL.ranges), at<uint32_t>(binning, BL.gidx), R, overflow,
+                                       at<uint32_t>(binning, BL.tile_order), s);
             if (rc) return rc;
         } else {
             DMGS_CUDA(cudaMemsetAsync(at<uint2>(binning, BL.ranges), 0, sizeof(uint2) * (size_t)T, s));

@@ -21,7 +21,7 @@
 namespace dmgs {
 
 __global__ void __launch_bounds__(BLK, FWD_MIN_BLOCKS)
-blend_fwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ ranges,
+blend_fwd_kernel(const __grid_constant__ BlendArgs a, const uint32_t *__restrict__ tile_order, const uint2 *__restrict__ ranges,
                  const uint32_t *__restrict__ gidx, const float4 *__restrict__ rec, const float4 *__restrict__ rgb4,
                  float *__restrict__ out_color, float *__restrict__ final_T, uint32_t *__restrict__ n_contrib)
 {
@@ -29,7 +29,7 @@ blend_fwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
 
     const int lane = threadIdx.x & 31;
     int tile, px0, py0;
-    if (!warp_square(a, tile, px0, py0)) return;
+    if (!warp_square(a, tile_order, tile, px0, py0)) return;
     const int px = px0 + (lane & 7), pya = py0 + (lane >> 3), pyb = pya + 4;
     const bool in_a = px < a.W && pya < a.H, in_b = px < a.W && pyb < a.H;
     if (!__any_sync(0xffffffffu, in_a)) return;  // the whole square lies outside the image
@@ -140,7 +140,7 @@ int launch_blend_fwd(const dmgs_params *prm, const void *geom, const GeomLayout 
     a.gx = (a.W + DMGS_TILE - 1) / DMGS_TILE; a.gy = (a.H + DMGS_TILE - 1) / DMGS_TILE;
     for (int i = 0; i < 3; ++i) a.bg[i] = prm->bg[i];
     if (a.W <= 0 || a.H <= 0) return 0;
-    blend_fwd_kernel<<<blend_grid(a), BLK, 0, s>>>(a, at<uint2>(binning, BL.ranges), at<uint32_t>(binning, BL.gidx),
+    blend_fwd_kernel<<<blend_grid(a), BLK, 0, s>>>(a, BL.has_order ? at<uint32_t>(binning, BL.tile_order) : nullptr, at<uint2>(binning, BL.ranges), at<uint32_t>(binning, BL.gidx),
                                                       at<float4>(geom, GL.rec), at<float4>(geom, GL.rgb), out_color,
                                                       at<float>(image, IL.final_T), at<uint32_t>(image, IL.n_contrib));
     DMGS_CUDA(cudaGetLastError());

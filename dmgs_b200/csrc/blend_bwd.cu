@@ -50,7 +50,7 @@ constexpr uint32_t ACC_ROW = 48u;                       // 9 sums (+3 pad) per l
 constexpr uint32_t ACC_WARP_BYTES = 32u * ACC_ROW;      // 1.5 KB per warp
 
 __global__ void __launch_bounds__(BLK, BWD_MIN_BLOCKS)
-blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ ranges,
+blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint32_t *__restrict__ tile_order, const uint2 *__restrict__ ranges,
                  const uint32_t *__restrict__ gidx, const float4 *__restrict__ rec, const float4 *__restrict__ rgb4,
                  const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
                  const float *__restrict__ dL_dpix, float *__restrict__ grad_blend)
@@ -60,7 +60,7 @@ blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint2 *__restrict__ 
 
     const int lane = threadIdx.x & 31;
     int tile, px0, py0;
-    if (!warp_square(a, tile, px0, py0)) return;
+    if (!warp_square(a, tile_order, tile, px0, py0)) return;
     const int px = px0 + (lane & 7), pya = py0 + (lane >> 3), pyb = pya + 4;
     const bool in_a = px < a.W && pya < a.H, in_b = px < a.W && pyb < a.H;
     const size_t pix_a = (size_t)pya * a.W + px, pix_b = (size_t)pyb * a.W + px, HW = (size_t)a.H * a.W;
@@ -219,7 +219,7 @@ int launch_blend_bwd(const dmgs_params *prm, const void *geom, const GeomLayout 
     a.gx = (a.W + DMGS_TILE - 1) / DMGS_TILE; a.gy = (a.H + DMGS_TILE - 1) / DMGS_TILE;
     for (int i = 0; i < 3; ++i) a.bg[i] = prm->bg[i];
     if (a.W <= 0 || a.H <= 0) return 0;
-    blend_bwd_kernel<<<blend_grid(a), BLK, 0, s>>>(a, at<uint2>(binning, BL.ranges), at<uint32_t>(binning, BL.gidx),
+    blend_bwd_kernel<<<blend_grid(a), BLK, 0, s>>>(a, BL.has_order ? at<uint32_t>(binning, BL.tile_order) : nullptr, at<uint2>(binning, BL.ranges), at<uint32_t>(binning, BL.gidx),
                                                       at<float4>(geom, GL.rec), at<float4>(geom, GL.rgb),
                                                       at<float>(image, IL.final_T), at<uint32_t>(image, IL.n_contrib),
                                                       dL_dpix, grad_blend);

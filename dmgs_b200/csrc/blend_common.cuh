@@ -212,11 +212,14 @@ __device__ __forceinline__ bool cull_rect(float gx, float gy, float A, float B, 
 
 // square sq = 4 * tile + q owns the 8x8 pixels (q & 1, q >> 1) of its tile; lane -> column lane & 7, rows lane >> 3
 // and + 4.  Returns false for the padding warps of the last CTA.
-__device__ __forceinline__ bool warp_square(const BlendArgs &a, int &tile, int &px0, int &py0)
+// tile_order (optional): tiles by descending list length -- the squares of the longest lists are handed out first
+__device__ __forceinline__ bool warp_square(const BlendArgs &a, const uint32_t *__restrict__ tile_order, int &tile,
+                                            int &px0, int &py0)
 {
     const int sq = blockIdx.x * (BLK / 32) + (threadIdx.x >> 5);
     tile = sq >> 2;
     if (tile >= a.gx * a.gy) return false;
+    if (tile_order) tile = (int)tile_order[tile];
     const int ty = tile / a.gx, tx = tile - ty * a.gx, q = sq & 3;
     px0 = tx * DMGS_TILE + (q & 1) * 8;
     py0 = ty * DMGS_TILE + (q >> 1) * 8;

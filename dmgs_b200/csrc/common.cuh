@@ -53,8 +53,9 @@ struct BinLayout {
     size_t tiles, gidx, ranges;  // inspection arrays (final sorted list)
     size_t tiles_b, gidx_b, hist, scan_tmp;  // radix tile partition (sort.cu)
     size_t srec, table, gsum, tile_start;    // direct tile placement (place.cu)
+    size_t tile_order;                       // tiles by descending list length (written with the ranges by place.cu)
     size_t total;
-    int sort_blocks;
+    int sort_blocks, has_order;
 };
 // direct tile placement plan (place.cu): nseg depth-ordered segments of seg Gaussians, one per warp
 struct PlacePlan {
@@ -119,6 +120,8 @@ static inline BinLayout bin_layout(int32_t P, int64_t R, int32_t W, int32_t H)
         L.table = o;      o += align_up((size_t)pl.nseg * T * 4);
         L.gsum = o;       o += align_up((size_t)pl.groups * T * 4);
         L.tile_start = o; o += align_up(T * 4);
+        L.tile_order = o; o += align_up(T * 4);
+        L.has_order = (R > 0 && P > 0) ? 1 : 0;  // the cases in which the placement kernels run (api.cu)
     } else {
         L.tiles_b = o; o += align_up(n * 4);
         L.gidx_b = o;  o += align_up(n * 4);

@@ -48,7 +48,7 @@ int launch_sorted_keys(int64_t R, const uint32_t *sorted_tiles, const uint32_t *
 int launch_tile_placement(const PlacePlan &pl, int P, int T, int gx, const uint32_t *order_a, const uint32_t *order_b,
                           const uint32_t *stat, const uint2 *rect,
                           uint4 *srec, uint32_t *table, uint32_t *gsum, uint32_t *tile_start, uint2 *ranges,
-                          uint32_t *out_gidx, int64_t capacity, uint32_t *overflow, cudaStream_t s);
+                          uint32_t *out_gidx, int64_t capacity, uint32_t *overflow, uint32_t *tile_order, cudaStream_t s);
 int launch_fill_tiles(int T, const uint2 *ranges, uint32_t *sorted_tiles, cudaStream_t s);
 
 // blend.cu

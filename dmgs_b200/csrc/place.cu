@@ -177,11 +177,13 @@ group_scan_kernel(int T, int groups, uint32_t *__restrict__ gsum, uint32_t *__re
 // placed: every range stays (0,0), *overflow receives the total (0 otherwise) and the place kernel exits.
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(int T, uint32_t *__restrict__ tile_start, uint2 *__restrict__ ranges, uint32_t capacity,
-                 uint32_t *__restrict__ overflow)
+                 uint32_t *__restrict__ overflow, uint32_t *__restrict__ tile_order)
 {
     __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t bucket[33];  // tiles per list-length class (class = bit length of the list length)
     const int per = (T + (int)blockDim.x - 1) / (int)blockDim.x;
     const int t0 = threadIdx.x * per, t1 = min(T, t0 + per);
+    if (threadIdx.x < 33) bucket[threadIdx.x] = 0;
     uint32_t local = 0;
     for (int t = t0; t < t1; ++t) local += tile_start[t];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -194,12 +196,21 @@ tile_scan_kernel(int T, uint32_t *__restrict__ tile_start, uint2 *__restrict__ r
     if (threadIdx.x < 32) warp_sums[threadIdx.x] = 0;
     __syncthreads();
     if (lane == 31) warp_sums[w] = incl;
+    for (int t = t0; t < t1; ++t) atomicAdd(&bucket[32 - __clz(tile_start[t])], 1u);
     __syncthreads();
     uint32_t base = 0, total = 0;
     for (int k = 0; k < 32; ++k) {
         if (k < w) base += warp_sums[k];
         total += warp_sums[k];
     }
+    // longest lists first: class c starts after all longer classes (the blend kernels hand the squares of the
+    // tiles out in this order, so the long walks start first and the short ones fill the tail of the grid)
+    uint32_t my_class_base = 0;
+    if (threadIdx.x < 33)
+        for (int c = 32; c > (int)threadIdx.x; --c) my_class_base += bucket[c];
+    __syncthreads();
+    if (threadIdx.x < 33) bucket[threadIdx.x] = my_class_base;
+    __syncthreads();
     const bool fits = total <= capacity;
     if (threadIdx.x == 0 && overflow) *overflow = fits ? 0u : total;
     uint32_t run = base + incl - local;
@@ -208,6 +219,7 @@ tile_scan_kernel(int T, uint32_t *__restrict__ tile_start, uint2 *__restrict__ r
         tile_start[t] = run;
         ranges[t] = (tot && fits) ? make_uint2(run, run + tot) : make_uint2(0u, 0u);
         run += tot;
+        tile_order[atomicAdd(&bucket[32 - __clz(tot)], 1u)] = (uint32_t)t;
     }
 }
 
@@ -312,7 +324,7 @@ int launch_fill_tiles(int T, const uint2 *ranges, uint32_t *sorted_tiles, cudaSt
 int launch_tile_placement(const PlacePlan &pl, int P, int T, int gx, const uint32_t *order_a, const uint32_t *order_b,
                           const uint32_t *stat, const uint2 *rect,
                           uint4 *srec, uint32_t *table, uint32_t *gsum, uint32_t *tile_start, uint2 *ranges,
-                          uint32_t *out_gidx, int64_t capacity, uint32_t *overflow, cudaStream_t s)
+                          uint32_t *out_gidx, int64_t capacity, uint32_t *overflow, uint32_t *tile_order, cudaStream_t s)
 {
     if (once_per_device(ONCE_PLACE)) {
         DMGS_CUDA(cudaFuncSetAttribute(tile_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -327,7 +339,7 @@ int launch_tile_placement(const PlacePlan &pl, int P, int T, int gx, const uint3
     const size_t count_smem = (size_t)pl.wpb * (gx + 1) * (T / gx + 1) * sizeof(uint32_t);  // the difference images
     tile_count_kernel<<<blocks, threads, count_smem, s>>>(P, T, gx, pl.seg, pl.nseg, srec, table, gsum);
     group_scan_kernel<<<(T + 31) / 32, GS_WARPS * 32, 0, s>>>(T, pl.groups, gsum, tile_start);
-    tile_scan_kernel<<<1, 1024, 0, s>>>(T, tile_start, ranges, (uint32_t)capacity, overflow);
+    tile_scan_kernel<<<1, 1024, 0, s>>>(T, tile_start, ranges, (uint32_t)capacity, overflow, tile_order);
     tile_place_kernel<<<blocks, threads, pl.smem, s>>>(P, T, gx, pl.seg, pl.nseg, srec, table, gsum, tile_start, overflow, out_gidx);
     DMGS_CUDA(cudaGetLastError());
     count_launches(5);

@@ -101,6 +101,86 @@ if "c2" in which:
                       "note": "stage times from a second pass with events + sync per step; ms_per_step is the free-running loop"}),
           flush=True)
 
+if "c2f" in which:
+    # the same step on the FUSED path: the binding lives inside preprocess forward / backward
+    # (dmgs_preprocess_forward_bound / _backward_bound): no xyz / cov3D_precomp / dL/dxyz / dL/dcov tensors
+    from dmgs_b200.rasterizer import BoundMesh, rasterize_backward_bound
+    m = S.mesh_bound_inputs(50_000, 6, seed=1)
+    verts = m["verts"].to(dev)
+    faces, bc = m["faces"].to(dev), m["bc"].to(dev)
+    feats = m["features"].to(dev)
+    sf = torch.tensor([m["scale_factor"]], device=dev)
+    P = faces.shape[0] * m["k"]
+    op = torch.full((P, 1), 0.9999, device=dev)
+    W = H = 800
+    cams = [S.nerf_synthetic_camera(i, W, H) for i in range(8)]
+    bg = torch.ones(3, device=dev)
+    sets = [settings(c, bg) for c in cams]
+    gts = [torch.rand(3, H, W, generator=torch.Generator().manual_seed(i)).to(dev) for i in range(8)]
+    opt = FusedAdam([{"params": [verts], "lr": 1e-5, "name": "verts"},
+                     {"params": [feats], "lr": 2.5e-3, "name": "features"},
+                     {"params": [sf], "lr": 1e-3, "name": "scale_factor"}], lr=0.0, eps=1e-15)
+    names = ["render_fwd", "loss_fwd_bwd", "render_bwd", "adam"]
+    acc = {n: 0.0 for n in names}
+    dverts, dg = torch.zeros_like(verts), torch.zeros(1, device=dev)
+
+    def step(i, rec):
+        e = [ev()]
+        g = torch.tanh(sf) * 2.0  # mlp_flex.py:377 (two tiny elementwise kernels)
+        mesh = BoundMesh(verts, faces, bc, m["rad_base"], m["spatial_lr_scale"] * 1e-6, g, True)
+        color, radii, st = rasterize_forward(sets[i % 8], None, op, feats, None, None, None, None, sh_layout=1,
+                                             sh_activation=1, bound=mesh)
+        e.append(ev())
+        _, dL = LU.l1_ssim_loss_and_grad(color, gts[i % 8], 0.2, need_loss=False)
+        e.append(ev())
+        dverts.zero_(); dg.zero_()
+        gm2d, gfe, _, gop = rasterize_backward_bound(st, dL, mesh, feats, False, dverts, dg, verify=False)  # polled below
+        dsf = dg * (1.0 - torch.tanh(sf) ** 2) * 2.0
+        e.append(ev())
+        opt.step(grads={"verts": dverts, "features": gfe, "scale_factor": dsf})
+        e.append(ev())
+        if rec:
+            torch.cuda.synchronize()
+            for n, a, b in zip(names, e[:-1], e[1:]):
+                acc[n] += a.elapsed_time(b)
+        return st
+
+    for i in range(5):
+        step(i, False)
+    dmgs_b200.check_async()
+    torch.cuda.synchronize()
+    N = 24
+    t0 = ev()
+    for i in range(N):
+        st = step(i, False)
+    t1 = ev()
+    torch.cuda.synchronize()
+    total = t0.elapsed_time(t1) / N
+    for i in range(N):
+        step(i, True)
+    ok = dmgs_b200.check_async()
+    if os.environ.get("DMGS_HOST_PROFILE"):
+        import cProfile, pstats, io, time
+        torch.cuda.synchronize()
+        t_ = time.perf_counter()
+        for i in range(N):
+            step(i, False)
+        host_ms = (time.perf_counter() - t_) / N * 1e3
+        torch.cuda.synchronize()
+        pr = cProfile.Profile(); pr.enable()
+        for i in range(N):
+            step(i, False)
+        pr.disable(); torch.cuda.synchronize()
+        sio = io.StringIO(); pstats.Stats(pr, stream=sio).sort_stats("tottime").print_stats(28)
+        print("host ms per step (enqueue only): %.3f" % host_ms, file=sys.stderr)
+        print(sio.getvalue()[:6000], file=sys.stderr)
+    print(json.dumps({"config": "c2 fused: stage-2 training step, binding inside preprocess fwd/bwd (F=%d, k=6, P=%d), 800x800, "
+                                "fused sigmoid-SH, L1+SSIM loss, Adam" % (faces.shape[0], P),
+                      "ms_per_step": round(total, 4), "steps_per_s": round(1e3 / total, 1),
+                      "stage_ms": {n: round(acc[n] / N, 4) for n in names}, "R": st.num_rendered, "binning_fit": ok,
+                      "note": "stage times from a second pass with events + sync per step; ms_per_step is the free-running loop"}),
+          flush=True)
+
 if "c5" in which:
     with torch.no_grad():
         for (W, H) in [(800, 800), (1920, 1080)]:
