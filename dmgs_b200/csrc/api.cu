@@ -477,6 +477,33 @@ int dmgs_adam_step(int32_t nseg, const dmgs_adam_segment *segments_host, double 
     return launch_adam(nseg, segments_host, beta1, beta2, eps, step, grad_scale, zero_grad, (cudaStream_t)stream);
 }
 
+int64_t dmgs_texture_grid_params(void) { return texture_grid_params(); }
+
+int dmgs_texture_cast_params(int64_t n_params, const float *params, void *params_half, void *stream)
+{
+    if (n_params != texture_grid_params()) { set_error("texture: the hash grid holds %lld parameters, got %lld", (long long)texture_grid_params(), (long long)n_params); return -14; }
+    if (!params || !params_half) { set_error("texture: NULL required pointer"); return -6; }
+    return launch_texture_cast(n_params, params, params_half, (cudaStream_t)stream);
+}
+
+int dmgs_texture_forward(int64_t N, int32_t channels, const float *aabb6_host, const float *xyz, const void *grid_half,
+                         const float *W0, const float *W1, const float *W2, float *out, void *enc_out, void *stream)
+{
+    if (N > 0 && (!aabb6_host || !xyz || !grid_half || !W0 || !W1 || !W2 || !out)) { set_error("texture: NULL required pointer"); return -6; }
+    if (!aabb6_host) { set_error("texture: NULL AABB"); return -6; }
+    return launch_texture_fwd(N, channels, aabb6_host, xyz, grid_half, W0, W1, W2, out, enc_out, (cudaStream_t)stream);
+}
+
+int dmgs_texture_backward(int64_t N, int32_t channels, const float *aabb6_host, const float *xyz, const void *grid_half,
+                          const void *enc, const float *W0, const float *W1, const float *W2, const float *dL_dout,
+                          float grid_grad_scale, float *d_grid, float *dW0, float *dW1, float *dW2, float *d_xyz, void *stream)
+{
+    if (!aabb6_host) { set_error("texture: NULL AABB"); return -6; }
+    if (N > 0 && (!xyz || !grid_half || !enc || !W0 || !W1 || !W2 || !dL_dout || !dW0 || !dW1 || !dW2)) { set_error("texture: NULL required pointer"); return -6; }
+    return launch_texture_bwd(N, channels, aabb6_host, xyz, grid_half, enc, W0, W1, W2, dL_dout, grid_grad_scale, d_grid,
+                              dW0, dW1, dW2, d_xyz, (cudaStream_t)stream);
+}
+
 int dmgs_allreduce_peer(int64_t n, int32_t world, int32_t rank, const void *const *peer_ptrs_host, void *multicast_ptr,
                         float scale, void *stream)
 {

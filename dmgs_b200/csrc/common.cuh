@@ -28,7 +28,7 @@ void count_launches(int n);  // kernels launched by this library (bench.py repor
 // Per-DEVICE launch state (a process may drive several GPUs): multiprocessor count of the current device
 // (DMGS_DEFAULT_SMS when none can be queried) and a once-per-device latch for the cudaFuncSetAttribute opt-ins.
 int num_sms();
-enum { ONCE_PREPROCESS_FWD = 0, ONCE_PREPROCESS_BWD, ONCE_SH_EXPAND, ONCE_PLACE, ONCE_BIND_FUSED, ONCE_SLOTS };
+enum { ONCE_PREPROCESS_FWD = 0, ONCE_PREPROCESS_BWD, ONCE_SH_EXPAND, ONCE_PLACE, ONCE_BIND_FUSED, ONCE_TEXTURE_BWD, ONCE_SLOTS };
 bool once_per_device(int slot);
 
 #define DMGS_CUDA(call)                                                              \

@@ -90,6 +90,15 @@ int launch_adam(int nseg, const dmgs_adam_segment *segs, double beta1, double be
 int launch_allreduce_peer(int64_t n, int world, int rank, const void *const *peer_ptrs_host, void *multicast_ptr,
                           float scale, cudaStream_t s);
 
+// texture.cu
+int64_t texture_grid_params();
+int launch_texture_cast(int64_t n_params, const float *params, void *params_half, cudaStream_t s);
+int launch_texture_fwd(int64_t N, int C, const float *aabb6_host, const float *xyz, const void *grid_half, const float *W0,
+                       const float *W1, const float *W2, float *out, void *enc_out, cudaStream_t s);
+int launch_texture_bwd(int64_t N, int C, const float *aabb6_host, const float *xyz, const void *grid_half, const void *enc,
+                       const float *W0, const float *W1, const float *W2, const float *dL_dout, float grid_grad_scale,
+                       float *d_grid, float *dW0, float *dW1, float *dW2, float *d_xyz, cudaStream_t s);
+
 // binding.cu
 int launch_bind_fwd(int64_t F, int k, const float *verts, const int64_t *faces, const float *bc, float rad_base,
                     float thin_z, const float *g, int adaptive, float *xyz, float *cov6, float *rot_t2w, cudaStream_t s);

@@ -229,6 +229,26 @@ typedef struct dmgs_adam_segment {
 int dmgs_adam_step(int32_t nseg, const dmgs_adam_segment *segments_host, double beta1, double beta2, double eps,
                    int64_t step, float grad_scale, int32_t zero_grad, void *stream);
 
+/* ---- stage-2 colour field: multiresolution hash-grid encoding + bias-free MLP (replaces
+ *      geo/texture.py:99-111 `MLPTexture3D.sample_noact`, i.e. tinycudann's HashGrid encoder [16 levels x 2 features,
+ *      2^19 entries per level, base resolution 16, finest 4096; geo/texture.py:50-72] followed by the reference's
+ *      torch `_MLP` [Linear(32,32) ReLU Linear(32,32) ReLU Linear(32,channels), no bias; geo/texture.py:18-41];
+ *      consumer scene/gaussian_geo_model_mlp_flex.py:313).
+ * grid: dmgs_texture_grid_params() fp32 parameters (level-major, entry, feature), which the kernels read through an
+ * fp16 copy made by dmgs_texture_cast_params (the encoder's parameters and output are fp16 in the reference).
+ * forward: xyz [N,3] -> out [N,channels] (channels a multiple of 4, <= 64); enc_out (optional, N*32 halfs) keeps the
+ * encoder output for the backward.  backward: dW0/dW1/dW2 and d_grid (optional) are ADDED to (the caller zeroes
+ * them); d_grid is multiplied by grid_grad_scale (the net effect of the reference's two backward hooks is 128 on
+ * the encoder parameters and 1 everywhere else, geo/texture.py:30-31, :69-71); d_xyz (optional, [N,3]) is written.
+ * aabb6_host: HOST array {min x,y,z, max x,y,z}; coordinates are normalised and clamped to [0,1] (:102-103). */
+int64_t dmgs_texture_grid_params(void);
+int dmgs_texture_cast_params(int64_t n_params, const float *params, void *params_half, void *stream);
+int dmgs_texture_forward(int64_t N, int32_t channels, const float *aabb6_host, const float *xyz, const void *grid_half,
+                         const float *W0, const float *W1, const float *W2, float *out, void *enc_out, void *stream);
+int dmgs_texture_backward(int64_t N, int32_t channels, const float *aabb6_host, const float *xyz, const void *grid_half,
+                          const void *enc, const float *W0, const float *W1, const float *W2, const float *dL_dout,
+                          float grid_grad_scale, float *d_grid, float *dW0, float *dW1, float *dW2, float *d_xyz, void *stream);
+
 /* ---- all-reduce (sum) of a flat fp32 buffer over NVLink peer memory (view-partitioned training step:
  *      the per-Gaussian gradient exchange; replaces ncclAllReduce on one box).
  * Every rank passes the same-sized buffer of n floats (n % 4 == 0, 16-byte aligned), mapped into every

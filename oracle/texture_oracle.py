@@ -66,8 +66,15 @@ def _ste_half(x):
     return x + (x.detach().half().to(x.dtype) - x.detach())
 
 
-def encode(t, grid, half=True):
-    """t [N,3] in [0,1] -> [N,32].  grid: flat [n_params] (level-major, then cell, then feature)."""
+def _ste_f32(x):
+    return x + (x.detach().float().to(x.dtype) - x.detach())
+
+
+def encode(t, grid, half=True, f32_coords=False):
+    """t [N,3] in [0,1] -> [N,32].  grid: flat [n_params] (level-major, then cell, then feature).
+    f32_coords (t in float64): the cell position is rounded to fp32 as `fmaf(scale, t, 0.5)` gives it -- at the finest
+    level one fp32 ulp of the position is 2.4e-4 of a cell, which moves the trilinear weights far more than fp32
+    arithmetic anywhere else does."""
     scales, res, offs = level_table()
     N = t.shape[0]
     dt = t.dtype
@@ -78,6 +85,8 @@ def encode(t, grid, half=True):
         hsize = int(offs[l + 1] - offs[l])
         r = int(res[l])
         pos = t * s + 0.5  # fmaf(scale, x, 0.5)
+        if f32_coords:
+            pos = _ste_f32(pos)
         pg = torch.floor(pos.detach())
         w = pos - pg
         pgi = pg.to(torch.int64)
@@ -113,12 +122,16 @@ def encode(t, grid, half=True):
     return _ste_half(enc) if half else enc
 
 
-def sample_noact(xyz, aabb, grid, ws, half=True):
+def sample_noact(xyz, aabb, grid, ws, half=True, f32_coords=False):
     """geo/texture.py:99-111.  xyz [N,3]; aabb [2,3]; -> [N, C].  Gradients: true ones (multiply grid.grad by
-    GRAD_SCALE to get what the reference's hooks hand to its optimiser)."""
-    t = (xyz - aabb[0][None]) / (aabb[1][None] - aabb[0][None])
+    GRAD_SCALE to get what the reference's hooks hand to its optimiser).  f32_coords: see `encode` (the normalised
+    coordinate is rounded to fp32 too, as the reference's fp32 tensors are)."""
+    if f32_coords:  # every fp32 operation of (x - lo) / (hi - lo) rounds on its own
+        t = _ste_f32(_ste_f32(xyz - aabb[0][None]) / _ste_f32(aabb[1][None] - aabb[0][None]))
+    else:
+        t = (xyz - aabb[0][None]) / (aabb[1][None] - aabb[0][None])
     t = torch.clamp(t, min=0, max=1)
-    x = encode(t, grid, half)
+    x = encode(t, grid, half, f32_coords)
     h = torch.relu(torch.nn.functional.linear(x, ws[0]))
     h = torch.relu(torch.nn.functional.linear(h, ws[1]))
     return torch.nn.functional.linear(h, ws[2])

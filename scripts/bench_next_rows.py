@@ -109,3 +109,35 @@ n = sum(params[k].numel() for k in names)
 line(f"adam step {n} parameters (1 M Gaussians, SH-3)", timed(ours, flush=False), n * 32, timed(ref, flush=False),
      "32 B per parameter (p, g, m, v read; p, m, v, g=0 written); working set 944 MB >> L2, no flush; torch side = "
      "torch.optim.Adam (its default foreach path) + grad.zero_()")
+
+# ---- stage-2 colour field: hash-grid encoder + MLP at every Gaussian centre (C2: 491 520 points, 48 channels)
+if "texture" in sys.argv or len(sys.argv) == 1:
+    from dmgs_b200.texture import MLPTexture3D
+    N, Cc = 491_520, 48
+    aabb = torch.tensor([[-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]], device=dev)
+    tex = MLPTexture3D(aabb, channels=Cc)
+    with torch.no_grad():
+        tex.encoder.params.mul_(500.0)
+    pts = (torch.rand(N, 3, device=dev) * 2 - 1).requires_grad_()
+    dLt = torch.randn(N, Cc, device=dev)
+    def fwd():
+        with torch.no_grad():
+            return tex.sample_noact(pts)
+    def fwd_bwd():
+        for p_ in tex.parameters():
+            p_.grad = None
+        pts.grad = None
+        tex.sample_noact(pts).backward(dLt)
+    t_f, t_fb = timed(fwd), timed(fwd_bwd)
+    n_par = tex.encoder.params.numel()
+    print(json.dumps({"row": f"hash-grid texture sample_noact, {N} points x {Cc} channels (16 levels x 8 corners, MLP 32-32-32-{Cc})",
+                      "forward_ms": round(t_f, 4), "forward_backward_ms": round(t_fb, 4),
+                      "algorithmic": {"gathers_per_point": 128, "mlp_fma_per_point": 32 * 32 * 2 + 32 * Cc,
+                                      "bytes_forward": N * (12 + 4 * Cc + 64) + n_par * (4 + 2),
+                                      "note": "forward: xyz 12 B + output 192 B + saved encoding 64 B per point, the fp32->fp16 "
+                                              "cast of the 12.6 M table parameters (73 MB) and 128 four-byte gathers per point that "
+                                              "hit the L2-resident 24 MB fp16 table; backward adds 128 eight-byte reductions per "
+                                              "point into the fp32 gradient table and a 50 MB memset of it"},
+                      "forward_GFMA_per_s": round(N * (32 * 32 * 2 + 32 * Cc) / (t_f * 1e-3) / 1e9, 1),
+                      "torch_ms": None, "torch_note": "the reference runs tinycudann here, which is not in this image: no op-by-op "
+                                                      "comparator"}), flush=True)

@@ -25,13 +25,26 @@ if out_path:
 dev = torch.device("cuda", 0)
 res = {}
 for name in args or ["h0"]:
-    P, W, H, kind, extent, lsm = WORKLOADS[name]
-    cl = S.random_cloud(P, seed=0, extent=extent, log_scale_mean=lsm)
-    d = {k: v.to(dev) for k, v in cl.items()}
-    c = make_camera(kind, 0, W, H).to(dev)
-    st_ = GaussianRasterizationSettings(H, W, math.tan(c.FoVx / 2), math.tan(c.FoVy / 2), torch.zeros(3, device=dev), 1.0,
-                                        c.world_view_transform, c.full_proj_transform, 3, c.camera_center, False, False)
-    color, radii, st = rasterize_forward(st_, d["means3D"], d["opacities"], d["shs"], None, d["scales"], d["rotations"], None)
+    if name == "c2":  # mesh-bound stage-2 cloud (scripts/bench_configs.py c2): ~490 k small Gaussians on a sphere mesh
+        from dmgs_b200.binding import bind_faces
+        m = S.mesh_bound_inputs(50_000, 6, seed=1)
+        W = H = 800
+        c = S.nerf_synthetic_camera(0, W, H).to(dev)
+        xyz, cov = bind_faces(m["verts"].to(dev), m["faces"].to(dev), m["bc"].to(dev), m["rad_base"],
+                              m["spatial_lr_scale"] * 1e-6, torch.tensor([m["scale_factor"]], device=dev), 2.0)
+        P = xyz.shape[0]
+        st_ = GaussianRasterizationSettings(H, W, math.tan(c.FoVx / 2), math.tan(c.FoVy / 2), torch.ones(3, device=dev), 1.0,
+                                            c.world_view_transform, c.full_proj_transform, 3, c.camera_center, False, False)
+        color, radii, st = rasterize_forward(st_, xyz.detach(), torch.full((P, 1), 0.9999, device=dev), m["features"].to(dev),
+                                             None, None, None, cov.detach(), sh_layout=1, sh_activation=1)
+    else:
+        P, W, H, kind, extent, lsm = WORKLOADS[name]
+        cl = S.random_cloud(P, seed=0, extent=extent, log_scale_mean=lsm)
+        d = {k: v.to(dev) for k, v in cl.items()}
+        c = make_camera(kind, 0, W, H).to(dev)
+        st_ = GaussianRasterizationSettings(H, W, math.tan(c.FoVx / 2), math.tan(c.FoVy / 2), torch.zeros(3, device=dev), 1.0,
+                                            c.world_view_transform, c.full_proj_transform, 3, c.camera_center, False, False)
+        color, radii, st = rasterize_forward(st_, d["means3D"], d["opacities"], d["shs"], None, d["scales"], d["rotations"], None)
     g, b, im = st.geom_arrays(), st.binning_arrays(), st.image_arrays()
     out = torch.zeros(24, dtype=torch.int64, device=dev)
     rc = lib.blend_stats(W, H, b["ranges"].data_ptr(), b["gidx"].data_ptr(), g["rec"].data_ptr(),
@@ -50,6 +63,12 @@ for name in args or ["h0"]:
                       "lanes_hit_per_surviving_pair": hits / max(surv, 1) / px,
                       "lanes_hit_per_hit_pair": hits / max(surv_hit, 1) / px}
         assert surv_hit == anyhit, "cull_rect dropped a contributing pair"
+    rg = b["ranges"].long()
+    lens = (rg[:, 1] - rg[:, 0]).float()
+    row["list_len"] = {"mean": lens.mean().item(), "p50": lens.median().item(), "p99": lens.quantile(0.99).item(),
+                       "max": lens.max().item()}
+    nc = im["n_contrib"].float()
+    row["n_contrib"] = {"mean": nc.mean().item(), "p99": nc.flatten().quantile(0.99).item(), "max": nc.max().item()}
     res[name] = row
     print(name, json.dumps(row))
 if out_path:
