@@ -415,7 +415,10 @@ def run_ours(args):
     #                    autograd accumulating .grad over the views of the step
     #   "training_step": dmgs_b200.multiview (ViewStreams + accumulate_view over the C ABI) -- the same call
     #                    sequence as the `value` region, plus the copies and the loss
-    staged = MV.StagedInputs(host, dev)
+    # N > 1: the inputs are replicated, so every rank copies 1/N of every tensor over PCIe and the pieces are
+    # all-gathered over NVLink on the copy stream (its own communicator: never queued behind the gradient exchange)
+    stage_group = dist.new_group() if world > 1 else None
+    staged = MV.StagedInputs(host, dev, group=stage_group)
 
     def e2e_step_module(i, last):
         slot = i & 1
@@ -492,6 +495,13 @@ def run_ours(args):
     e2e_module = time_e2e(e2e_step_module) if full else None
     e2e_training = time_e2e(e2e_step_training) if full else None
     h2d = staged.bytes_per_step
+    # what the staging delivered must be the resident copy, bit for bit (sharded copy + all-gather at N > 1)
+    torch.cuda.synchronize()
+    staged_ok = all(bool(torch.equal(staged.dev[s_][k], d[k])) for s_ in range(2) for k in names) if full else None
+    if world > 1 and full:
+        ok_t = torch.tensor([1.0 if staged_ok else 0.0], device=dev)
+        dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+        staged_ok = bool(ok_t.item() > 0.5)
 
     if rank != 0:
         if world > 1:
@@ -587,7 +597,12 @@ def run_ours(args):
                 "read back every step",
                 "training_step": e2e_training,
                 "training_step_api": "dmgs_b200.multiview training step (ViewStreams + accumulate_view over the C ABI), "
-                                     "same copies and read-back"},
+                                     "same copies and read-back",
+                "staging": ("every rank copies 1/N of every (replicated) input tensor from pinned host memory, the pieces "
+                            "are all-gathered over NVLink on the copy stream; h2d_bytes_per_step is per rank" if world > 1
+                            else "all inputs copied from pinned host memory on a copy stream, double-buffered"),
+                "h2d_bytes_per_step_all_ranks": int(sum(v.numel() * v.element_size() for v in host.values())) if world > 1 else h2d,
+                "staged_equals_resident": staged_ok},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if mgpu is not None:

@@ -305,6 +305,16 @@ def accumulate_view(settings, inputs: Dict[str, Optional[torch.Tensor]], image_g
     return loss, color, radii
 
 
+def shard_rows(n_rows: int, world: int, rank: int) -> Tuple[int, int, int]:
+    """Row range [lo, hi) of an [n_rows, ...] tensor that `rank` stages, and the per-rank chunk (rows, the same on
+    every rank: all-gather needs equal pieces, so the last chunks may be short or empty)."""
+    if not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside world of {world}")
+    chunk = (n_rows + world - 1) // world
+    lo = min(rank * chunk, n_rows)
+    return lo, min(lo + chunk, n_rows), chunk
+
+
 class StagedInputs:
     """Double-buffered host -> device staging of a step's inputs on a side stream.
 
@@ -313,22 +323,45 @@ class StagedInputs:
     returns the device tensors; `release(slot)` marks the buffers free once the compute stream has
     consumed them.  With two slots the copy of step i+1 overlaps the kernels of step i (PCIe and the
     SMs are independent engines), so a training loop whose inputs arrive from the host every step is
-    not serialised behind the H2D transfer."""
+    not serialised behind the H2D transfer.
 
-    def __init__(self, host: Dict[str, torch.Tensor], device, slots: int = 2):
+    group (ranks of ONE box holding identical host tensors -- the replicated Gaussians of the view-partitioned
+    step): every rank copies only its 1/N row range of every tensor over PCIe and the pieces are all-gathered
+    in place over NVLink (`dist.all_gather_into_tensor` on the copy stream), so the box moves the inputs
+    over its host links once per step instead of once per rank."""
+
+    def __init__(self, host: Dict[str, torch.Tensor], device, slots: int = 2, group=None):
         self.host = host
-        self.dev = [{k: torch.empty(v.shape, dtype=v.dtype, device=device) for k, v in host.items()} for _ in range(slots)]
+        self.group = group
+        self.world = dist.get_world_size(group) if group is not None else 1
+        self.rank = dist.get_rank(group) if group is not None else 0
+        self.dev, self._full, self.plan = [], [], {}
+        for k, v in host.items():
+            self.plan[k] = shard_rows(v.shape[0], self.world, self.rank)
+        for _ in range(slots):
+            full = {k: torch.empty((self.plan[k][2] * self.world,) + tuple(v.shape[1:]), dtype=v.dtype, device=device)
+                    for k, v in host.items()}
+            self._full.append(full)  # padded to world equal chunks; the tensors handed out are the first n_rows
+            self.dev.append({k: full[k][:v.shape[0]] for k, v in host.items()})
         self.copy_stream = torch.cuda.Stream(device=device)
         self.ready: List[Optional[torch.cuda.Event]] = [None] * slots
         self.freed: List[Optional[torch.cuda.Event]] = [None] * slots
-        self.bytes_per_step = sum(v.numel() * v.element_size() for v in host.values())
+        # bytes this rank copies host -> device per step
+        self.bytes_per_step = sum((self.plan[k][1] - self.plan[k][0]) * (v[0].numel() if v.shape[0] else 0) * v.element_size()
+                                  for k, v in host.items())
 
     def prefetch(self, slot: int):
         with torch.cuda.stream(self.copy_stream):
             if self.freed[slot] is not None:
                 self.copy_stream.wait_event(self.freed[slot])
             for k, v in self.host.items():
-                self.dev[slot][k].copy_(v, non_blocking=True)
+                lo, hi, chunk = self.plan[k]
+                if hi > lo:
+                    self._full[slot][k][lo:hi].copy_(v[lo:hi], non_blocking=True)
+            if self.world > 1:
+                for k in self.host:
+                    chunk, full = self.plan[k][2], self._full[slot][k]
+                    dist.all_gather_into_tensor(full, full[self.rank * chunk:(self.rank + 1) * chunk], group=self.group)
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
             self.ready[slot] = ev

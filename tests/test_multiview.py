@@ -96,3 +96,21 @@ def test_two_ranks_equal_one_rank(tmp_path):
     assert np.linalg.norm(f0 - ref) <= 1e-5 * np.linalg.norm(ref)
     l0, l1 = float(np.load(tmp_path / "loss0.npy")), float(np.load(tmp_path / "loss1.npy"))
     assert l0 == l1 and abs(l0 - float(loss)) <= 1e-4 * abs(float(loss))
+
+
+def test_shard_rows_cover_every_row_once():
+    """StagedInputs at N > 1: equal chunks (all-gather), every row staged by exactly one rank, ragged tails."""
+    from dmgs_b200.multiview import shard_rows
+    for n in (0, 1, 7, 8, 1000, 1_000_003):
+        for world in (1, 2, 3, 8):
+            seen = 0
+            chunks = set()
+            for r in range(world):
+                lo, hi, chunk = shard_rows(n, world, r)
+                assert 0 <= lo <= hi <= n and hi - lo <= chunk
+                assert lo == min(r * chunk, n)
+                seen += hi - lo
+                chunks.add(chunk)
+            assert seen == n and len(chunks) == 1 and chunks.pop() * world >= n
+    with pytest.raises(ValueError):
+        shard_rows(10, 2, 2)
