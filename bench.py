@@ -272,7 +272,7 @@ def run_ours(args):
             events.append((name, e))
         return hook
 
-    stats = {"R": 0, "frames": 0, "redone": 0}
+    stats = {"R": 0, "frames": 0, "redone": 0, "host_s": 0.0}
     r_dev = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(N_STREAMS)]
 
     def one_view(j, v, record, acc):
@@ -298,6 +298,7 @@ def run_ours(args):
     def step(record, single=False, exchange=True):
         # single=True: every view on the current stream into the first accumulator (the stage-timing steps
         # after the timed region; record=True puts CUDA events between the stages)
+        th = time.perf_counter()
         if single:
             vs.begin()
             for j, v in enumerate(my_views):
@@ -311,6 +312,7 @@ def run_ours(args):
             vs.finish(d["means3D"], d["shs"], 3)
         if world > 1 and exchange:
             vs.all_reduce_()
+        stats["host_s"] += time.perf_counter() - th  # host time to ENQUEUE the step (no synchronisation so far)
         if not dmgs_b200.check_async():  # a frame overflowed its binning buffer: the step does not count
             stats["redone"] += 1
             if record:
@@ -321,7 +323,7 @@ def run_ours(args):
     for _ in range(Wm):
         step(False)
     torch.cuda.synchronize()
-    stats.update(R=0, frames=0, redone=0)
+    stats.update(R=0, frames=0, redone=0, host_s=0.0)
     for t in r_dev:
         t.zero_()
     launches0 = lib.dmgs_launch_count()
@@ -350,6 +352,7 @@ def run_ours(args):
         dist.all_reduce(lt)
         launches = int(lt.item())
     frames_timed, redone_timed = stats["frames"], stats["redone"]
+    host_enqueue_ms = 1e3 * stats["host_s"] / max(K, 1)
 
     # ---- multi-GPU correctness, outside the timed region (driver-visible: keys of the JSON line)
     mgpu = None
@@ -603,7 +606,7 @@ def run_ours(args):
                             else "all inputs copied from pinned host memory on a copy stream, double-buffered"),
                 "h2d_bytes_per_step_all_ranks": int(sum(v.numel() * v.element_size() for v in host.values())) if world > 1 else h2d,
                 "staged_equals_resident": staged_ok},
-        "gpu_launches": int(launches), "clocks": clocks,
+        "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_enqueue_ms, 3), "clocks": clocks,
     }
     if mgpu is not None:
         line.update(mgpu)

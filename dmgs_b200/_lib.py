@@ -65,7 +65,8 @@ _SIGS = {
     "dmgs_texture_grid_params": (_i64, []),
     "dmgs_texture_cast_params": (C.c_int, [_i64, _vp, _vp, _vp]),
     "dmgs_texture_forward": (C.c_int, [_i64, _i32, C.POINTER(_f)] + [_vp] * 8),
-    "dmgs_texture_backward": (C.c_int, [_i64, _i32, C.POINTER(_f)] + [_vp] * 7 + [_f] + [_vp] * 6),
+    "dmgs_texture_backward": (C.c_int, [_i64, _i32, C.POINTER(_f)] + [_vp] * 7 + [_f] + [_vp] * 7),
+    "dmgs_texture_backward_scratch_bytes": (C.c_size_t, [_i64]),
     "dmgs_allreduce_peer": (C.c_int, [_i64, _i32, _i32, C.POINTER(C.c_void_p), _vp, _f, _vp]),
     "dmgs_geom_layout": (C.c_int, [_i32, C.POINTER(_i64)]),
     "dmgs_binning_layout": (C.c_int, [_i32, _i64, _i32, _i32, C.POINTER(_i64)]),

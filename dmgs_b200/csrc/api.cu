@@ -496,13 +496,16 @@ int dmgs_texture_forward(int64_t N, int32_t channels, const float *aabb6_host, c
 
 int dmgs_texture_backward(int64_t N, int32_t channels, const float *aabb6_host, const float *xyz, const void *grid_half,
                           const void *enc, const float *W0, const float *W1, const float *W2, const float *dL_dout,
-                          float grid_grad_scale, float *d_grid, float *dW0, float *dW1, float *dW2, float *d_xyz, void *stream)
+                          float grid_grad_scale, float *d_grid, float *dW0, float *dW1, float *dW2, float *d_xyz,
+                          void *scratch, void *stream)
 {
     if (!aabb6_host) { set_error("texture: NULL AABB"); return -6; }
-    if (N > 0 && (!xyz || !grid_half || !enc || !W0 || !W1 || !W2 || !dL_dout || !dW0 || !dW1 || !dW2)) { set_error("texture: NULL required pointer"); return -6; }
+    if (N > 0 && (!xyz || !grid_half || !enc || !W0 || !W1 || !W2 || !dL_dout || !dW0 || !dW1 || !dW2 || !scratch)) { set_error("texture: NULL required pointer"); return -6; }
     return launch_texture_bwd(N, channels, aabb6_host, xyz, grid_half, enc, W0, W1, W2, dL_dout, grid_grad_scale, d_grid,
-                              dW0, dW1, dW2, d_xyz, (cudaStream_t)stream);
+                              dW0, dW1, dW2, d_xyz, scratch, (cudaStream_t)stream);
 }
+
+size_t dmgs_texture_backward_scratch_bytes(int64_t N) { return texture_bwd_scratch_bytes(N); }
 
 int dmgs_allreduce_peer(int64_t n, int32_t world, int32_t rank, const void *const *peer_ptrs_host, void *multicast_ptr,
                         float scale, void *stream)

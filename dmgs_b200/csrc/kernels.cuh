@@ -97,7 +97,8 @@ int launch_texture_fwd(int64_t N, int C, const float *aabb6_host, const float *x
                        const float *W1, const float *W2, float *out, void *enc_out, cudaStream_t s);
 int launch_texture_bwd(int64_t N, int C, const float *aabb6_host, const float *xyz, const void *grid_half, const void *enc,
                        const float *W0, const float *W1, const float *W2, const float *dL_dout, float grid_grad_scale,
-                       float *d_grid, float *dW0, float *dW1, float *dW2, float *d_xyz, cudaStream_t s);
+                       float *d_grid, float *dW0, float *dW1, float *dW2, float *d_xyz, void *scratch, cudaStream_t s);
+size_t texture_bwd_scratch_bytes(int64_t N);
 
 // binding.cu
 int launch_bind_fwd(int64_t F, int k, const float *verts, const int64_t *faces, const float *bc, float rad_base,

@@ -88,10 +88,11 @@ class _SampleNoAct(torch.autograd.Function):
         d_grid = torch.zeros(n_params, dtype=torch.float32, device=dev) if need_grid else None
         dW = [torch.zeros_like(t) for t in (W0, W1, W2)]
         d_xyz = torch.empty(N, 3, dtype=torch.float32, device=dev) if need_xyz else None
+        scratch = torch.empty(int(L.lib().dmgs_texture_backward_scratch_bytes(N)), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             L.check(L.lib().dmgs_texture_backward(N, Cc, aabb6, L.ptr(x), L.ptr(grid_half), L.ptr(enc), L.ptr(W0), L.ptr(W1),
                                                   L.ptr(W2), L.ptr(g), gscale, L.ptr(d_grid), L.ptr(dW[0]), L.ptr(dW[1]),
-                                                  L.ptr(dW[2]), L.ptr(d_xyz), _stream(dev)), "dmgs_texture_backward")
+                                                  L.ptr(dW[2]), L.ptr(d_xyz), L.ptr(scratch), _stream(dev)), "dmgs_texture_backward")
         return d_xyz, d_grid, dW[0], dW[1], dW[2], None, None, None
 
 

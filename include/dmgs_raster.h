@@ -239,7 +239,8 @@ int dmgs_adam_step(int32_t nseg, const dmgs_adam_segment *segments_host, double 
  * forward: xyz [N,3] -> out [N,channels] (channels a multiple of 4, <= 64); enc_out (optional, N*32 halfs) keeps the
  * encoder output for the backward.  backward: dW0/dW1/dW2 and d_grid (optional) are ADDED to (the caller zeroes
  * them); d_grid is multiplied by grid_grad_scale (the net effect of the reference's two backward hooks is 128 on
- * the encoder parameters and 1 everywhere else, geo/texture.py:30-31, :69-71); d_xyz (optional, [N,3]) is written.
+ * the encoder parameters and 1 everywhere else, geo/texture.py:30-31, :69-71); d_xyz (optional, [N,3]) is written;
+ * scratch: dmgs_texture_backward_scratch_bytes(N) bytes (dL/d(encoding) between the two backward kernels).
  * aabb6_host: HOST array {min x,y,z, max x,y,z}; coordinates are normalised and clamped to [0,1] (:102-103). */
 int64_t dmgs_texture_grid_params(void);
 int dmgs_texture_cast_params(int64_t n_params, const float *params, void *params_half, void *stream);
@@ -247,7 +248,9 @@ int dmgs_texture_forward(int64_t N, int32_t channels, const float *aabb6_host, c
                          const float *W0, const float *W1, const float *W2, float *out, void *enc_out, void *stream);
 int dmgs_texture_backward(int64_t N, int32_t channels, const float *aabb6_host, const float *xyz, const void *grid_half,
                           const void *enc, const float *W0, const float *W1, const float *W2, const float *dL_dout,
-                          float grid_grad_scale, float *d_grid, float *dW0, float *dW1, float *dW2, float *d_xyz, void *stream);
+                          float grid_grad_scale, float *d_grid, float *dW0, float *dW1, float *dW2, float *d_xyz,
+                          void *scratch, void *stream);
+size_t dmgs_texture_backward_scratch_bytes(int64_t N);
 
 /* ---- all-reduce (sum) of a flat fp32 buffer over NVLink peer memory (view-partitioned training step:
  *      the per-Gaussian gradient exchange; replaces ncclAllReduce on one box).

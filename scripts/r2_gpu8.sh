@@ -1,0 +1,17 @@
+#!/bin/bash
+# 8-GPU session: H0 weak-scaled at 8 and 4 ranks, C4 (3 M Gaussians, 64 views, 1245x825) at 8 and 4 ranks.
+TAG=${1:-r2n8}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,memory.total --format=csv > $OUT/env.txt 2>&1
+timeout 300 python -m pytest tests/test_gpu_peer_allreduce.py -x -q > $OUT/pytest_peer.log 2>&1; echo "pytest peer rc=$?"; tail -2 $OUT/pytest_peer.log
+run() { # name, N, extra env...
+  local name=$1; local N=$2; shift; shift
+  timeout 600 env "$@" python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
+      bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline > $OUT/$name.json 2> $OUT/$name.err
+  echo "$name rc=$?"; cut -c1-400 $OUT/$name.json; grep -o '"e2e": {"value": [0-9.]*' $OUT/$name.json; grep -o '"training_step": [0-9.]*' $OUT/$name.json; tail -2 $OUT/$name.err | cut -c1-300
+}
+run bench_h0_n8 8 DMGS_BENCH_WORKLOAD=h0
+run bench_c4_n8 8 DMGS_BENCH_WORKLOAD=c4
+run bench_h0_n4 4 DMGS_BENCH_WORKLOAD=h0
+run bench_c4_n4 4 DMGS_BENCH_WORKLOAD=c4
