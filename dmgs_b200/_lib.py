@@ -31,6 +31,14 @@ class AdamSegment(C.Structure):
                 ("n", C.c_int64), ("lr", C.c_double), ("lr_hi", C.c_double), ("period", C.c_int32), ("split", C.c_int32)]
 
 
+class AdamXSegment(C.Structure):
+    """struct dmgs_adam_xsegment (include/dmgs_raster.h)."""
+
+    _fields_ = [("grad_offset", C.c_int64), ("param_offset", C.c_int64), ("n", C.c_int64), ("exp_avg_shard", C.c_void_p),
+                ("exp_avg_sq_shard", C.c_void_p), ("lr", C.c_double), ("lr_hi", C.c_double), ("period", C.c_int32),
+                ("split", C.c_int32)]
+
+
 _lib = None
 
 _vp, _i32, _i64, _f = C.c_void_p, C.c_int32, C.c_int64, C.c_float
@@ -67,6 +75,9 @@ _SIGS = {
     "dmgs_texture_forward": (C.c_int, [_i64, _i32, C.POINTER(_f)] + [_vp] * 8),
     "dmgs_texture_backward": (C.c_int, [_i64, _i32, C.POINTER(_f)] + [_vp] * 7 + [_f] + [_vp] * 7),
     "dmgs_texture_backward_scratch_bytes": (C.c_size_t, [_i64]),
+    "dmgs_adam_exchange_shard": (C.c_int, [_i64, _i32, _i32, C.POINTER(_i64), C.POINTER(_i64)]),
+    "dmgs_adam_exchange_peer": (C.c_int, [_i32, _i32, _i32, C.POINTER(AdamXSegment), C.POINTER(C.c_void_p), _vp,
+                                          C.POINTER(C.c_void_p), _vp, C.c_double, C.c_double, C.c_double, _i64, _f, _vp]),
     "dmgs_allreduce_peer": (C.c_int, [_i64, _i32, _i32, C.POINTER(C.c_void_p), _vp, _f, _vp]),
     "dmgs_geom_layout": (C.c_int, [_i32, C.POINTER(_i64)]),
     "dmgs_binning_layout": (C.c_int, [_i32, _i64, _i32, _i32, C.POINTER(_i64)]),

@@ -14,6 +14,7 @@
 //   v  = b2 v + (1 - b2) g g                  (mul, addcmul)
 //   p  = p - (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
 // with the bias corrections computed on the host in double precision and rounded as torch does.
+#include "adam_math.cuh"
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -31,19 +32,15 @@ struct AdamArgs {
     AdamSeg seg[ADAM_MAX_SEG];
     int nseg;
     long long total;
-    float b1, b2, one_minus_b1, one_minus_b2, sqrt_bc2, eps, grad_scale;
+    AdamConsts c;
     int zero_grad;
 };
 
 __device__ __forceinline__ void adam_update(const AdamArgs &a, const AdamSeg &sg, long long i, int k, float &p, float g,
                                             float &m, float &v, uint32_t ph)
 {
-    const float gk = g * a.grad_scale;
-    m = fma_(a.one_minus_b1, gk - m, m);
-    v = fma_(a.one_minus_b2 * gk, gk, v * a.b2);
-    const float denom = sqrtf(v) / a.sqrt_bc2 + a.eps;
     const float st = (sg.period > 0 && (ph + k) % (uint32_t)sg.period >= (uint32_t)sg.split) ? sg.step_hi : sg.step_lo;
-    p = p - st * (m / denom);
+    adam_math(a.c, st, p, g, m, v);
 }
 
 __global__ void __launch_bounds__(256, 4)
@@ -114,11 +111,11 @@ int launch_adam(int nseg, const dmgs_adam_segment *segs, double beta1, double be
         if (u.n > nmax) nmax = u.n;
     }
     a.nseg = nseg; a.total = pos;
-    a.b1 = (float)beta1; a.b2 = (float)beta2;
-    a.one_minus_b1 = (float)(1.0 - beta1);
-    a.one_minus_b2 = (float)(1.0 - beta2);
-    a.sqrt_bc2 = (float)sqrt(bc2);
-    a.eps = (float)eps; a.grad_scale = grad_scale; a.zero_grad = zero_grad;
+    a.c.b2 = (float)beta2;
+    a.c.one_minus_b1 = (float)(1.0 - beta1);
+    a.c.one_minus_b2 = (float)(1.0 - beta2);
+    a.c.sqrt_bc2 = (float)sqrt(bc2);
+    a.c.eps = (float)eps; a.c.grad_scale = grad_scale; a.zero_grad = zero_grad;
     if (pos == 0) return 0;
     long long blocks = (nmax / 4 + 255) / 256;
     const long long cap = (long long)num_sms() * 8;

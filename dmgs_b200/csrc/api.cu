@@ -507,6 +507,23 @@ int dmgs_texture_backward(int64_t N, int32_t channels, const float *aabb6_host, 
 
 size_t dmgs_texture_backward_scratch_bytes(int64_t N) { return texture_bwd_scratch_bytes(N); }
 
+int dmgs_adam_exchange_shard(int64_t n, int32_t world, int32_t rank, int64_t *begin4, int64_t *end4)
+{
+    if (!begin4 || !end4 || n < 0 || world < 1 || rank < 0 || rank >= world) { set_error("adam_exchange_shard: bad arguments"); return -12; }
+    adam_exchange_shard(n, world, rank, begin4, end4);
+    return 0;
+}
+
+int dmgs_adam_exchange_peer(int32_t world, int32_t rank, int32_t nseg, const dmgs_adam_xsegment *segments_host,
+                            const void *const *grad_peer_ptrs_host, void *grad_multicast_ptr,
+                            const void *const *param_peer_ptrs_host, void *param_multicast_ptr, double beta1, double beta2,
+                            double eps, int64_t step, float grad_scale, void *stream)
+{
+    if (!segments_host || !grad_peer_ptrs_host || !param_peer_ptrs_host) { set_error("adam_exchange: NULL required pointer"); return -6; }
+    return launch_adam_exchange(world, rank, nseg, segments_host, grad_peer_ptrs_host, grad_multicast_ptr, param_peer_ptrs_host,
+                                param_multicast_ptr, beta1, beta2, eps, step, grad_scale, (cudaStream_t)stream);
+}
+
 int dmgs_allreduce_peer(int64_t n, int32_t world, int32_t rank, const void *const *peer_ptrs_host, void *multicast_ptr,
                         float scale, void *stream)
 {

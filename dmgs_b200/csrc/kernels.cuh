@@ -90,6 +90,11 @@ int launch_adam(int nseg, const dmgs_adam_segment *segs, double beta1, double be
 int launch_allreduce_peer(int64_t n, int world, int rank, const void *const *peer_ptrs_host, void *multicast_ptr,
                           float scale, cudaStream_t s);
 
+void adam_exchange_shard(int64_t n, int world, int rank, int64_t *begin4, int64_t *end4);
+int launch_adam_exchange(int world, int rank, int nseg, const dmgs_adam_xsegment *segs, const void *const *grad_peers_host,
+                         void *grad_multicast, const void *const *param_peers_host, void *param_multicast, double beta1,
+                         double beta2, double eps, int64_t step, float grad_scale, cudaStream_t s);
+
 // texture.cu
 int64_t texture_grid_params();
 int launch_texture_cast(int64_t n_params, const float *params, void *params_half, cudaStream_t s);

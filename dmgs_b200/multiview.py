@@ -106,6 +106,39 @@ class ViewParallel:
         return loss
 
 
+class SymmetricFlat:
+    """A flat fp32 buffer in torch symmetric memory, mapped into every rank of `group` (CUDA VMM peer mappings plus,
+    on NVSwitch systems, the multicast mapping).  Construction is a collective (rendezvous).  `allocate` has the
+    signature FlatGradBuffer's `allocate=` expects, so gradients AND parameters can live in such buffers."""
+
+    def __init__(self, numel: int, device, group=None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.flat = symm.empty(int(numel), dtype=torch.float32, device=device)
+        self.flat.zero_()
+        self.hdl = symm.rendezvous(self.flat, self.group)
+        self.world, self.rank = int(self.hdl.world_size), int(self.hdl.rank)
+        self.peers = [self.flat if k == self.rank else self.hdl.get_buffer(k, (int(numel),), torch.float32)
+                      for k in range(self.world)]  # keep the mappings alive
+        self.ptrs = (C.c_void_p * self.world)(*[p.data_ptr() for p in self.peers])
+        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+        if mc:
+            base = int(self.hdl.buffer_ptrs[self.rank])
+            mc += self.flat.data_ptr() - base  # the tensor's offset inside the symmetric allocation
+        self.multicast_ptr = mc
+
+    @classmethod
+    def allocator(cls, device, group=None):
+        """-> (allocate(numel) -> tensor, holder list that receives the SymmetricFlat)."""
+        holder: List["SymmetricFlat"] = []
+
+        def allocate(numel):
+            holder.append(cls(numel, device, group))
+            return holder[-1].flat
+        return allocate, holder
+
+
 class PeerAllReduce:
     """Sum of a flat fp32 buffer over the ranks of one box through NVLink peer memory, in place
     (libdmgs_raster.so: dmgs_allreduce_peer) -- the gradient exchange of the view-partitioned step
@@ -128,19 +161,11 @@ class PeerAllReduce:
     def allocate(self, numel: int) -> torch.Tensor:
         if self.flat is not None:
             raise RuntimeError("PeerAllReduce serves one buffer")
-        self.flat = self._symm.empty(int(numel), dtype=torch.float32, device=self.device)
-        self.flat.zero_()
-        self.hdl = self._symm.rendezvous(self.flat, self.group)
-        self.world, self.rank = int(self.hdl.world_size), int(self.hdl.rank)
-        import ctypes as C
-        peers = [self.flat if k == self.rank else self.hdl.get_buffer(k, (int(numel),), torch.float32) for k in range(self.world)]
-        self._peers = peers  # keep the mappings alive
-        self._ptrs = (C.c_void_p * self.world)(*[p.data_ptr() for p in peers])
-        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
-        if mc:
-            base = int(self.hdl.buffer_ptrs[self.rank])
-            mc += self.flat.data_ptr() - base  # the tensor's offset inside the symmetric allocation
-        self.multicast_ptr = mc
+        sym = SymmetricFlat(numel, self.device, self.group)
+        self._sym = sym
+        self.flat, self.hdl, self.world, self.rank = sym.flat, sym.hdl, sym.world, sym.rank
+        self._peers, self._ptrs, self.multicast_ptr = sym.peers, sym.ptrs, sym.multicast_ptr
+        self.ptrs = sym.ptrs
         return self.flat
 
     def all_reduce_(self, scale: float = 1.0, use_multicast: Optional[bool] = None):
@@ -303,6 +328,89 @@ def accumulate_view(settings, inputs: Dict[str, Optional[torch.Tensor]], image_g
                        g("cov3D_precomp"), g("colors_precomp") is not None, accumulate_into=acc, sh_record=sh_record,
                        verify=False)  # sync-free binning: the step polls dmgs_b200.check_async() once, after its views
     return loss, color, radii
+
+
+class ShardedPeerAdam:
+    """Adam over REPLICATED parameters with the gradient exchange fused in (libdmgs_raster.so:
+    dmgs_adam_exchange_peer) -- the tail of a view-partitioned training step in one kernel per rank instead of
+    "all-reduce, then the same Adam step on every replica": rank r sums slice r of every rank's gradients (in the
+    NVSwitch when multicast is available), updates slice r of every parameter tensor with ITS shard of
+    exp_avg / exp_avg_sq and writes the new parameters into all replicas.
+
+    params / grads: FlatGradBuffer objects whose flat tensors live in symmetric memory (`SymmetricFlat`; the gradient
+    buffer of `ViewStreams(peer_group=...)` does), with a field of the same name and size for every group.
+    groups: {field name: {'lr': ..., optional 'lr_hi', 'period', 'split'}} as for FusedAdam.  Arithmetic =
+    torch.optim.Adam (the same device function as dmgs_adam_step).  Gradients are not cleared (ViewStreams.begin()
+    does that)."""
+
+    MULTICAST_MIN_WORLD = PeerAllReduce.MULTICAST_MIN_WORLD
+
+    def __init__(self, params: FlatGradBuffer, param_sym: SymmetricFlat, grads: FlatGradBuffer, grad_sym, groups: Dict[str, dict],
+                 betas=(0.9, 0.999), eps: float = 1e-8):
+        import ctypes as C
+        from . import _lib as L
+        self.params, self.grads, self.psym, self.gsym = params, grads, param_sym, grad_sym
+        self.world, self.rank = int(param_sym.world), int(param_sym.rank)
+        if (int(grad_sym.world), int(grad_sym.rank)) != (self.world, self.rank):
+            raise ValueError("parameter and gradient buffers belong to different groups")
+        self.betas, self.eps, self.step_count = tuple(betas), float(eps), 0
+        self.groups = {k: dict(v) for k, v in groups.items()}
+        self.state: Dict[str, dict] = {}
+        dev = params.flat.device
+        for name in self.groups:
+            if name not in params.offsets or name not in grads.offsets:
+                raise KeyError(f"group {name!r} is not a field of both buffers")
+            (po, pn), (go, gn) = params.offsets[name], grads.offsets[name]
+            if pn != gn:
+                raise ValueError(f"field {name!r}: {pn} parameters but {gn} gradients")
+            b, e = C.c_int64(), C.c_int64()
+            L.check(L.lib().dmgs_adam_exchange_shard(pn, self.world, self.rank, C.byref(b), C.byref(e)), "dmgs_adam_exchange_shard")
+            n = 4 * (e.value - b.value)
+            self.state[name] = {"begin": 4 * b.value, "end": 4 * e.value,
+                                "exp_avg": torch.zeros(max(n, 4), dtype=torch.float32, device=dev),
+                                "exp_avg_sq": torch.zeros(max(n, 4), dtype=torch.float32, device=dev)}
+
+    @torch.no_grad()
+    def step(self, grad_scale: float = 1.0, use_multicast: Optional[bool] = None):
+        import ctypes as C
+        from . import _lib as L
+        self.step_count += 1
+        names = list(self.groups)
+        segs = (L.AdamXSegment * len(names))()
+        for i, name in enumerate(names):
+            g, st = self.groups[name], self.state[name]
+            segs[i] = L.AdamXSegment(self.grads.offsets[name][0], self.params.offsets[name][0], self.params.offsets[name][1],
+                                     st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), float(g["lr"]),
+                                     float(g.get("lr_hi", g["lr"])), int(g.get("period", 0)), int(g.get("split", 0)))
+        if use_multicast is None:
+            use_multicast = self.world >= self.MULTICAST_MIN_WORLD
+        mc = bool(use_multicast and self.psym.multicast_ptr and self.gsym.multicast_ptr)
+        dev = self.params.flat.device
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        self.gsym.hdl.barrier(channel=0)  # every rank's gradients are complete, nobody still reads the old parameters
+        for k in range(0, len(names), 8):  # DMGS_ADAM_MAX_SEGMENTS tensors per launch
+            part = (L.AdamXSegment * len(names[k:k + 8]))(*segs[k:k + 8])
+            L.check(L.lib().dmgs_adam_exchange_peer(self.world, self.rank, len(part), part, self.gsym.ptrs,
+                                                    C.c_void_p(self.gsym.multicast_ptr) if mc else None, self.psym.ptrs,
+                                                    C.c_void_p(self.psym.multicast_ptr) if mc else None, self.betas[0], self.betas[1],
+                                                    self.eps, self.step_count, float(grad_scale), stream), "dmgs_adam_exchange_peer")
+        self.gsym.hdl.barrier(channel=1)  # every slice of the new parameters has reached every replica
+        return self.params
+
+    def state_dict(self) -> dict:
+        """This rank's SHARD of the state (ranges in elements of each field)."""
+        return {"step": self.step_count, "betas": self.betas, "eps": self.eps, "world": self.world, "rank": self.rank,
+                "groups": {k: dict(v) for k, v in self.groups.items()},
+                "state": {k: {"begin": v["begin"], "end": v["end"], "exp_avg": v["exp_avg"].clone(),
+                              "exp_avg_sq": v["exp_avg_sq"].clone()} for k, v in self.state.items()}}
+
+    def load_state_dict(self, sd: dict):
+        if (sd["world"], sd["rank"]) != (self.world, self.rank):
+            raise ValueError("state shard of another rank / world size")
+        self.step_count = int(sd["step"])
+        for k, v in sd["state"].items():
+            self.state[k]["exp_avg"].copy_(v["exp_avg"])
+            self.state[k]["exp_avg_sq"].copy_(v["exp_avg_sq"])
 
 
 def shard_rows(n_rows: int, world: int, rank: int) -> Tuple[int, int, int]:

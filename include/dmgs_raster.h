@@ -265,6 +265,29 @@ size_t dmgs_texture_backward_scratch_bytes(int64_t N);
 int dmgs_allreduce_peer(int64_t n, int32_t world, int32_t rank, const void *const *peer_ptrs_host, void *multicast_ptr,
                         float scale, void *stream);
 
+/* ---- the gradient exchange FUSED with the optimiser step (view-partitioned training; replaces
+ *      dmgs_allreduce_peer followed by dmgs_adam_step on every rank -- i.e. ncclAllReduce + torch.optim.Adam.step of
+ *      train_geo_stage3.py:164-166 run data parallel).  Rank r owns slice r (dmgs_adam_exchange_shard) of every
+ *      parameter tensor: ONE kernel sums that slice of all ranks' gradients (NVSwitch multimem.ld_reduce when the
+ *      multicast pointers are given, peer loads otherwise), applies Adam with the rank's SHARD of exp_avg / exp_avg_sq
+ *      (arrays of 4 * (end4 - begin4) floats) and writes the new parameters into every rank's parameter buffer
+ *      (multimem.st / peer stores).  Parameters and gradients live in two flat buffers mapped into every rank (as for
+ *      dmgs_allreduce_peer); a segment = one tensor: its offsets (in floats, multiples of 4) in the two buffers and
+ *      its n elements; the ceil(n/4)*4 - n padding floats of a field are updated too (they stay zero).  The caller
+ *      brackets the call with two device-side barriers, as for dmgs_allreduce_peer.  Gradients are NOT cleared. */
+typedef struct dmgs_adam_xsegment {
+    int64_t grad_offset, param_offset, n;
+    float *exp_avg_shard, *exp_avg_sq_shard;
+    double lr, lr_hi;
+    int32_t period, split;
+} dmgs_adam_xsegment;
+int dmgs_adam_exchange_shard(int64_t n, int32_t world, int32_t rank, int64_t *begin4, int64_t *end4);
+int dmgs_adam_exchange_peer(int32_t world, int32_t rank, int32_t nseg, const dmgs_adam_xsegment *segments_host,
+                            const void *const *grad_peer_ptrs_host, void *grad_multicast_ptr,
+                            const void *const *param_peer_ptrs_host, void *param_multicast_ptr, double beta1, double beta2,
+                            double eps, int64_t step, float grad_scale, void *stream);
+
+
 /* ---- inspection (parity tests): byte offsets of the named arrays inside the state buffers.
  * geom:    [0] depths f32[P]  [1] rec f32[P][8]={x,y,conA,conB,conC,opacity,cut,_}  [2] rgb f32[P][4]
  *          [3] clamped u8[P] (bit ch)  [4] cov3D f32[P][6]  [5] tiles_touched u32[P]

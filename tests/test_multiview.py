@@ -114,3 +114,21 @@ def test_shard_rows_cover_every_row_once():
             assert seen == n and len(chunks) == 1 and chunks.pop() * world >= n
     with pytest.raises(ValueError):
         shard_rows(10, 2, 2)
+
+
+def test_adam_exchange_shards_partition_every_field():
+    """dmgs_adam_exchange_shard: the ranks' 16-byte-group ranges tile ceil(n/4) groups exactly once, in rank order."""
+    import ctypes as C
+    from dmgs_b200 import _lib as L
+    lib = L.lib()
+    for n in (0, 1, 5, 50_001, 150_003, 48_000_000):
+        for world in (1, 2, 3, 8):
+            prev = 0
+            for r in range(world):
+                b, e = C.c_int64(), C.c_int64()
+                assert lib.dmgs_adam_exchange_shard(n, world, r, C.byref(b), C.byref(e)) == 0
+                assert 0 <= b.value <= e.value and b.value in (prev, e.value)
+                prev = e.value
+            assert prev == (n + 3) // 4
+    b, e = C.c_int64(), C.c_int64()
+    assert lib.dmgs_adam_exchange_shard(10, 2, 2, C.byref(b), C.byref(e)) != 0
