@@ -359,6 +359,8 @@ def run_ours(args):
     if world > 1:
         mgpu = multi_gpu_checks(torch, dist, MV, vs, dev, world, rank, P, n_views, settings, d, dLs, step,
                                 rasterize_forward, rasterize_backward)
+        if vs.peer is not None and not args.quick:
+            mgpu["optimizer_tail"] = optimizer_tail_timing(torch, dist, MV, vs, dev, world, P, d, names)
 
     # per-stage kernel durations: two more steps on ONE stream with CUDA events between the stages (with
     # several views in flight the stages of different views overlap and cannot be timed individually)
@@ -615,6 +617,62 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def optimizer_tail_timing(torch, dist, MV, vs, dev, world, P, d, names, iters=10):
+    """The tail of a training step, outside the timed region: (a) dmgs_allreduce_peer followed by FusedAdam on every
+    replica, (b) the two fused (dmgs_adam_exchange_peer: reduce-scatter + sharded Adam + parameter all-gather in
+    one kernel per rank).  ms per step, CUDA events, max over ranks; the two paths must agree on the parameters."""
+    from dmgs_b200.optim import FusedAdam
+    widths = {k: tuple(d[k].shape[1:]) for k in names}
+    lrs = {"means3D": {"lr": 1.6e-4}, "opacities": {"lr": 5e-2}, "scales": {"lr": 5e-3}, "rotations": {"lr": 1e-3},
+           "shs": {"lr": 2.5e-3, "lr_hi": 2.5e-3 / 20, "period": 48, "split": 3}}
+    palloc, ph = MV.SymmetricFlat.allocator(dev, dist.group.WORLD)
+    params = MV.FlatGradBuffer(P, widths, dev, allocate=palloc)
+    for k in names:
+        params.views[k].copy_(d[k])
+    replica = {k: d[k].clone() for k in names}
+    fused = MV.ShardedPeerAdam(params, ph[0], vs.buf, vs.peer, {k: lrs[k] for k in names}, eps=1e-15)
+    plain = FusedAdam([{"params": [replica[k]], "name": k, **lrs[k]} for k in names], lr=0.0, eps=1e-15)
+    gen = torch.Generator(device=dev).manual_seed(4321 + dist.get_rank())
+    grad0 = torch.zeros_like(vs.buf.flat)
+    for k, view in vs.buf.views.items():
+        o, m = vs.buf.offsets[k]
+        grad0[o:o + m] = torch.randn(m, generator=gen, device=dev) * 1e-3
+    scale = 1.0 / (8 * world)
+
+    def timed(fn):
+        ts = []
+        for _ in range(iters + 2):
+            vs.buf.flat.copy_(grad0)
+            torch.cuda.synchronize()
+            dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts = sorted(ts[2:])
+        t = torch.tensor([ts[len(ts) // 2]], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def two_kernels():
+        vs.all_reduce_(scale)
+        plain.step(grads={k: vs.buf.views[k] for k in names})
+
+    ms_plain = timed(two_kernels)
+    ms_fused = timed(lambda: fused.step(grad_scale=scale))
+    err = max(float((params.views[k] - replica[k]).abs().max() / replica[k].abs().max()) for k in names)
+    e = torch.tensor([err], device=dev)
+    dist.all_reduce(e, op=dist.ReduceOp.MAX)
+    return {"allreduce_then_adam_ms": round(ms_plain, 4), "fused_exchange_adam_ms": round(ms_fused, 4),
+            "params_max_rel_diff_after_%d_steps" % (iters + 2): float(e.item()),
+            "optimizer_state_bytes_per_rank": {"replicated": 8 * sum(int(d[k].numel()) for k in names),
+                                               "sharded": 8 * sum(int(v["exp_avg"].numel()) for v in fused.state.values())},
+            "note": "tail of a training step: dmgs_allreduce_peer + dmgs_adam_step on every replica vs ONE "
+                    "dmgs_adam_exchange_peer per rank (slice-owner reduces, applies Adam on its state shard, broadcasts parameters)"}
 
 
 def multi_gpu_checks(torch, dist, MV, vs, dev, world, rank, P, n_views, settings, d, dLs, step, rasterize_forward,
