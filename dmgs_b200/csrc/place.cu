@@ -225,8 +225,9 @@ tile_scan_kernel(int T, uint32_t *__restrict__ tile_start, uint2 *__restrict__ r
 
 // ------------------------------------------------------------------------------ C: place
 // The CTA first turns its rows of counts into cursors (tile start + CTAs before + warps before), then
-// every warp walks its segment: one Gaussian per step, in depth order; lanes <-> the tiles of its
-// rectangle (all distinct, so the read-modify-write of the cursors needs no atomics and keeps the order).
+// every warp walks its segment in depth order: four Gaussians per step (eight lanes each over the tiles of a
+// rectangle) when their rectangles are disjoint, else one Gaussian per step with all lanes over its tiles -- the tiles
+// touched in one step are all distinct, so the read-modify-write of the cursors needs no atomics and keeps the order.
 __global__ void __launch_bounds__(128)
 tile_place_kernel(int P, int T, int gx, int seg, int nseg, const uint4 *__restrict__ srec,
                   const uint32_t *__restrict__ table, const uint32_t *__restrict__ gsum,
@@ -277,28 +278,62 @@ tile_place_kernel(int P, int T, int gx, int seg, int nseg, const uint4 *__restri
     if (sg >= nseg) return;
     const int s0 = sg * seg, s1 = min(P, s0 + seg);
     uint4 nxt = s0 + lane < s1 ? srec[s0 + lane] : make_uint4(0, 0, 0, 0);
+    const int oct = lane >> 3, sub = lane & 7;
     for (int sb = s0; sb < s1; sb += 32) {
         // lane <-> Gaussian: 32 depth-ordered records at once; the next batch is already in flight
         const uint4 rc = nxt;
         const int sn = sb + 32 + lane;
         nxt = sn < s1 ? srec[sn] : make_uint4(0, 0, 0, 0);
-        const uint32_t x0 = rc.x & 0xffff, y0 = rc.y & 0xffff, wd = (rc.x >> 16) - x0;
-        const uint32_t n = wd * ((rc.y >> 16) - y0), tb = y0 * (uint32_t)gx + x0;
-        uint32_t m = __ballot_sync(0xffffffffu, n != 0);
-        while (m) {
-            const int i = __ffs(m) - 1;
-            m &= m - 1;
-            const uint32_t ni = __shfl_sync(0xffffffffu, n, i), wi = __shfl_sync(0xffffffffu, wd, i);
-            const uint32_t tbase = __shfl_sync(0xffffffffu, tb, i);
-            const uint32_t mg = __shfl_sync(0xffffffffu, rc.z, i), gi = __shfl_sync(0xffffffffu, rc.w, i);
-            for (uint32_t k = lane; k < ni; k += 32) {
-                const uint32_t q = mg ? __umulhi(k, mg) : k;  // k / width (exact for k < 2^18)
-                const uint32_t t = tbase + q * (uint32_t)gx + (k - q * wi);
-                const uint32_t slot = cur[t];
-                cur[t] = slot + 1;
-                out_gidx[slot] = gi;
+        const uint32_t x0 = rc.x & 0xffff, y0 = rc.y & 0xffff, x1 = rc.x >> 16, y1 = rc.y >> 16, wd = x1 - x0;
+        const uint32_t n = wd * (y1 - y0), tb = y0 * (uint32_t)gx + x0;
+        const uint32_t live = __ballot_sync(0xffffffffu, n != 0);
+        if (!live) continue;
+        // FOUR Gaussians per step, eight lanes each, whenever the four rectangles of a quad are pairwise disjoint
+        // (then no two of them bump the same cursor and the order inside every tile's list is untouched); a quad
+        // with an overlap -- or with a rectangle of more than 64 tiles -- is walked one Gaussian at a time by the
+        // whole warp, as before.  A lane compares its rectangle with the earlier ones of its quad.
+        bool cf = n > 64u;
+#pragma unroll
+        for (int d = 1; d < 4; ++d) {
+            const uint32_t ox = __shfl_up_sync(0xffffffffu, rc.x, d), oy = __shfl_up_sync(0xffffffffu, rc.y, d);
+            const uint32_t ox0 = ox & 0xffff, ox1 = ox >> 16, oy0 = oy & 0xffff, oy1 = oy >> 16;
+            if ((lane & 3) >= d && n != 0 && ox1 > ox0 && oy1 > oy0 && x0 < ox1 && ox0 < x1 && y0 < oy1 && oy0 < y1) cf = true;
+        }
+        const uint32_t cmask = __ballot_sync(0xffffffffu, cf);
+        for (int q = 0; q < 8; ++q) {
+            const uint32_t lq = (live >> (4 * q)) & 0xfu;
+            if (!lq) continue;
+            if ((cmask >> (4 * q)) & 0xfu) {
+                uint32_t m = lq << (4 * q);
+                while (m) {
+                    const int i = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t ni = __shfl_sync(0xffffffffu, n, i), wi = __shfl_sync(0xffffffffu, wd, i);
+                    const uint32_t tbase = __shfl_sync(0xffffffffu, tb, i);
+                    const uint32_t mg = __shfl_sync(0xffffffffu, rc.z, i), gi = __shfl_sync(0xffffffffu, rc.w, i);
+                    for (uint32_t k = lane; k < ni; k += 32) {
+                        const uint32_t qq = mg ? __umulhi(k, mg) : k;  // k / width (exact for k < 2^18)
+                        const uint32_t t = tbase + qq * (uint32_t)gx + (k - qq * wi);
+                        const uint32_t slot = cur[t];
+                        cur[t] = slot + 1;
+                        out_gidx[slot] = gi;
+                    }
+                    __syncwarp();
+                }
+            } else {
+                const int i = 4 * q + oct;
+                const uint32_t ni = __shfl_sync(0xffffffffu, n, i), wi = __shfl_sync(0xffffffffu, wd, i);
+                const uint32_t tbase = __shfl_sync(0xffffffffu, tb, i);
+                const uint32_t mg = __shfl_sync(0xffffffffu, rc.z, i), gi = __shfl_sync(0xffffffffu, rc.w, i);
+                for (uint32_t k = sub; k < ni; k += 8) {
+                    const uint32_t qq = mg ? __umulhi(k, mg) : k;
+                    const uint32_t t = tbase + qq * (uint32_t)gx + (k - qq * wi);
+                    const uint32_t slot = cur[t];
+                    cur[t] = slot + 1;
+                    out_gidx[slot] = gi;
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
     }
 }
