@@ -18,9 +18,11 @@ import subprocess
 import sys
 
 FAMILIES = [("blend_fwd", r"blend_fwd_kernel"), ("blend_bwd", r"blend_bwd_kernel"),
-            ("preprocess_fwd", r"preprocess_fwd_kernel"), ("preprocess_bwd", r"preprocess_bwd_kernel"),
+            ("preprocess_fwd", r"preprocess_fwd_kernel"),
+            # <3, *> = deferred SH gradient (the timed region of the bench); <1, *> / <2, *> = the row-writing variants of the module path
+            ("preprocess_bwd", r"preprocess_bwd_kernel<3"), ("preprocess_bwd_rows", r"preprocess_bwd_kernel<[12]"),
             ("tile_place", r"tile_place_kernel"), ("tile_count", r"tile_count_kernel"),
-            ("sh_grad_expand", r"sh_grad_expand_kernel"), ("radix_scatter", r"radix_scatter_kernel"),
+            ("sh_grad_expand", r"sh_grad_expand_kernel"), ("radix_scatter", r"radix_scatter_kernel"), ("onesweep_pass", r"onesweep_pass_kernel"),
             ("bind_preprocess_fwd", r"bind_preprocess_fwd_kernel"), ("bind_preprocess_bwd", r"bind_preprocess_bwd_kernel")]
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "usecond": 1e-6, "msecond": 1e-3,
         "nsecond": 1e-9, "ms": 1e-3, "second": 1.0}
