@@ -1,5 +1,5 @@
 #!/bin/bash
-# 8-GPU session: H0 weak-scaled at 8 and 4 ranks, C4 (3 M Gaussians, 64 views, 1245x825) at 8 and 4 ranks.
+# 8-GPU session: the two 2-GPU tests, H0 weak-scaled at 8 and 4 ranks, C4 (3 M Gaussians, 64 views, 1245x825) at 8 ranks.
 TAG=${1:-r2n8}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
@@ -9,9 +9,17 @@ run() { # name, N, extra env...
   local name=$1; local N=$2; shift; shift
   timeout 600 env "$@" python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
       bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline > $OUT/$name.json 2> $OUT/$name.err
-  echo "$name rc=$?"; cut -c1-400 $OUT/$name.json; grep -o '"e2e": {"value": [0-9.]*' $OUT/$name.json; grep -o '"training_step": [0-9.]*' $OUT/$name.json; tail -2 $OUT/$name.err | cut -c1-300
+  echo "$name rc=$?"; python - $OUT/$name.json <<'PY'
+import json, sys
+try:
+    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print(round(d["value"], 1), "frames/s", round(d["ms_per_step"], 3), "ms/step; e2e", round(d["e2e"]["value"], 1), round(d["e2e"]["training_step"], 1),
+          "; tail", json.dumps({k: v for k, v in (d.get("optimizer_tail") or {}).items() if k != "note"}), "; nrank", d.get("nrank_vs_1rank_rel_err"))
+except Exception as e:
+    print("failed", e)
+PY
+  tail -2 $OUT/$name.err | cut -c1-300
 }
 run bench_h0_n8 8 DMGS_BENCH_WORKLOAD=h0
 run bench_c4_n8 8 DMGS_BENCH_WORKLOAD=c4
 run bench_h0_n4 4 DMGS_BENCH_WORKLOAD=h0
-run bench_c4_n4 4 DMGS_BENCH_WORKLOAD=c4
