@@ -273,6 +273,9 @@ def run_ours(args):
         return hook
 
     stats = {"R": 0, "frames": 0, "redone": 0, "host_s": 0.0}
+    # views as CUDA graphs (multiview.ViewStreams.capture): captured during the warm-up steps, after one eager step
+    GRAPHS = os.environ.get("DMGS_BENCH_GRAPHS", "1") == "1"
+    graphs = {"ready": False, "captures": 0}
     r_dev = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(N_STREAMS)]
 
     def one_view(j, v, record, acc):
@@ -291,7 +294,6 @@ def run_ours(args):
             r_dev[j % N_STREAMS].add_(st.ws.meta[0:1])
         else:
             stats["R"] += st.num_rendered
-        stats["frames"] += 1
         if record:
             ev_log.append(events)
 
@@ -308,12 +310,27 @@ def run_ours(args):
         else:
             vs.begin()
             for j, v in enumerate(my_views):
-                vs.run(j, lambda acc, j=j, v=v: one_view(j, v, False, acc))
+                if graphs["ready"] and not vs.captured(j):
+                    try:
+                        vs.capture(j, lambda acc, j=j, v=v: one_view(j, v, False, acc))
+                        graphs["captures"] += 1
+                    except Exception as e:  # capture unavailable: the eager path is the same work
+                        graphs["ready"], graphs["error"] = False, f"{type(e).__name__}: {e}"[:200]
+                        vs.drop_graphs()
+                if graphs["ready"]:  # the whole view (forward + backward, ~25 launches) is ONE graph launch
+                    vs.replay(j)
+                else:
+                    vs.run(j, lambda acc, j=j, v=v: one_view(j, v, False, acc))
             vs.finish(d["means3D"], d["shs"], 3)
+        stats["frames"] += len(my_views)
         if world > 1 and exchange:
             vs.all_reduce_()
         stats["host_s"] += time.perf_counter() - th  # host time to ENQUEUE the step (no synchronisation so far)
-        if not dmgs_b200.check_async():  # a frame overflowed its binning buffer: the step does not count
+        ok = dmgs_b200.check_async()
+        ok = vs.poll_captured() and ok
+        if not single and GRAPHS and not args.sync_binning and "error" not in graphs:
+            graphs["ready"] = True  # capacities and host-side camera values exist after the first eager step
+        if not ok:  # a frame overflowed its binning buffer: the step does not count
             stats["redone"] += 1
             if record:
                 del ev_log[-len(my_views):]
@@ -326,7 +343,7 @@ def run_ours(args):
     stats.update(R=0, frames=0, redone=0, host_s=0.0)
     for t in r_dev:
         t.zero_()
-    launches0 = lib.dmgs_launch_count()
+    launches0 = lib.dmgs_launch_count() + vs.replayed_kernel_launches
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -342,7 +359,7 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     ms = t0.elapsed_time(t1)
-    launches = lib.dmgs_launch_count() - launches0
+    launches = lib.dmgs_launch_count() + vs.replayed_kernel_launches - launches0  # eager launches + graph kernel nodes
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         tm = torch.tensor([ms], device=dev)
@@ -580,6 +597,8 @@ def run_ours(args):
                    "one all-reduce of the flat gradient buffer per step)" if world > 1 else "single GPU",
                    "all_reduce": allreduce_kind,
                    "avg_instances_R": Ravg, "view_streams": N_STREAMS,
+                   "cuda_graphs": ("one graph per view (forward + backward), captured in the warm-up, replayed in the "
+                                   f"timed region; {graphs['captures']} captures") if graphs["ready"] else graphs.get("error", "off"),
                    "sh_gradient": "deferred: 16-byte records per view, rows formed once per step (dmgs_sh_grad_expand)" if deferred
                    else "read-modify-write of the [P,16,3] rows every view",
                    "stage_timing": "2 single-stream steps right after the timed region, CUDA events between stages",

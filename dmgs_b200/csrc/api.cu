@@ -13,6 +13,14 @@ static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add((uint64_t)n); }
 
+static int env_residency(const char *name)
+{
+    const char *v = getenv(name);
+    const int k = v ? atoi(v) : 0;
+    return k >= 1 && k <= 8 ? k : 8;
+}
+int g_blend_residency[2] = {env_residency("DMGS_BLEND_FWD_RESIDENCY"), env_residency("DMGS_BLEND_BWD_RESIDENCY")};
+
 static int current_device()
 {
     int d = -1;
@@ -96,12 +104,20 @@ extern "C" {
 
 int dmgs_abi_version(void) { return 1; }
 uint64_t dmgs_launch_count(void) { return g_launches.load(); }
+int dmgs_set_blend_residency(int32_t forward, int32_t backward)
+{
+    if (forward < 0 || forward > 8 || backward < 0 || backward > 8) { set_error("blend residency: 0..8 CTAs per SM"); return -7; }
+    if (forward) g_blend_residency[0] = forward;
+    if (backward) g_blend_residency[1] = backward;
+    return 0;
+}
 const char *dmgs_last_error(void) { return g_err; }
 
 size_t dmgs_geom_bytes(int32_t P) { return geom_layout(P).total; }
 size_t dmgs_binning_bytes(int32_t P, int64_t R, int32_t W, int32_t H) { return bin_layout(P, R, W, H).total; }
 size_t dmgs_image_bytes(int32_t W, int32_t H) { return img_layout(W, H).total; }
-size_t dmgs_backward_scratch_bytes(int32_t P) { return align_up((size_t)(P > 0 ? P : 1) * 12 * sizeof(float)); }
+// P x 12 sums of the blend backward + the square counter of its persistent grid (zeroed together)
+size_t dmgs_backward_scratch_bytes(int32_t P) { return align_up((size_t)(P > 0 ? P : 1) * 12 * sizeof(float) + 16); }
 
 int dmgs_geom_layout(int32_t P, int64_t *o)
 {
@@ -314,7 +330,7 @@ int dmgs_blend_backward(const dmgs_params *prm, const void *geom, const void *bi
     const BinLayout BL = bin_layout(P, R, prm->image_width, prm->image_height);
     const ImgLayout IL = img_layout(prm->image_width, prm->image_height);
     float *grad_blend = (float *)scratch;
-    DMGS_CUDA(cudaMemsetAsync(grad_blend, 0, (size_t)P * 12 * sizeof(float), s));
+    DMGS_CUDA(cudaMemsetAsync(grad_blend, 0, (size_t)P * 12 * sizeof(float) + 16, s));
     if (R > 0) {
         rc = launch_blend_bwd(prm, geom, GL, binning, BL, image, IL, dL_dpix, grad_blend, s);
         if (rc) return rc;

@@ -23,16 +23,20 @@ namespace dmgs {
 __global__ void __launch_bounds__(BLK, FWD_MIN_BLOCKS)
 blend_fwd_kernel(const __grid_constant__ BlendArgs a, const uint32_t *__restrict__ tile_order, const uint2 *__restrict__ ranges,
                  const uint32_t *__restrict__ gidx, const float4 *__restrict__ rec, const float4 *__restrict__ rgb4,
-                 float *__restrict__ out_color, float *__restrict__ final_T, uint32_t *__restrict__ n_contrib)
+                 float *__restrict__ out_color, float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
+                 uint32_t *__restrict__ counter)
 {
     __shared__ __align__(16) unsigned char s_cw[(BLK / 32) * CW_WARP_BYTES];  // per-warp compacted survivors
 
     const int lane = threadIdx.x & 31;
+    const uint32_t a_cw = smem_addr(s_cw) + (uint32_t)(threadIdx.x >> 5) * CW_WARP_BYTES;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (bool first = true;; first = false) {  // persistent warp: one 8x8 square per iteration
     int tile, px0, py0;
-    if (!warp_square(a, tile_order, tile, px0, py0)) return;
+    if (!next_square(a, tile_order, counter, first, lane, tile, px0, py0)) break;
     const int px = px0 + (lane & 7), pya = py0 + (lane >> 3), pyb = pya + 4;
     const bool in_a = px < a.W && pya < a.H, in_b = px < a.W && pyb < a.H;
-    if (!__any_sync(0xffffffffu, in_a)) return;  // the whole square lies outside the image
+    if (!__any_sync(0xffffffffu, in_a)) continue;  // the whole square lies outside the image
     const float pxf = (float)px;
     const f32x2 npx = pk2(-pxf, -pxf), npy = pk2(-(float)pya, -(float)pyb);
     const float rx0 = (float)px0, rx1 = (float)(px0 + 7), ry0 = (float)py0, ry1 = (float)(py0 + 7);
@@ -44,8 +48,6 @@ blend_fwd_kernel(const __grid_constant__ BlendArgs a, const uint32_t *__restrict
     float Ta = 1.0f, Ca0 = 0.0f, Ca1 = 0.0f, Ca2 = 0.0f;
     float Tb = 1.0f, Cb0 = 0.0f, Cb1 = 0.0f, Cb2 = 0.0f;
     uint32_t last_a = 0, last_b = 0;
-    const uint32_t a_cw = smem_addr(s_cw) + (uint32_t)(threadIdx.x >> 5) * CW_WARP_BYTES;
-    const uint32_t lt_mask = (1u << lane) - 1u;
 
     // software pipeline: records of group k + 1 and indices of group k + 2 are in flight while group k is blended
     float4 ra = make_float4(0, 0, 0, 0), rb = ra, col = ra;
@@ -73,6 +75,7 @@ blend_fwd_kernel(const __grid_constant__ BlendArgs a, const uint32_t *__restrict
         if (!n) continue;
         __syncwarp();
         // lane <-> pixel pair over the survivors, in list order
+        DMGS_UNROLL(FWD_UNROLL)
         for (int t = 0; t < n; ++t) {
             const uint32_t cw = a_cw + CW_REC * (uint32_t)t;
             f32x2 power, alpha, dx, dy, G;
@@ -130,6 +133,7 @@ blend_fwd_kernel(const __grid_constant__ BlendArgs a, const uint32_t *__restrict
         out_color[HW + pix] = fma_(Tb, a.bg[1], Cb1);
         out_color[2 * HW + pix] = fma_(Tb, a.bg[2], Cb2);
     }
+    }  // next square
 }
 
 int launch_blend_fwd(const dmgs_params *prm, const void *geom, const GeomLayout &GL, const void *binning,
@@ -140,9 +144,11 @@ int launch_blend_fwd(const dmgs_params *prm, const void *geom, const GeomLayout 
     a.gx = (a.W + DMGS_TILE - 1) / DMGS_TILE; a.gy = (a.H + DMGS_TILE - 1) / DMGS_TILE;
     for (int i = 0; i < 3; ++i) a.bg[i] = prm->bg[i];
     if (a.W <= 0 || a.H <= 0) return 0;
-    blend_fwd_kernel<<<blend_grid(a), BLK, 0, s>>>(a, BL.has_order ? at<uint32_t>(binning, BL.tile_order) : nullptr, at<uint2>(binning, BL.ranges), at<uint32_t>(binning, BL.gidx),
+    uint32_t *counter = at<uint32_t>(image, IL.counter);
+    DMGS_CUDA(cudaMemsetAsync(counter, 0, sizeof(uint32_t), s));
+    blend_fwd_kernel<<<blend_grid(a, 0), BLK, 0, s>>>(a, BL.has_order ? at<uint32_t>(binning, BL.tile_order) : nullptr, at<uint2>(binning, BL.ranges), at<uint32_t>(binning, BL.gidx),
                                                       at<float4>(geom, GL.rec), at<float4>(geom, GL.rgb), out_color,
-                                                      at<float>(image, IL.final_T), at<uint32_t>(image, IL.n_contrib));
+                                                      at<float>(image, IL.final_T), at<uint32_t>(image, IL.n_contrib), counter);
     DMGS_CUDA(cudaGetLastError());
     count_launches(1);
     return 0;

@@ -53,21 +53,29 @@ __global__ void __launch_bounds__(BLK, BWD_MIN_BLOCKS)
 blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint32_t *__restrict__ tile_order, const uint2 *__restrict__ ranges,
                  const uint32_t *__restrict__ gidx, const float4 *__restrict__ rec, const float4 *__restrict__ rgb4,
                  const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
-                 const float *__restrict__ dL_dpix, float *__restrict__ grad_blend)
+                 const float *__restrict__ dL_dpix, float *__restrict__ grad_blend, uint32_t *__restrict__ counter)
 {
     __shared__ __align__(16) unsigned char s_cw[(BLK / 32) * CW_WARP_BYTES];    // per-warp compacted survivors
     __shared__ __align__(16) unsigned char s_acc[(BLK / 32) * ACC_WARP_BYTES];  // per-warp sums of the current group
 
     const int lane = threadIdx.x & 31;
+    const float ddelx_dx = 0.5f * (float)a.W, ddely_dy = 0.5f * (float)a.H;
+    const int slot = tr_slot9(lane);
+    const bool owner = slot >= 0 && !(lane & 1);
+    const uint32_t a_cw = smem_addr(s_cw) + (uint32_t)(threadIdx.x >> 5) * CW_WARP_BYTES;
+    const uint32_t a_acc = smem_addr(s_acc) + (uint32_t)(threadIdx.x >> 5) * ACC_WARP_BYTES;
+    const uint32_t a_own = a_acc + 4u * (uint32_t)(slot < 0 ? 0 : slot);
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (bool first = true;; first = false) {  // persistent warp: one 8x8 square per iteration (blend_common.cuh)
     int tile, px0, py0;
-    if (!warp_square(a, tile_order, tile, px0, py0)) return;
+    if (!next_square(a, tile_order, counter, first, lane, tile, px0, py0)) break;
     const int px = px0 + (lane & 7), pya = py0 + (lane >> 3), pyb = pya + 4;
     const bool in_a = px < a.W && pya < a.H, in_b = px < a.W && pyb < a.H;
     const size_t pix_a = (size_t)pya * a.W + px, pix_b = (size_t)pyb * a.W + px, HW = (size_t)a.H * a.W;
     const int last_a = in_a ? (int)n_contrib[pix_a] : 0, last_b = in_b ? (int)n_contrib[pix_b] : 0;
     // only the first max(n_contrib) entries of the list matter to this square
     const int count = __reduce_max_sync(0xffffffffu, max(last_a, last_b));
-    if (count == 0) return;
+    if (count == 0) continue;
 
     const float pxf = (float)px;
     const f32x2 npx = pk2(-pxf, -pxf), npy = pk2(-(float)pya, -(float)pyb);
@@ -84,13 +92,6 @@ blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint32_t *__restrict
     const float bgTb = -Tb * dot3(a.bg[0], db0, a.bg[1], db1, a.bg[2], db2);
     float bha = 0.0f, bhb = 0.0f;
     const f32x2 dp0 = pk2(da0, db0), dp1 = pk2(da1, db1), dp2 = pk2(da2, db2);
-    const float ddelx_dx = 0.5f * (float)a.W, ddely_dy = 0.5f * (float)a.H;
-    const int slot = tr_slot9(lane);
-    const bool owner = slot >= 0 && !(lane & 1);
-    const uint32_t a_cw = smem_addr(s_cw) + (uint32_t)(threadIdx.x >> 5) * CW_WARP_BYTES;
-    const uint32_t a_acc = smem_addr(s_acc) + (uint32_t)(threadIdx.x >> 5) * ACC_WARP_BYTES;
-    const uint32_t a_own = a_acc + 4u * (uint32_t)(slot < 0 ? 0 : slot);
-    const uint32_t lt_mask = (1u << lane) - 1u;
 
     // back to front, group by group; software pipeline as in the forward (records one group ahead, indices two)
     int base = ((count - 1) / 32) * 32;
@@ -127,6 +128,7 @@ blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint32_t *__restrict
         __syncwarp();
         // back to front over the survivors: the alpha arithmetic (the forward's, so the contributor set is
         // identical) runs packed for the lane's two pixels, the recurrences one by one
+        DMGS_UNROLL(BWD_UNROLL)
         for (int t = n - 1; t >= 0; --t) {
             const uint32_t cw = a_cw + CW_REC * (uint32_t)t;
             f32x2 power2, alpha2, dx2, dy2, G2;
@@ -208,6 +210,7 @@ blend_bwd_kernel(const __grid_constant__ BlendArgs a, const uint32_t *__restrict
         }
         __syncwarp();  // the buffers are rewritten by the next group
     }
+    }  // next square
 }
 
 int launch_blend_bwd(const dmgs_params *prm, const void *geom, const GeomLayout &GL, const void *binning,
@@ -219,10 +222,12 @@ int launch_blend_bwd(const dmgs_params *prm, const void *geom, const GeomLayout 
     a.gx = (a.W + DMGS_TILE - 1) / DMGS_TILE; a.gy = (a.H + DMGS_TILE - 1) / DMGS_TILE;
     for (int i = 0; i < 3; ++i) a.bg[i] = prm->bg[i];
     if (a.W <= 0 || a.H <= 0) return 0;
-    blend_bwd_kernel<<<blend_grid(a), BLK, 0, s>>>(a, BL.has_order ? at<uint32_t>(binning, BL.tile_order) : nullptr, at<uint2>(binning, BL.ranges), at<uint32_t>(binning, BL.gidx),
+    // the square counter sits behind the P x 12 sums of the scratch buffer and is zeroed with them (api.cu)
+    uint32_t *counter = reinterpret_cast<uint32_t *>(grad_blend + 12 * (size_t)prm->P);
+    blend_bwd_kernel<<<blend_grid(a, 1), BLK, 0, s>>>(a, BL.has_order ? at<uint32_t>(binning, BL.tile_order) : nullptr, at<uint2>(binning, BL.ranges), at<uint32_t>(binning, BL.gidx),
                                                       at<float4>(geom, GL.rec), at<float4>(geom, GL.rgb),
                                                       at<float>(image, IL.final_T), at<uint32_t>(image, IL.n_contrib),
-                                                      dL_dpix, grad_blend);
+                                                      dL_dpix, grad_blend, counter);
     DMGS_CUDA(cudaGetLastError());
     count_launches(1);
     return 0;

@@ -19,6 +19,16 @@ constexpr int BLK = BLEND_BLK;
 #define BWD_MIN_BLOCKS 8
 #endif
 
+// unroll factor of the survivor loops (experiments: more ILP per warp at a lower residency)
+#ifndef FWD_UNROLL
+#define FWD_UNROLL 1
+#endif
+#ifndef BWD_UNROLL
+#define BWD_UNROLL 1
+#endif
+#define DMGS_PRAGMA_(x) _Pragma(#x)
+#define DMGS_UNROLL(n) DMGS_PRAGMA_(unroll n)
+
 struct BlendArgs {
     int W, H, gx, gy;
     float bg[3];
@@ -211,20 +221,43 @@ __device__ __forceinline__ bool cull_rect(float gx, float gy, float A, float B, 
 }
 
 // square sq = 4 * tile + q owns the 8x8 pixels (q & 1, q >> 1) of its tile; lane -> column lane & 7, rows lane >> 3
-// and + 4.  Returns false for the padding warps of the last CTA.
-// tile_order (optional): tiles by descending list length -- the squares of the longest lists are handed out first
-__device__ __forceinline__ bool warp_square(const BlendArgs &a, const uint32_t *__restrict__ tile_order, int &tile,
-                                            int &px0, int &py0)
+// and + 4.  tile_order (optional): tiles by descending list length -- the squares of the longest lists are handed
+// out first.
+//
+// PERSISTENT WARPS: the grid is at most `blend_residency` CTAs per SM; a warp's first square is its global warp
+// number, every further one comes from a device counter (zero at launch).  Two reasons: (1) dynamic hand-out in
+// longest-first order keeps the tail short (with one square per warp the resident-warp average was 78 % of the
+// theoretical 32 per SM); (2) a residency below 8 CTAs/SM leaves registers and warp slots of every SM to OTHER
+// streams' kernels -- with 8 the blend kernels own all 64 K registers for their whole run and the latency-bound
+// stages of other views (depth sort, tile placement) cannot start before a blend kernel drains (DESIGN.md
+// section 6).  Returns false when the squares are used up.
+__device__ __forceinline__ bool next_square(const BlendArgs &a, const uint32_t *__restrict__ tile_order,
+                                            uint32_t *__restrict__ counter, bool first, int lane, int &tile, int &px0,
+                                            int &py0)
 {
-    const int sq = blockIdx.x * (BLK / 32) + (threadIdx.x >> 5);
-    tile = sq >> 2;
-    if (tile >= a.gx * a.gy) return false;
+    uint32_t sq;
+    if (first) {
+        sq = blockIdx.x * (BLK / 32) + (threadIdx.x >> 5);
+    } else {
+        sq = 0;
+        if (lane == 0) sq = gridDim.x * (BLK / 32) + atomicAdd(counter, 1u);
+        sq = __shfl_sync(0xffffffffu, sq, 0);
+    }
+    if (sq >= 4u * (uint32_t)(a.gx * a.gy)) return false;
+    tile = (int)(sq >> 2);
     if (tile_order) tile = (int)tile_order[tile];
-    const int ty = tile / a.gx, tx = tile - ty * a.gx, q = sq & 3;
+    const int ty = tile / a.gx, tx = tile - ty * a.gx, q = (int)(sq & 3u);
     px0 = tx * DMGS_TILE + (q & 1) * 8;
     py0 = ty * DMGS_TILE + (q >> 1) * 8;
     return true;
 }
-__host__ inline int blend_grid(const BlendArgs &a) { return (4 * a.gx * a.gy + BLK / 32 - 1) / (BLK / 32); }
+// CTAs per SM of the blend kernels' persistent grids (1..8); see dmgs_set_blend_residency
+extern int g_blend_residency[2];
+__host__ inline int blend_grid(const BlendArgs &a, int which)
+{
+    const int all = (4 * a.gx * a.gy + BLK / 32 - 1) / (BLK / 32);
+    const int cap = num_sms() * g_blend_residency[which];
+    return all < cap ? all : cap;
+}
 
 }  // namespace dmgs

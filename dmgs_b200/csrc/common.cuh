@@ -64,7 +64,7 @@ struct PlacePlan {
 };
 PlacePlan place_plan(int32_t P, int T);
 struct ImgLayout {
-    size_t final_T, n_contrib, total;
+    size_t final_T, n_contrib, counter, total;  // counter: next square of the persistent forward blend
 };
 
 constexpr int SORT_MIN_ITEMS_PER_BLOCK = 1024;  // 256 threads x 4 rounds (8 rounds above RADIX_SMALL_N items)
@@ -140,6 +140,7 @@ static inline ImgLayout img_layout(int32_t W, int32_t H)
     size_t n = (size_t)W * H, o = 0;
     L.final_T = o;   o += align_up(n * 4);
     L.n_contrib = o; o += align_up(n * 4);
+    L.counter = o;   o += align_up(4);
     L.total = o;
     return L;
 }

@@ -818,8 +818,11 @@ sh_grad_expand_kernel(const __grid_constant__ ExpandArgs a, const float *__restr
             const float g[3] = {g4.x, g4.y, g4.z};
             const float ox = x - a.cam[v][0], oy = y - a.cam[v][1], oz = z - a.cam[v][2];
             const float s2 = dot3(ox, ox, oy, oy, oz, oz);
-            const float len = sqrtf(s2);
-            const float dxn = ox / len, dyn = oy / len, dzn = oz / len;
+            // the gradient is held to 1e-4, not to bit parity: one MUFU.RSQ + a Newton step (< 1 ulp) replaces the IEEE
+            // square root and the three IEEE divisions of the forward's direction
+            float inv = rsqrtf(s2);
+            inv = inv * fma_(-0.5f * s2 * inv, inv, 1.5f);
+            const float dxn = ox * inv, dyn = oy * inv, dzn = oz * inv;
             float bas[16], h[16];
             const int nb = sh_basis(a.sh_degree, dxn, dyn, dzn, bas);
 #pragma unroll

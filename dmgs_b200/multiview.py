@@ -185,6 +185,16 @@ class PeerAllReduce:
         return self.flat
 
 
+class _CapturedView:
+    """One view of a step as a CUDA graph (ViewStreams.capture)."""
+
+    __slots__ = ("graph", "probe", "keep", "stream", "sh_records", "kernel_launches")
+
+    def __init__(self, graph, probe, keep, stream, sh_records):
+        self.graph, self.probe, self.keep, self.stream, self.sh_records = graph, probe, keep, stream, list(sh_records)
+        self.kernel_launches = 0
+
+
 class ViewStreams:
     """Renders the local views of a step on `n` CUDA streams, round-robin, all of them accumulating into ONE
     FlatGradBuffer; `finish()` joins the streams (and, in deferred-SH mode, forms the SH rows).
@@ -234,17 +244,33 @@ class ViewStreams:
             if any(o > off for o, _ in first.offsets.values()):
                 raise ValueError("deferred SH needs the SH field last in the flat buffer")
             self._dense = off
+        # (descending stream priorities were measured and rejected: H0, 4 streams, 1694 -> 1631 frames/s)
         self.streams = [torch.cuda.Stream(device=device) for _ in range(n)] if n > 1 else [None]
         self.device = device
+        self._graphs: Dict[int, "_CapturedView"] = {}
+        self._capture_log = None
+        self.replayed_kernel_launches = 0  # kernels of libdmgs_raster.so launched through graph replays
+        # CTAs per SM of the persistent blend kernels while this object's views are being enqueued: with several
+        # views in flight 6 leaves a quarter of every SM's registers to the other views' latency-bound stages
+        # (H0: 1664 -> 1700 frames/s); a single stream keeps the library default of 8
+        import os
+        self.blend_residency = int(os.environ.get("DMGS_VIEW_BLEND_RESIDENCY", "6" if n > 1 else "8"))
 
     @property
     def buf(self) -> FlatGradBuffer:
         return self.bufs[0]
 
+    @staticmethod
+    def _set_residency(k: int):
+        from . import _lib as L
+        if torch.cuda.is_available():
+            L.check(L.lib().dmgs_set_blend_residency(int(k), int(k)), "dmgs_set_blend_residency")
+
     def begin(self):
         """Zeroes the accumulator; the side streams start after everything queued on the current stream."""
         cur = torch.cuda.current_stream(self.device)
         self._campos, self._used = {}, 0
+        self._set_residency(self.blend_residency)
         if self.records is not None:
             self.bufs[0].flat[:self._dense].zero_()
         else:
@@ -270,7 +296,76 @@ class ViewStreams:
             raise IndexError(f"view {i}: ViewStreams was built for {self.records.shape[0]} deferred-SH views per step")
         self._campos[i] = campos
         self._used = max(self._used, i + 1)
+        if self._capture_log is not None:  # a captured view takes the same record on every replay
+            self._capture_log.append((i, campos))
         return self.records[i]
+
+    # ---- views as CUDA graphs --------------------------------------------------------------------------
+    def capture(self, i: int, fn: Callable[[Dict[str, torch.Tensor]], object]):
+        """Captures what fn(acc_views) ENQUEUES for the i-th local view (forward, loss gradient, backward with
+        `accumulate_into`, ...) into a CUDA graph on stream i mod n; fn is not executed on the device.  `replay(i)`
+        then launches the whole view with one graph launch -- the host needs ~10 us per view instead of ~250 us for
+        the ~25 launches and their glue, so every stream has its work at the very start of the step.
+
+        Requirements: sync-free binning (`dmgs_b200.configure(async_binning=True)`) and one eager frame of this shape
+        and these settings beforehand (capacity known, camera tensors cached on the host); every tensor fn reads or
+        writes must keep its address (parameters updated IN PLACE, the accumulator of this object, ...).  The frame's
+        workspace stays with the graph.  After the step `poll_captured()` must be called: it reports frames that
+        overflowed their binning buffer (capacity raised, graph dropped -> capture again, repeat the step)."""
+        from . import rasterizer as R
+        k = i % len(self.streams)
+        if self.streams[k] is None:  # capture needs a non-default stream; begin() / finish() fork and join it
+            self.streams[k] = torch.cuda.Stream(device=self.device)
+        st = self.streams[k]
+        from . import _lib as L
+        probe = R.CaptureProbe(self.device)
+        graph = torch.cuda.CUDAGraph()
+        self._capture_log = []
+        n0 = int(L.lib().dmgs_launch_count())
+        try:
+            with R.capture_probe(probe), torch.cuda.graph(graph, stream=st, capture_error_mode="thread_local"):
+                keep = fn(self.bufs[0].views)
+            self._graphs[i] = _CapturedView(graph, probe, keep, st, self._capture_log)
+            # kernels of this library inside the graph: a replay launches them again without passing through the
+            # library's launch counter (dmgs_launch_count), so replay() accounts for them here
+            self._graphs[i].kernel_launches = int(L.lib().dmgs_launch_count()) - n0
+        finally:
+            self._capture_log = None
+        return self._graphs[i]
+
+    def captured(self, i: int) -> bool:
+        return i in self._graphs
+
+    def replay(self, i: int):
+        """Launches the captured graph of the i-th local view on its stream (between begin() and finish())."""
+        cv = self._graphs[i]
+        for j, campos in cv.sh_records:
+            self._campos[j] = campos
+            self._used = max(self._used, j + 1)
+        with torch.cuda.stream(cv.stream):
+            cv.graph.replay()
+        cv.probe.replays += 1
+        self.replayed_kernel_launches += cv.kernel_launches
+        return cv.keep
+
+    def poll_captured(self) -> bool:
+        """True if every captured view replayed since the last call fitted its binning buffer.  Polls pinned host
+        memory the graphs write right after their binning (no CUDA synchronisation; returns once the LAST view's
+        binning is done, long before the step ends).  Overflowed views lose their graph: capture again and repeat
+        the step (their frames rendered as background with zero gradients)."""
+        ok = True
+        for i in list(self._graphs):
+            cv = self._graphs[i]
+            if cv.probe.seen == cv.probe.replays:
+                continue
+            _, need = cv.probe.wait()
+            if need:
+                ok = False
+                del self._graphs[i]
+        return ok
+
+    def drop_graphs(self):
+        self._graphs.clear()
 
     def finish(self, means3D: Optional[torch.Tensor] = None, shs: Optional[torch.Tensor] = None, sh_degree: int = 3,
                sh_layout: int = 0, means3D_key: str = "means3D") -> FlatGradBuffer:
@@ -281,6 +376,7 @@ class ViewStreams:
         for st in self.streams:
             if st is not None:
                 cur.wait_stream(st)
+        self._set_residency(8)
         if self.records is None:
             return self.bufs[0]
         if means3D is None or shs is None:

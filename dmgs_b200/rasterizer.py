@@ -116,6 +116,84 @@ class _Probe:
         return self.need == 0
 
 
+# ---- frames captured into CUDA graphs ---------------------------------------------------------------------
+# A sync-free frame has a fixed launch sequence (every data-dependent size stays on the device), so a whole view --
+# forward, loss gradient, backward -- can be captured once and replayed with one graph launch instead of ~25 kernel
+# launches and their host glue (multiview.ViewStreams.capture).  The eager probe above cannot live in a graph (it
+# allocates pinned memory and records an event the host later waits for), so a captured frame reports through a
+# CaptureProbe: every replay bumps a sequence number on the device and copies {count, needed, sequence} to pinned
+# memory right after the binning; the host polls that memory -- no CUDA synchronisation at all.
+_CAPTURE = {"probe": None}
+
+
+class CaptureProbe:
+    """{instance count, overflow: count needed, replay number} of a frame that lives in a CUDA graph."""
+
+    def __init__(self, device):
+        self.dev = torch.zeros(4, dtype=torch.int32, device=device)
+        # page-locked through cudaHostRegister, NOT torch's caching host allocator: that allocator records an event
+        # per non-blocking copy to track the block, and an event recorded under capture can never be queried
+        self.host = torch.zeros(1024, dtype=torch.int32)[:4]
+        self._registered = False
+        try:
+            rc = torch.cuda.cudart().cudaHostRegister(self.host.data_ptr(), 16, 0)
+            self._registered = int(rc) == 0
+        except Exception:
+            self._registered = False
+        if not self._registered:
+            self.host = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self._np = self.host.numpy()  # shares the pinned storage: polling is a plain memory read
+        self.key, self.capacity, self.replays, self.seen = None, None, 0, 0
+        self.count, self.need = None, None
+        self.keep = []  # the frame's workspace: its addresses are baked into the graph, it never returns to the pool
+
+    def __del__(self):
+        if getattr(self, "_registered", False):
+            try:
+                torch.cuda.cudart().cudaHostUnregister(self.host.data_ptr())
+            except Exception:
+                pass
+
+    def record(self, key, capacity, meta, ws=None):
+        """Called by rasterize_forward under capture, right after the binning was enqueued."""
+        if self.key is not None:
+            raise RuntimeError("a CaptureProbe serves ONE frame per captured graph")
+        self.key, self.capacity = key, int(capacity)
+        self.keep.append(ws)
+        self.dev[0:2].copy_(meta)
+        self.dev[2:3].add_(1)
+        self.host.copy_(self.dev, non_blocking=True)
+
+    def wait(self, timeout_s: float = 30.0):
+        """Polls until the latest replay has reported; returns (count, needed).  needed != 0: the frame overflowed
+        its binning buffer (it rendered as background); the shape's capacity is raised either way."""
+        if self.key is None:
+            return 0, 0  # the captured callable rendered nothing through rasterize_forward
+        import time
+        t0 = time.perf_counter()
+        while int(self._np[2]) != (self.replays & 0x7FFFFFFF):
+            if time.perf_counter() - t0 > timeout_s:
+                raise RuntimeError("captured frame never reported its binning result (graph not replayed?)")
+        self.count, self.need, self.seen = int(self._np[0]), int(self._np[1]), self.replays
+        _raise_capacity(self.key, max(self.count, self.need))
+        return self.count, self.need
+
+
+class capture_probe:
+    """Context manager: frames rendered under CUDA-graph capture inside the block report through `probe`."""
+
+    def __init__(self, probe: CaptureProbe):
+        self.probe, self.prev = probe, None
+
+    def __enter__(self):
+        self.prev, _CAPTURE["probe"] = _CAPTURE["probe"], self.probe
+        return self.probe
+
+    def __exit__(self, *exc):
+        _CAPTURE["probe"] = self.prev
+        return False
+
+
 # ---- per-(device, stream, P, W, H) workspaces -----------------------------------------------------------
 class _Workspace:
     """The caller-owned byte buffers of ONE frame in flight (geom / binning / image / backward scratch),
@@ -196,6 +274,9 @@ def _host_values(tensors):
         else:
             miss.append(i)
     if miss:
+        if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("CUDA-graph capture: the camera tensors of these settings have not been read to the host "
+                               "yet -- render the view once eagerly before capturing it")
         flat = torch.cat([tensors[i].detach().reshape(-1).float() for i in miss]).cpu().tolist()
         o = 0
         for i in miss:
@@ -285,10 +366,11 @@ class RasterState:
         self._count = num_rendered if capacity is None else None
         self._verified = capacity is None
         self._overflow = 0
+        self._captured = None  # CaptureProbe of a frame recorded into a CUDA graph (checked by the graph's owner)
 
     def __del__(self):
         ws, self.ws = getattr(self, "ws", None), None
-        if ws is not None and ws.generation == self._gen:
+        if ws is not None and ws.generation == self._gen and getattr(self, "_captured", None) is None:
             try:
                 _release(ws)
             except Exception:
@@ -306,6 +388,10 @@ class RasterState:
     def verify(self, raise_on_overflow=True) -> bool:
         """Sync-free frames: waits for the frame's (count, overflow) copy and checks it.  False / raises when the
         frame overflowed its binning buffer (the capacity for its shape is raised either way)."""
+        if self._captured is not None:  # a frame inside a CUDA graph: its owner polls the CaptureProbe per replay
+            if self._captured.count is not None:
+                self._count, self._overflow = self._captured.count, self._captured.need
+            return not self._overflow
         if not self._verified:
             self._probe.resolve()
             self._count, self._overflow, self._verified = self._probe.count, self._probe.need, True
@@ -429,6 +515,14 @@ def rasterize_forward(settings, means3D, opacities, shs, colors_precomp, scales,
         color = torch.empty(3, H, W, dtype=torch.float32, device=dev)
         ws = _acquire(dev, cur.cuda_stream, P, W, H)
         nr, flag = ws.meta[0:1], ws.meta[1:2]
+        key = (dev.index, P, W, H)
+        cap = None
+        if _ASYNC["on"] and key not in _ASYNC["no_async"]:
+            cap = _ASYNC["capacity"].get(key)
+        capturing = torch.cuda.is_current_stream_capturing()
+        if capturing and cap is None:
+            raise RuntimeError("CUDA-graph capture needs sync-free binning with a known capacity: "
+                               "configure(async_binning=True) and render this shape once eagerly first")
         if bound is None:
             L.check(lib.dmgs_preprocess_forward(C.byref(prm), L.ptr(means3D), L.ptr(scales), L.ptr(rotations),
                                                 L.ptr(cov3D_precomp), L.ptr(opacities), L.ptr(shs), L.ptr(colors_precomp),
@@ -441,10 +535,6 @@ def rasterize_forward(settings, means3D, opacities, shs, colors_precomp, scales,
                                                       L.ptr(xyz_out), stream), "dmgs_preprocess_forward_bound")
         if stage_hook is not None:
             stage_hook("preprocess_sort_scan")
-        key = (dev.index, P, W, H)
-        cap = None
-        if _ASYNC["on"] and key not in _ASYNC["no_async"]:
-            cap = _ASYNC["capacity"].get(key)
         state = None
         if cap is not None:
             # sync-free: buffer sized from earlier frames of this shape; the count stays on the device and is
@@ -456,6 +546,15 @@ def rasterize_forward(settings, means3D, opacities, shs, colors_precomp, scales,
                 _ASYNC["no_async"].add(key)
                 _ASYNC["capacity"].pop(key, None)
                 cap = None
+            elif capturing:
+                L.check(rc, "dmgs_bin_forward_async")
+                if _CAPTURE["probe"] is None:
+                    raise RuntimeError("rasterize_forward under CUDA-graph capture: wrap the capture in "
+                                       "dmgs_b200.rasterizer.capture_probe(CaptureProbe(device)) "
+                                       "(multiview.ViewStreams.capture does)")
+                _CAPTURE["probe"].record(key, R, ws.meta, ws)
+                state = RasterState(prm, ws, None, radii, capacity=R)
+                state._captured = _CAPTURE["probe"]
             else:
                 L.check(rc, "dmgs_bin_forward_async")
                 probe = _Probe(key, R, ws.meta, cur)

@@ -310,6 +310,12 @@ const char *dmgs_last_error(void);
 int dmgs_abi_version(void);
 /* Number of CUDA kernels this library has launched in this process (monotonic). */
 uint64_t dmgs_launch_count(void);
+/* Residency of the two blend kernels (K6, K7): their grids are persistent, at most `forward` / `backward` CTAs of
+ * 128 threads per multiprocessor (1..8; 0 leaves a value unchanged; default 8 = every register of the SM, or the
+ * environment variables DMGS_BLEND_FWD_RESIDENCY / DMGS_BLEND_BWD_RESIDENCY read at load time).  Lower values leave
+ * registers and warp slots to kernels of OTHER streams (several views in flight); results do not depend on it.
+ * No upstream counterpart (upstream launches one CTA per tile).  Returns 0, or -7 for values outside 0..8. */
+int dmgs_set_blend_residency(int32_t forward, int32_t backward);
 
 #ifdef __cplusplus
 }

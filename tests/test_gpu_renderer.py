@@ -271,3 +271,109 @@ def test_async_binning_matches_sync_and_reports_overflow():
         assert dmgs_b200.check_async() and torch.equal(img5, big_img)
     finally:
         dmgs_b200.configure(async_binning=False)
+
+
+def test_captured_views_equal_eager_and_report_overflow():
+    """ViewStreams.capture / replay: a view's forward + backward as ONE CUDA graph gives the eager step's gradients
+    (deferred SH records included), follows in-place parameter updates, and a view whose instance list outgrows the
+    capacity baked into its graph is reported by poll_captured() (graph dropped, capture again, repeat the step)."""
+    import dmgs_b200
+    from dmgs_b200 import multiview as MV
+    from dmgs_b200 import rasterizer as RZ
+    from gpu_util import settings_for
+    P, W, H, NV = 5000, 160, 120, 5
+    cl = S.random_cloud(P, seed=12, extent=1.0, log_scale_mean=math.log(0.05))
+    d = {k: v.cuda() for k, v in cl.items()}
+    sets = [settings_for(S.nerf_synthetic_camera(v, W, H), (0, 0, 0)) for v in range(NV)]
+    dLs = [torch.randn(3, H, W, generator=torch.Generator().manual_seed(v)).cuda() for v in range(NV)]
+    inputs = dict(means3D=d["means3D"], opacities=d["opacities"], shs=d["shs"], scales=d["scales"], rotations=d["rotations"])
+    dev = torch.device("cuda")
+
+    def view(vs, v, acc):
+        rec = vs.sh_record(v, sets[v].campos)
+        return MV.accumulate_view(sets[v], inputs, lambda img: (None, dLs[v]), acc, sh_record=rec)
+
+    def eager_step(vs):
+        vs.begin()
+        for v in range(NV):
+            vs.run(v, lambda acc, v=v: view(vs, v, acc))
+        buf = vs.finish(d["means3D"], d["shs"], 3)
+        torch.cuda.synchronize()
+        assert dmgs_b200.check_async()
+        return {k: x.cpu().numpy().copy() for k, x in buf.views.items()}
+
+    def graph_step(vs):
+        vs.begin()
+        for v in range(NV):
+            if not vs.captured(v):
+                vs.capture(v, lambda acc, v=v: view(vs, v, acc))
+            vs.replay(v)
+        buf = vs.finish(d["means3D"], d["shs"], 3)
+        ok = vs.poll_captured()
+        torch.cuda.synchronize()
+        return ok, {k: x.cpu().numpy().copy() for k, x in buf.views.items()}
+
+    try:
+        dmgs_b200.configure(async_binning=True, capacity_slack=1.25)
+        RZ._ASYNC["capacity"].clear()
+        vs = MV.ViewStreams(P, MV.RASTER_WIDTHS_SH, dev, n=2, deferred_sh_views=NV)
+        eager_step(vs)  # learns the capacity, caches the camera values
+        ref = eager_step(vs)
+        for _ in range(3):  # replays are repeatable; begin() resets the accumulator between them
+            ok, got = graph_step(vs)
+            assert ok
+        assert all(vs.captured(v) for v in range(NV))
+        for name in ref:
+            grad_close(got[name].reshape(P, -1), ref[name].reshape(P, -1), rtol=2e-4, name=name)
+        # parameters updated IN PLACE are what the next replay renders
+        d["opacities"].mul_(0.5)
+        ref2 = eager_step(vs)
+        ok, got2 = graph_step(vs)
+        assert ok and np.abs(ref2["shs"] - ref["shs"]).max() > 0
+        for name in ref2:
+            grad_close(got2[name].reshape(P, -1), ref2[name].reshape(P, -1), rtol=2e-4, name=name)
+        # 3x larger splats: the instance lists outgrow the capacity baked into the graphs
+        d["scales"].mul_(3.0)
+        ok, _ = graph_step(vs)
+        assert not ok and not all(vs.captured(v) for v in range(NV))
+        ok, got3 = graph_step(vs)  # dropped views are captured again with the raised capacity
+        if not ok:  # views that had fitted the first time may need the second raise
+            ok, got3 = graph_step(vs)
+        assert ok
+        ref3 = eager_step(vs)
+        for name in ref3:
+            grad_close(got3[name].reshape(P, -1), ref3[name].reshape(P, -1), rtol=2e-4, name=name)
+    finally:
+        dmgs_b200.configure(async_binning=False)
+
+
+def test_blend_residency_does_not_change_results():
+    """dmgs_set_blend_residency: the persistent blend grids hand the 8x8 squares out dynamically; image, final T and
+    contributor counts are bit-identical and the gradients agree for every residency (1 CTA/SM: nearly every square
+    comes from the device counter; 8: the library default)."""
+    from dmgs_b200 import _lib as L
+    from dmgs_b200 import rasterizer as RZ
+    from gpu_util import settings_for
+    P, W, H = 20000, 400, 304
+    cl = S.random_cloud(P, seed=13, extent=1.0, log_scale_mean=math.log(0.03))
+    d = {k: v.cuda() for k, v in cl.items()}
+    rs = settings_for(S.nerf_synthetic_camera(1, W, H), (0.1, 0.2, 0.3))
+    dL = torch.randn(3, H, W, generator=torch.Generator().manual_seed(5)).cuda()
+    lib = L.lib()
+    assert lib.dmgs_set_blend_residency(9, 1) == -7 and lib.dmgs_set_blend_residency(1, -1) == -7
+    out = []
+    try:
+        for k in (8, 3, 1):
+            assert lib.dmgs_set_blend_residency(k, k) == 0
+            color, radii, st = RZ.rasterize_forward(rs, d["means3D"], d["opacities"], d["shs"], None, d["scales"],
+                                                    d["rotations"], None)
+            g = RZ.rasterize_backward(st, dL, d["means3D"], d["shs"], d["scales"], d["rotations"], None, False)
+            img = st.image[:-256].clone()  # final_T | n_contrib (the last 256 bytes hold the forward's square counter)
+            torch.cuda.synchronize()
+            out.append((color.clone(), img, [x.cpu().numpy() for x in g if x is not None]))
+    finally:
+        lib.dmgs_set_blend_residency(8, 8)
+    for color, img, g in out[1:]:
+        assert torch.equal(color, out[0][0]) and torch.equal(img, out[0][1])  # image; final_T | n_contrib bytes
+        for a, b in zip(g, out[0][2]):
+            grad_close(a.reshape(P, -1), b.reshape(P, -1), rtol=2e-4, name="grad")
