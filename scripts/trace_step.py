@@ -3,7 +3,7 @@
 in the image): which kernels run concurrently, how long the device idles, how the stages of different views
 interleave.  Writes a compact per-kernel table (name, stream, start us, duration us) and a summary.
 
-    python scripts/trace_step.py OUT_DIR [streams] [front_priority 0|1] [steps]
+    python scripts/trace_step.py OUT_DIR [streams] [graphs 0|1] [steps]
 """
 import json
 import math
@@ -22,12 +22,12 @@ from dmgs_b200.rasterizer import rasterize_backward, rasterize_forward  # noqa: 
 def main():
     out = sys.argv[1]
     n_streams = int(sys.argv[2]) if len(sys.argv) > 2 else 4
-    prio = bool(int(sys.argv[3])) if len(sys.argv) > 3 else False
+    graphs = bool(int(sys.argv[3])) if len(sys.argv) > 3 else False
     steps = int(sys.argv[4]) if len(sys.argv) > 4 else 2
     os.makedirs(out, exist_ok=True)
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
-    dmgs_b200.configure(async_binning=True, front_priority=prio)
+    dmgs_b200.configure(async_binning=True)
     P, W, H, V = 1_000_000, 800, 800, 8
     cl = S.random_cloud(P, seed=0, extent=1.3, log_scale_mean=math.log(0.01))
     names = ["means3D", "scales", "rotations", "opacities", "shs"]
@@ -48,12 +48,22 @@ def main():
         rasterize_backward(st, dLs[j], d["means3D"], d["shs"], d["scales"], d["rotations"], None, False,
                            accumulate_into=acc, sh_record=rec, verify=False)
 
+    ready = [False]
+
     def step():
         vs.begin()
         for j in range(V):
-            vs.run(j, lambda acc, j=j: one_view(j, acc))
+            if graphs and ready[0]:  # one CUDA graph per view (ViewStreams.capture), as bench.py does
+                if not vs.captured(j):
+                    vs.capture(j, lambda acc, j=j: one_view(j, acc))
+                vs.replay(j)
+            else:
+                vs.run(j, lambda acc, j=j: one_view(j, acc))
         vs.finish(d["means3D"], d["shs"], 3)
-        if not dmgs_b200.check_async():
+        ok = dmgs_b200.check_async()
+        ok = vs.poll_captured() and ok
+        ready[0] = True
+        if not ok:
             step()
 
     for _ in range(4):
@@ -73,7 +83,7 @@ def main():
     t0 = ks[0]["ts"]
     rows = [{"name": e["name"][:60], "stream": e["args"].get("stream"), "ts": round(e["ts"] - t0, 2), "dur": round(e["dur"], 2)}
             for e in ks]
-    json.dump(rows, open(os.path.join(out, f"kernels_s{n_streams}_p{int(prio)}.json"), "w"))
+    json.dump(rows, open(os.path.join(out, f"kernels_s{n_streams}_g{int(graphs)}.json"), "w"))
     # summary: busy time (union of intervals), concurrency-weighted time, per-kernel totals
     end = max(r["ts"] + r["dur"] for r in rows)
     pts = sorted([(r["ts"], 1) for r in rows] + [(r["ts"] + r["dur"], -1) for r in rows])
@@ -90,11 +100,11 @@ def main():
         a = tot.setdefault(k, [0, 0.0])
         a[0] += 1
         a[1] += r["dur"]
-    summ = {"streams": n_streams, "front_priority": prio, "steps": steps, "span_us": round(end, 1),
+    summ = {"streams": n_streams, "cuda_graphs": graphs, "steps": steps, "span_us": round(end, 1),
             "us_per_frame": round(end / (steps * V), 1), "busy_us": round(busy, 1), "idle_us": round(end - busy, 1),
             "time_at_concurrency_us": {str(k): round(v, 1) for k, v in sorted(conc.items())},
             "kernel_totals_us": {k: [n, round(t, 1), round(t / n, 1)] for k, (n, t) in sorted(tot.items(), key=lambda x: -x[1][1])}}
-    json.dump(summ, open(os.path.join(out, f"summary_s{n_streams}_p{int(prio)}.json"), "w"), indent=1)
+    json.dump(summ, open(os.path.join(out, f"summary_s{n_streams}_g{int(graphs)}.json"), "w"), indent=1)
     print(json.dumps(summ)[:3000])
 
 
