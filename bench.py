@@ -479,16 +479,31 @@ def run_ours(args):
         inputs = {k: bufs[k] for k in names}
         vs.begin()
         losses = []
-        for j, v in enumerate(my_views):
+
+        def view(j, v, acc):  # forward, loss, backward of one view on the staged inputs of this slot
             dl = dLs[j % len(dLs)]
             rec = vs.sh_record(j, settings[v].campos)
-            losses.append(vs.run(j, lambda acc, v=v, dl=dl, rec=rec: MV.accumulate_view(
-                settings[v], inputs, lambda img: ((img * dl).sum(), dl), acc, sh_record=rec)[0]))
+            return MV.accumulate_view(settings[v], inputs, lambda img: ((img * dl).sum(), dl), acc, sh_record=rec)[0]
+
+        for j, v in enumerate(my_views):
+            key = 1000 * (slot + 1) + j  # one graph per (staging slot, view): the slot's device buffers keep their addresses
+            if graphs["ready"] and not vs.captured(key):
+                try:
+                    vs.capture(key, lambda acc, j=j, v=v: view(j, v, acc))
+                    graphs["captures"] += 1
+                except Exception as e:
+                    graphs["ready"], graphs["error"] = False, f"{type(e).__name__}: {e}"[:200]
+                    vs.drop_graphs()
+            if graphs["ready"]:
+                losses.append(vs.replay(key))  # the captured callable's result: the view's loss (a static 0-d tensor)
+            else:
+                losses.append(vs.run(j, lambda acc, j=j, v=v: view(j, v, acc)))
         vs.finish(inputs["means3D"], inputs["shs"], 3)
         if world > 1:
             vs.all_reduce_()
         host_loss = float(torch.stack(losses).sum().cpu())  # device -> host read of the step's result
-        if not dmgs_b200.check_async():
+        ok = dmgs_b200.check_async()
+        if not (vs.poll_captured() and ok):
             staged.ready[slot] = torch.cuda.Event()
             staged.ready[slot].record()
             return e2e_step_training(i, last)
@@ -515,7 +530,9 @@ def run_ours(args):
         return (views_per_rank * world * Ke) / dt
 
     e2e_module = time_e2e(e2e_step_module) if full else None
+    vs.drop_graphs()  # the graphs of the `value` region own one workspace each: free them before capturing the e2e ones
     e2e_training = time_e2e(e2e_step_training) if full else None
+    vs.drop_graphs()
     h2d = staged.bytes_per_step
     # what the staging delivered must be the resident copy, bit for bit (sharded copy + all-gather at N > 1)
     torch.cuda.synchronize()
@@ -621,7 +638,8 @@ def run_ours(args):
                 "after the other, autograd accumulating .grad; host inputs staged from pinned memory every step, loss "
                 "read back every step",
                 "training_step": e2e_training,
-                "training_step_api": "dmgs_b200.multiview training step (ViewStreams + accumulate_view over the C ABI), "
+                "training_step_api": "dmgs_b200.multiview training step (ViewStreams + accumulate_view over the C ABI; one CUDA "
+                                     "graph per (staging slot, view) when graphs are on), "
                                      "same copies and read-back",
                 "staging": ("every rank copies 1/N of every (replicated) input tensor from pinned host memory, the pieces "
                             "are all-gathered over NVLink on the copy stream; h2d_bytes_per_step is per rank" if world > 1
