@@ -614,7 +614,7 @@ def run_ours(args):
                    "one all-reduce of the flat gradient buffer per step)" if world > 1 else "single GPU",
                    "all_reduce": allreduce_kind,
                    "avg_instances_R": Ravg, "view_streams": N_STREAMS,
-                   "blend_residency_ctas_per_sm": vs.blend_residency,
+                   "blend_residency_ctas_per_sm": vs.blend_residency, "place_smem_kb_per_sm": vs.place_smem_kb,
                    "cuda_graphs": ("one graph per view (forward + backward), captured in the warm-up, replayed in the "
                                    f"timed region; {graphs['captures']} captures") if graphs["ready"] else graphs.get("error", "off"),
                    "sh_gradient": "deferred: 16-byte records per view, rows formed once per step (dmgs_sh_grad_expand)" if deferred

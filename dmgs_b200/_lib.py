@@ -56,6 +56,7 @@ _SIGS = {
     "dmgs_preprocess_backward": (C.c_int, [C.POINTER(DmgsParams)] + [_vp] * 16 + [_i32, _vp]),
     "dmgs_launch_count": (C.c_uint64, []),
     "dmgs_set_blend_residency": (C.c_int, [_i32, _i32]),
+    "dmgs_set_place_smem_kb": (C.c_int, [_i32]),
     "dmgs_mark_visible": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp]),
     "dmgs_bind_forward": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _f, _f, _vp, _i32, _vp, _vp, _vp, _vp]),
     "dmgs_bind_backward": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _f, _f, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -104,6 +104,12 @@ extern "C" {
 
 int dmgs_abi_version(void) { return 1; }
 uint64_t dmgs_launch_count(void) { return g_launches.load(); }
+int dmgs_set_place_smem_kb(int32_t kb)
+{
+    if (kb < 64 || kb > 200) { set_error("placement shared memory: 64..200 KB per SM"); return -7; }
+    g_place_smem_kb = kb;
+    return 0;
+}
 int dmgs_set_blend_residency(int32_t forward, int32_t backward)
 {
     if (forward < 0 || forward > 8 || backward < 0 || backward > 8) { set_error("blend residency: 0..8 CTAs per SM"); return -7; }
@@ -238,7 +244,7 @@ static int bin_forward_impl(const dmgs_params *prm, const void *geom, int64_t R,
     if (!binning) { set_error("binning buffer is NULL"); return -6; }
     const GeomLayout GL = geom_layout(P);
     const BinLayout BL = bin_layout(P, R, W, H);
-    const PlacePlan pl = place_plan(P, T);
+    const PlacePlan pl = place_plan_run(P, T);
     if (pl.ok) {
         // direct placement from the depth-sorted Gaussian order (place.cu); ranges fall out of the scan
         if (R > 0 && P > 0) {

@@ -62,7 +62,9 @@ struct PlacePlan {
     int ok, wpb, seg, nseg, groups, rows_per_group;
     size_t smem;
 };
-PlacePlan place_plan(int32_t P, int T);
+PlacePlan place_plan(int32_t P, int T);      // the LAYOUT plan (200 KB of counters per SM): buffer sizes, path decision
+PlacePlan place_plan_run(int32_t P, int T);  // the plan the kernels run with (dmgs_set_place_smem_kb): a prefix of its rows
+extern int g_place_smem_kb;
 struct ImgLayout {
     size_t final_T, n_contrib, counter, total;  // counter: next square of the persistent forward blend
 };
@@ -118,7 +120,7 @@ static inline BinLayout bin_layout(int32_t P, int64_t R, int32_t W, int32_t H)
     if (pl.ok) {
         L.srec = o;       o += align_up((size_t)(P > 0 ? P : 1) * 16);
         L.table = o;      o += align_up((size_t)pl.nseg * T * 4);
-        L.gsum = o;       o += align_up((size_t)pl.groups * T * 4);
+        L.gsum = o;       o += align_up((size_t)((pl.nseg + 1) / 2 + 1 > pl.groups ? (pl.nseg + 1) / 2 + 1 : pl.groups) * T * 4);
         L.tile_start = o; o += align_up(T * 4);
         L.tile_order = o; o += align_up(T * 4);
         L.has_order = (R > 0 && P > 0) ? 1 : 0;  // the cases in which the placement kernels run (api.cu)

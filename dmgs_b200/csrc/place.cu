@@ -29,7 +29,18 @@
 
 namespace dmgs {
 
-PlacePlan place_plan(int32_t P, int T)
+// Shared memory per SM given to the per-warp tile counters.  200 KB (20 warps/SM at 2500 tiles) is the LAYOUT plan:
+// it sizes the count table and decides whether an image takes the placement path at all.  The kernels may RUN with
+// less (dmgs_set_place_smem_kb): they are latency bound (34 % issue utilisation), but at 200 KB no CTA of another
+// stream fits beside them on the SM; at 128 KB six blend CTAs do, and the walk is only 4 % slower.  A smaller
+// budget means fewer, longer segments, i.e. a prefix of the rows the layout reserved.
+int g_place_smem_kb = [] {
+    const char *v = getenv("DMGS_PLACE_SMEM_KB");
+    const int kb = v ? atoi(v) : 0;
+    return kb >= 64 && kb <= 200 ? kb : 200;
+}();
+
+static PlacePlan place_plan_budget(int32_t P, int T, size_t budget)
 {
     PlacePlan p;
     memset(&p, 0, sizeof(p));
@@ -38,7 +49,6 @@ PlacePlan place_plan(int32_t P, int T)
     // test hook: DMGS_TILE_PARTITION=radix forces the radix tile partition (sort.cu) for any image size
     const char *force = getenv("DMGS_TILE_PARTITION");
     if (force && strcmp(force, "radix") == 0) return p;
-    const size_t budget = 200 * 1024;  // shared memory per SM left to the counters
     int wps = (int)(budget / per_warp);
     if (wps > 32) wps = 32;
     if (wps < 2) return p;
@@ -55,6 +65,15 @@ PlacePlan place_plan(int32_t P, int T)
     p.smem = (size_t)p.wpb * per_warp;
     p.ok = 1;
     return p;
+}
+PlacePlan place_plan(int32_t P, int T) { return place_plan_budget(P, T, 200 * 1024); }
+PlacePlan place_plan_run(int32_t P, int T)
+{
+    const PlacePlan full = place_plan(P, T);
+    if (!full.ok || g_place_smem_kb >= 200) return full;
+    const PlacePlan p = place_plan_budget(P, T, (size_t)g_place_smem_kb * 1024);
+    // never more rows than the layout reserved (table: nseg rows; per-CTA sums: ceil(nseg / 2) rows)
+    return p.ok && p.nseg <= full.nseg && p.groups <= (full.nseg + 1) / 2 + 1 ? p : full;
 }
 
 // ------------------------------------------------------------------------------ depth-ordered rectangles

@@ -316,6 +316,12 @@ uint64_t dmgs_launch_count(void);
  * registers and warp slots to kernels of OTHER streams (several views in flight); results do not depend on it.
  * No upstream counterpart (upstream launches one CTA per tile).  Returns 0, or -7 for values outside 0..8. */
 int dmgs_set_blend_residency(int32_t forward, int32_t backward);
+/* Shared memory per multiprocessor the tile-placement kernels (K3-K5: per-warp tile counters) run with, 64..200 KB
+ * (default 200 = shortest walk for a frame rendered alone; env DMGS_PLACE_SMEM_KB at load time).  `ViewStreams` uses
+ * 128 KB while several views are in flight: six blend CTAs of another view then fit beside a placement kernel.  Buffer
+ * layouts do not depend on it (they are sized for 200 KB), so it may change between any two calls; the tile lists are
+ * identical for every value.  Returns 0, or -7 outside 64..200. */
+int dmgs_set_place_smem_kb(int32_t kb);
 
 #ifdef __cplusplus
 }

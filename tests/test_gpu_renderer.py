@@ -377,3 +377,39 @@ def test_blend_residency_does_not_change_results():
         assert torch.equal(color, out[0][0]) and torch.equal(img, out[0][1])  # image; final_T | n_contrib bytes
         for a, b in zip(g, out[0][2]):
             grad_close(a.reshape(P, -1), b.reshape(P, -1), rtol=2e-4, name="grad")
+
+
+def test_place_smem_budget_does_not_change_the_lists():
+    """dmgs_set_place_smem_kb: the placement kernels run with fewer, longer segments; tile ranges and the depth-ordered
+    lists are bit-identical for every budget, and the buffer layout does not depend on it (the budget may change
+    between a frame's forward and its backward)."""
+    from dmgs_b200 import _lib as L
+    from dmgs_b200 import rasterizer as RZ
+    from gpu_util import settings_for
+    P, W, H = 30000, 640, 400
+    cl = S.random_cloud(P, seed=14, extent=1.0, log_scale_mean=math.log(0.03))
+    d = {k: v.cuda() for k, v in cl.items()}
+    rs = settings_for(S.nerf_synthetic_camera(3, W, H), (0.0, 0.0, 0.0))
+    dL = torch.randn(3, H, W, generator=torch.Generator().manual_seed(6)).cuda()
+    lib = L.lib()
+    assert lib.dmgs_set_place_smem_kb(32) == -7 and lib.dmgs_set_place_smem_kb(256) == -7
+    out = []
+    try:
+        for kb_fwd, kb_bwd in ((200, 200), (128, 128), (64, 200), (200, 64)):
+            assert lib.dmgs_set_place_smem_kb(kb_fwd) == 0
+            color, radii, st = RZ.rasterize_forward(rs, d["means3D"], d["opacities"], d["shs"], None, d["scales"],
+                                                    d["rotations"], None)
+            b = st.binning_arrays()
+            lists = (b["gidx"].clone(), b["ranges"].clone())
+            assert lib.dmgs_set_place_smem_kb(kb_bwd) == 0
+            g = RZ.rasterize_backward(st, dL, d["means3D"], d["shs"], d["scales"], d["rotations"], None, False)
+            torch.cuda.synchronize()
+            out.append((color.clone(), lists, [x.cpu().numpy() for x in g if x is not None]))
+    finally:
+        lib.dmgs_set_place_smem_kb(200)
+    assert out[0][1][0].numel() > 50000
+    for color, lists, g in out[1:]:
+        assert torch.equal(color, out[0][0])
+        assert torch.equal(lists[0], out[0][1][0]) and torch.equal(lists[1], out[0][1][1])
+        for a, b in zip(g, out[0][2]):
+            grad_close(a.reshape(P, -1), b.reshape(P, -1), rtol=2e-4, name="grad")
