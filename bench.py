@@ -529,7 +529,11 @@ def run_ours(args):
             dt = float(tm.item())
         return (views_per_rank * world * Ke) / dt
 
+    # gradient accumulation over the step's views inside the kernels (opt-in: see dmgs_b200.configure)
+    FUSED_ACC = os.environ.get("DMGS_BENCH_FUSED_ACC", "1") == "1"
+    dmgs_b200.configure(accumulate_grad_in_place=FUSED_ACC)
     e2e_module = time_e2e(e2e_step_module) if full else None
+    dmgs_b200.configure(accumulate_grad_in_place=False)
     vs.drop_graphs()  # the graphs of the `value` region own one workspace each: free them before capturing the e2e ones
     e2e_training = time_e2e(e2e_step_training) if full else None
     vs.drop_graphs()
@@ -635,8 +639,11 @@ def run_ours(args):
                             "configure(async_binning=True)",
         "e2e": {"value": e2e_module, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "steps": Ke, "api": "drop-in GaussianRasterizer nn.Module (the reference-facing call), the step's views one "
-                "after the other, autograd accumulating .grad; host inputs staged from pinned memory every step, loss "
-                "read back every step",
+                "after the other, loss.backward() accumulating .grad over the views ("
+                + ("configure(async_binning=True, accumulate_grad_in_place=True): from the second view on the kernels add "
+                   "into the existing .grad instead of autograd's AccumulateGrad pass" if FUSED_ACC else
+                   "configure(async_binning=True); autograd's AccumulateGrad adds") +
+                "); host inputs staged from pinned memory every step, loss read back every step",
                 "training_step": e2e_training,
                 "training_step_api": "dmgs_b200.multiview training step (ViewStreams + accumulate_view over the C ABI; one CUDA "
                                      "graph per (staging slot, view) when graphs are on), "

@@ -58,18 +58,32 @@ _ASYNC = {"on": False, "slack": 1.25, "capacity": {}, "no_async": set(), "pendin
 _MAX_PENDING = 256
 
 
-def configure(async_binning: Optional[bool] = None, capacity_slack: Optional[float] = None):
+# ---- optional fused gradient accumulation of the autograd module (gradient-accumulation loops) -----------------------
+_FUSED_ACC = {"on": False}
+
+
+def configure(async_binning: Optional[bool] = None, capacity_slack: Optional[float] = None,
+              accumulate_grad_in_place: Optional[bool] = None):
     """async_binning: size the binning buffer from earlier frames instead of reading the instance
     count back (default False = upstream behaviour).  capacity_slack: head-room factor (default 1.25).
 
     Sync-free frames are verified, never trusted silently: every frame copies its instance count and
     overflow flag to pinned host memory behind an event; `rasterize_backward` (and the autograd
     backward) waits for that event -- long complete by then -- and raises `BinningOverflowError` if
-    the frame overflowed, `check_async()` polls all frames since the last call."""
+    the frame overflowed, `check_async()` polls all frames since the last call.
+
+    accumulate_grad_in_place (default False): when the autograd module's backward finds that an input is a leaf whose
+    `.grad` already holds a gradient (the second and later views of a gradient-accumulation step), the kernels ADD
+    into that `.grad` and autograd receives None for the input -- instead of writing a fresh [P, ...] gradient that
+    autograd's AccumulateGrad then adds with one more pass over both tensors (H0: 98 us of a 1089 us frame).  Only
+    meaningful under `loss.backward()`: `torch.autograd.grad`, tensor hooks and `create_graph` never see those
+    gradients, so it is opt-in (the same trade as Megatron's gradient-accumulation fusion)."""
     if async_binning is not None:
         _ASYNC["on"] = bool(async_binning)
     if capacity_slack is not None:
         _ASYNC["slack"] = float(capacity_slack)
+    if accumulate_grad_in_place is not None:
+        _FUSED_ACC["on"] = bool(accumulate_grad_in_place)
     if not _ASYNC["on"]:
         _ASYNC["pending"].clear()
 
@@ -735,6 +749,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.state = state
         ctx.save_for_backward(means3D_c, sh_c, sc_c, rot_c, cov_c)
         ctx.has_col = col_c is not None
+        # the caller's own tensors, for configure(accumulate_grad_in_place=True)
+        ctx.leaves = (means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp) if _FUSED_ACC["on"] else None
         if holder is not None:
             holder.last = state
         ctx.mark_non_differentiable(radii)
@@ -745,10 +761,48 @@ class _RasterizeGaussians(torch.autograd.Function):
         if ctx.state is None:
             return (None,) * 12
         means3D, sh, scales, rotations, cov = ctx.saved_tensors
+        leaves, ctx.leaves = ctx.leaves, None
+        if leaves is not None and _FUSED_ACC["on"]:
+            fused = _fused_accumulate(ctx, leaves, grad_color, means3D, sh, scales, rotations, cov)
+            if fused is not None:
+                return fused
         g = rasterize_backward(ctx.state, grad_color.contiguous().float(), means3D, sh, scales, rotations, cov,
                                ctx.has_col)
         g_means3D, g_means2D, g_shs, g_col, g_op, g_scales, g_rots, g_cov = g
         return (g_means3D, g_means2D, g_shs, g_col, g_op, g_scales, g_rots, g_cov, None, None, None, None)
+
+
+def _fused_accumulate(ctx, leaves, grad_color, means3D, sh, scales, rotations, cov):
+    """configure(accumulate_grad_in_place=True): gradients of inputs whose `.grad` exists are added into it by the
+    kernels (autograd gets None for them); the others get a fresh zero-initialised tensor that the kernels add into.
+    Returns None when nothing would be gained (no input has a usable `.grad`)."""
+    names = ("means3D", "means2D", "shs", "colors_precomp", "opacities", "scales", "rotations", "cov3D_precomp")
+    P = ctx.state.prm.P
+    acc, ret, hit = {}, [None] * 8, False
+    for k, (name, t) in enumerate(zip(names, leaves)):
+        if t is None or not ctx.needs_input_grad[k]:
+            continue
+        g = t.grad if t.is_leaf else None
+        ok = (g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.shape == t.shape and g.is_cuda
+              and not getattr(t, "_backward_hooks", None))
+        if ok:
+            acc[name], hit = g, True
+        else:
+            acc[name] = ret[k] = torch.zeros(t.shape, dtype=torch.float32, device=means3D.device)
+    if not hit:
+        return None
+    # the C entry point always writes these three: inputs that need no gradient get a scratch tensor
+    for name, shape in (("means3D", (P, 3)), ("means2D", (P, 3)), ("opacities", (P, 1))):
+        if name not in acc:
+            acc[name] = torch.zeros(shape, dtype=torch.float32, device=means3D.device)
+    for name, t in (("shs", sh), ("scales", scales), ("rotations", rotations), ("cov3D_precomp", cov)):
+        if t is not None and name not in acc:
+            acc[name] = torch.zeros(t.shape, dtype=torch.float32, device=means3D.device)
+    if ctx.has_col and "colors_precomp" not in acc:
+        acc["colors_precomp"] = torch.zeros(P, 3, dtype=torch.float32, device=means3D.device)
+    rasterize_backward(ctx.state, grad_color.contiguous().float(), means3D, sh, scales, rotations, cov, ctx.has_col,
+                       accumulate_into=acc)
+    return tuple(ret) + (None, None, None, None)
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,

@@ -413,3 +413,44 @@ def test_place_smem_budget_does_not_change_the_lists():
         assert torch.equal(lists[0], out[0][1][0]) and torch.equal(lists[1], out[0][1][1])
         for a, b in zip(g, out[0][2]):
             grad_close(a.reshape(P, -1), b.reshape(P, -1), rtol=2e-4, name="grad")
+
+
+def test_accumulate_grad_in_place_matches_autograd_accumulation():
+    """configure(accumulate_grad_in_place=True): from the second backward of an accumulation loop on, the kernels add into
+    the leaves' existing .grad (autograd receives None); the accumulated gradients equal autograd's own accumulation, the
+    .grad tensors keep their identity, and inputs without a .grad (a fresh means2D per view) still get theirs."""
+    import dmgs_b200
+    from dmgs_b200 import GaussianRasterizer
+    from gpu_util import settings_for
+    P, W, H, NV = 6000, 176, 128, 3
+    cl = S.random_cloud(P, seed=15, extent=1.0, log_scale_mean=math.log(0.05))
+    sets = [settings_for(S.nerf_synthetic_camera(v, W, H), (0.1, 0.1, 0.1)) for v in range(NV)]
+    dLs = [torch.randn(3, H, W, generator=torch.Generator().manual_seed(20 + v)).cuda() for v in range(NV)]
+    names = ["means3D", "opacities", "shs", "scales", "rotations"]
+
+    def loop(fused):
+        dmgs_b200.configure(accumulate_grad_in_place=fused)
+        t = {k: cl[k].cuda().requires_grad_() for k in names}
+        ids, m2d_grads = None, []
+        for v in range(NV):
+            m2d = torch.zeros_like(t["means3D"], requires_grad=True)
+            img, _ = GaussianRasterizer(sets[v])(means3D=t["means3D"], means2D=m2d, shs=t["shs"], opacities=t["opacities"],
+                                                 scales=t["scales"], rotations=t["rotations"])
+            (img * dLs[v]).sum().backward()
+            m2d_grads.append(m2d.grad.clone())
+            if v == 0:
+                ids = {k: t[k].grad.data_ptr() for k in names}
+        assert all(t[k].grad.data_ptr() == ids[k] for k in names)
+        torch.cuda.synchronize()
+        return {k: t[k].grad.cpu().numpy() for k in names}, [g.cpu().numpy() for g in m2d_grads]
+
+    try:
+        ref, ref2d = loop(False)
+        got, got2d = loop(True)
+    finally:
+        dmgs_b200.configure(accumulate_grad_in_place=False)
+    for k in names:
+        grad_close(got[k].reshape(P, -1), ref[k].reshape(P, -1), rtol=2e-4, name=k)
+    for a, b in zip(got2d, ref2d):
+        assert np.abs(b).max() > 0
+        grad_close(a, b, rtol=2e-4, name="means2D")
