@@ -130,7 +130,7 @@ __device__ __forceinline__ float sh_get(const float *__restrict__ shs, const Dev
 // from its mesh face (Gaussian i = face i / k, barycentric row i % k; bind_math.cuh) -- the binding fused into
 // preprocess: no xyz[P,3] / cov6[P,6] round trip through HBM (xyz_out, optional, serves the texture MLP).
 template <int SHMODE, bool BOUND>
-__global__ void __launch_bounds__(256, BOUND ? 3 : 4)
+__global__ void __launch_bounds__(PRE_BLK, (BOUND ? 3 : 4) * (256 / PRE_BLK))
 preprocess_fwd_kernel(const __grid_constant__ DevParams pr, const __grid_constant__ BindSrc bs, float *__restrict__ xyz_out,
                       const float *__restrict__ means3D, const float *__restrict__ scales,
                       const float *__restrict__ rotations, const float *__restrict__ cov3D_precomp,
@@ -357,15 +357,15 @@ int launch_preprocess_fwd(const dmgs_params *prm, const BindSrc *bind, float *xy
         at<float4>(geom, L.rec), at<float4>(geom, L.rgb), at<uint8_t>(geom, L.clamped), at<float>(geom, L.cov3D),    \
         at<uint32_t>(geom, L.tiles), at<uint2>(geom, L.rect), at<uint32_t>(geom, L.keys_a), at<uint32_t>(geom, L.order), \
         total_instances, key_stat
-    const int grid = (P + 255) / 256;
+    const int grid = (P + PRE_BLK - 1) / PRE_BLK;
     if (bind) {
-        if (mode == 1) preprocess_fwd_kernel<1, true><<<grid, 256, SH_STAGE_SMEM, s>>>(DMGS_FWD_ARGS);
-        else if (mode == 2) preprocess_fwd_kernel<2, true><<<grid, 256, SH_STAGE_SMEM, s>>>(DMGS_FWD_ARGS);
-        else preprocess_fwd_kernel<0, true><<<grid, 256, 0, s>>>(DMGS_FWD_ARGS);
+        if (mode == 1) preprocess_fwd_kernel<1, true><<<grid, PRE_BLK, SH_STAGE_SMEM, s>>>(DMGS_FWD_ARGS);
+        else if (mode == 2) preprocess_fwd_kernel<2, true><<<grid, PRE_BLK, SH_STAGE_SMEM, s>>>(DMGS_FWD_ARGS);
+        else preprocess_fwd_kernel<0, true><<<grid, PRE_BLK, 0, s>>>(DMGS_FWD_ARGS);
     } else {
-        if (mode == 1) preprocess_fwd_kernel<1, false><<<grid, 256, SH_STAGE_SMEM, s>>>(DMGS_FWD_ARGS);
-        else if (mode == 2) preprocess_fwd_kernel<2, false><<<grid, 256, SH_STAGE_SMEM, s>>>(DMGS_FWD_ARGS);
-        else preprocess_fwd_kernel<0, false><<<grid, 256, 0, s>>>(DMGS_FWD_ARGS);
+        if (mode == 1) preprocess_fwd_kernel<1, false><<<grid, PRE_BLK, SH_STAGE_SMEM, s>>>(DMGS_FWD_ARGS);
+        else if (mode == 2) preprocess_fwd_kernel<2, false><<<grid, PRE_BLK, SH_STAGE_SMEM, s>>>(DMGS_FWD_ARGS);
+        else preprocess_fwd_kernel<0, false><<<grid, PRE_BLK, 0, s>>>(DMGS_FWD_ARGS);
     }
 #undef DMGS_FWD_ARGS
     DMGS_CUDA(cudaGetLastError());
@@ -413,7 +413,7 @@ __device__ __forceinline__ void sh_dir_grad(int deg, const float *h, float ox, f
 // binding adjoint (the reference's truncated gradient: cov3D_L constant) to dverts / dg with atomics -- no
 // dL/dxyz[P,3] / dL/dcov6[P,6] is materialised.  dL_dmeans3D = dverts [V,3], dL_dcov3D = dg [1] in that mode.
 template <int SHMODE, bool BOUND>
-__global__ void __launch_bounds__(256, BOUND ? 2 : (SHMODE == 3 ? 4 : 3))
+__global__ void __launch_bounds__(PRE_BLK, (BOUND ? 2 : (SHMODE == 3 ? 4 : 3)) * (256 / PRE_BLK))
 preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const __grid_constant__ BindSrc bs,
                       const float *__restrict__ means3D, const float *__restrict__ scales,
                       const float *__restrict__ rotations, const float *__restrict__ cov3D_precomp,
@@ -659,7 +659,7 @@ preprocess_bwd_kernel(const __grid_constant__ DevParams pr, const __grid_constan
             if (threadIdx.x == 0) {
                 float t = 0;
 #pragma unroll
-                for (int w = 0; w < 8; ++w) t += red[w];
+                for (int w = 0; w < PRE_BLK / 32; ++w) t += red[w];
                 if (t != 0.0f) atomicAdd(dL_dcov3D, t);
             }
         }
@@ -763,15 +763,15 @@ int launch_preprocess_bwd(const dmgs_params *prm, const BindSrc *bind, const flo
     dp, bs, means3D, scales, rotations, cov3D_precomp, shs, radii, at<float>(geom, L.cov3D), at<uint8_t>(geom, L.clamped), \
         at<float4>(geom, L.rgb), reinterpret_cast<const float4 *>(grad_blend), dL_dmeans3D, dL_dmeans2D, dL_dopacity,   \
         dL_dcolprec, dL_dshs, dL_dscales, dL_drots, dL_dcov3D, accumulate
-    const int grid = (P + 255) / 256;
+    const int grid = (P + PRE_BLK - 1) / PRE_BLK;
     if (bind) {
-        if (mode == 1) preprocess_bwd_kernel<1, true><<<grid, 256, SH_STAGE_SMEM, s>>>(DMGS_BWD_ARGS);
-        else if (mode == 2) preprocess_bwd_kernel<2, true><<<grid, 256, SH_STAGE_SMEM, s>>>(DMGS_BWD_ARGS);
-        else preprocess_bwd_kernel<0, true><<<grid, 256, 0, s>>>(DMGS_BWD_ARGS);
-    } else if (mode == 1) preprocess_bwd_kernel<1, false><<<grid, 256, SH_STAGE_SMEM, s>>>(DMGS_BWD_ARGS);
-    else if (mode == 2) preprocess_bwd_kernel<2, false><<<grid, 256, SH_STAGE_SMEM, s>>>(DMGS_BWD_ARGS);
-    else if (mode == 3) preprocess_bwd_kernel<3, false><<<grid, 256, 0, s>>>(DMGS_BWD_ARGS);
-    else preprocess_bwd_kernel<0, false><<<grid, 256, 0, s>>>(DMGS_BWD_ARGS);
+        if (mode == 1) preprocess_bwd_kernel<1, true><<<grid, PRE_BLK, SH_STAGE_SMEM, s>>>(DMGS_BWD_ARGS);
+        else if (mode == 2) preprocess_bwd_kernel<2, true><<<grid, PRE_BLK, SH_STAGE_SMEM, s>>>(DMGS_BWD_ARGS);
+        else preprocess_bwd_kernel<0, true><<<grid, PRE_BLK, 0, s>>>(DMGS_BWD_ARGS);
+    } else if (mode == 1) preprocess_bwd_kernel<1, false><<<grid, PRE_BLK, SH_STAGE_SMEM, s>>>(DMGS_BWD_ARGS);
+    else if (mode == 2) preprocess_bwd_kernel<2, false><<<grid, PRE_BLK, SH_STAGE_SMEM, s>>>(DMGS_BWD_ARGS);
+    else if (mode == 3) preprocess_bwd_kernel<3, false><<<grid, PRE_BLK, 0, s>>>(DMGS_BWD_ARGS);
+    else preprocess_bwd_kernel<0, false><<<grid, PRE_BLK, 0, s>>>(DMGS_BWD_ARGS);
 #undef DMGS_BWD_ARGS
     DMGS_CUDA(cudaGetLastError());
     count_launches(1);
@@ -791,7 +791,7 @@ struct ExpandArgs {
 };
 
 template <int SHMODE>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(PRE_BLK, 2 * (256 / PRE_BLK))
 sh_grad_expand_kernel(const __grid_constant__ ExpandArgs a, const float *__restrict__ means3D, const float *__restrict__ shs,
                       const float *__restrict__ records, float *__restrict__ dL_dshs, float *__restrict__ dL_dmeans3D)
 {
@@ -910,10 +910,10 @@ int launch_sh_grad_expand(int P, int sh_degree, int M, int layout, int V, const 
     for (int v = 0; v < V; ++v)
         for (int c = 0; c < 3; ++c) a.cam[v][c] = campos_host[3 * v + c];
     const bool staged = M == 16 && !((reinterpret_cast<uintptr_t>(dL_dshs) | reinterpret_cast<uintptr_t>(shs)) & 15);
-    const int grid = (P + 255) / 256;
-    if (staged && layout == 0) sh_grad_expand_kernel<1><<<grid, 256, SH_STAGE_SMEM, s>>>(a, means3D, shs, records, dL_dshs, dL_dmeans3D);
-    else if (staged) sh_grad_expand_kernel<2><<<grid, 256, SH_STAGE_SMEM, s>>>(a, means3D, shs, records, dL_dshs, dL_dmeans3D);
-    else sh_grad_expand_kernel<0><<<grid, 256, 0, s>>>(a, means3D, shs, records, dL_dshs, dL_dmeans3D);
+    const int grid = (P + PRE_BLK - 1) / PRE_BLK;
+    if (staged && layout == 0) sh_grad_expand_kernel<1><<<grid, PRE_BLK, SH_STAGE_SMEM, s>>>(a, means3D, shs, records, dL_dshs, dL_dmeans3D);
+    else if (staged) sh_grad_expand_kernel<2><<<grid, PRE_BLK, SH_STAGE_SMEM, s>>>(a, means3D, shs, records, dL_dshs, dL_dmeans3D);
+    else sh_grad_expand_kernel<0><<<grid, PRE_BLK, 0, s>>>(a, means3D, shs, records, dL_dshs, dL_dmeans3D);
     DMGS_CUDA(cudaGetLastError());
     count_launches(1);
     return 0;

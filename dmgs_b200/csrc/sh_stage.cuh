@@ -17,7 +17,10 @@ namespace dmgs {
 constexpr int SH_ROW_FLOATS = 48;                   // 16 coefficients x 3 channels
 constexpr int SH_ROW_BYTES = SH_ROW_FLOATS * 4;     // 192
 constexpr int SH_ROW_STRIDE = 52;                   // floats
-constexpr int SH_STAGE_THREADS = 256;
+#ifndef PRE_BLK
+#define PRE_BLK 128   /* threads per CTA of the per-Gaussian kernels: 128 (8 K registers, 26 KB of staged rows) fits beside the blend and placement CTAs of other views where 256 did not (H0: 1741 -> 1766 frames/s, alone 3 % faster) */
+#endif
+constexpr int SH_STAGE_THREADS = PRE_BLK;
 constexpr int SH_STAGE_SMEM = SH_STAGE_THREADS * SH_ROW_STRIDE * 4 + (SH_STAGE_THREADS / 32) * 8;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
