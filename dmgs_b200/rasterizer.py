@@ -188,6 +188,7 @@ class CaptureProbe:
         while int(self._np[2]) != (self.replays & 0x7FFFFFFF):
             if time.perf_counter() - t0 > timeout_s:
                 raise RuntimeError("captured frame never reported its binning result (graph not replayed?)")
+            time.sleep(2e-5)  # give the interpreter lock away: other host threads (clock sampling, data loading) run on
         self.count, self.need, self.seen = int(self._np[0]), int(self._np[1]), self.replays
         _raise_capacity(self.key, max(self.count, self.need))
         return self.count, self.need
