@@ -97,7 +97,8 @@ int dmgs_backward(const dmgs_params *prm, const float *means3D, const float *sca
                   void *stream);
 size_t dmgs_backward_scratch_bytes(int32_t P);
 /* The two halves of dmgs_backward, callable separately (bench.py brackets them with CUDA events):
- * K7 accumulates per-Gaussian blend gradients into `scratch`; K8+K9 consume it.  With
+ * K7 accumulates per-Gaussian blend gradients into `scratch` (P x 12 floats, followed by the square
+ * counter of its persistent grid: always size it with dmgs_backward_scratch_bytes); K8+K9 consume it.  With
  * accumulate != 0 the gradients are ADDED to the output buffers (view-batched training:
  * one flat gradient buffer summed over the views of a step, no extra accumulation pass). */
 int dmgs_blend_backward(const dmgs_params *prm, const void *geom, const void *binning, const void *image,
@@ -296,7 +297,8 @@ int dmgs_adam_exchange_peer(int32_t world, int32_t rank, int32_t nseg, const dmg
  *          scan in depth order; radix tile partition only) u32[P]
  * binning: [0] sorted tile ids u32[R] (materialised by dmgs_sorted_keys on the placement path)
  *          [1] sorted Gaussian indices u32[R]  [2] ranges u32[T][2]
- * image:   [0] final_T f32[H*W]  [1] n_contrib u32[H*W]                                        */
+ * image:   [0] final_T f32[H*W]  [1] n_contrib u32[H*W]  (the buffer ends with 256 bytes of launch
+ *          state: the square counter of the persistent forward blend)                           */
 int dmgs_geom_layout(int32_t P, int64_t *offsets9);
 int dmgs_binning_layout(int32_t P, int64_t num_rendered, int32_t W, int32_t H, int64_t *offsets3);
 int dmgs_image_layout(int32_t W, int32_t H, int64_t *offsets2);
