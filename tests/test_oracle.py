@@ -269,3 +269,103 @@ def test_binning_equals_one_stable_sort_of_the_64_bit_keys():
     ne = counts > 0
     assert np.array_equal(b["ranges"][ne, 0], (ends - counts)[ne]) and np.array_equal(b["ranges"][ne, 1], ends[ne])
     assert not b["ranges"][~ne].any()
+
+
+# ------------------------------------------------------------------------------ rasteriser oracle: properties
+# The splat arithmetic of the oracle has no reference-held vectors, so besides the fp64 autograd
+# comparison above it is held to properties any faithful restatement of the published algorithm must have.
+def _render_precomp(pr, cl, colors, opac=None, order=None):
+    m, s, r = cl["means3D"].numpy(), cl["scales"].numpy(), cl["rotations"].numpy()
+    o = cl["opacities"].numpy() if opac is None else opac
+    if order is not None:
+        m, s, r, o, colors = m[order], s[order], r[order], o[order], colors[order]
+    return O.render_forward(pr, np.ascontiguousarray(m), np.ascontiguousarray(o), scales=np.ascontiguousarray(s),
+                            rotations=np.ascontiguousarray(r), colors_precomp=np.ascontiguousarray(colors))
+
+
+def test_oracle_image_is_linear_in_the_colours_and_affine_in_the_background():
+    cam, cl = small_scene(P=1500, W=96, H=64, scale=0.06)
+    P = 1500
+    rng = np.random.default_rng(0)
+    c1, c2 = rng.random((P, 3), dtype=np.float32), rng.random((P, 3), dtype=np.float32)
+    pr0 = cam_params(cam, P, [0, 0, 0])
+    i1 = _render_precomp(pr0, cl, c1)["img"]
+    i2 = _render_precomp(pr0, cl, c2)["img"]
+    i12 = _render_precomp(pr0, cl, (0.25 * c1 + 1.5 * c2).astype(np.float32))["img"]
+    assert np.abs(i12["color"] - (0.25 * i1["color"] + 1.5 * i2["color"])).max() < 2e-5
+    # the weights (final T, contributor counts) do not depend on the colours at all
+    assert np.array_equal(i1["final_T"], i2["final_T"]) and np.array_equal(i1["n_contrib"], i2["n_contrib"])
+    # background: image(bg) = image(0) + final_T * bg, pixel by pixel
+    bg = np.array([0.2, 0.7, 0.4], np.float32)
+    ib = _render_precomp(cam_params(cam, P, bg.tolist()), cl, c1)["img"]
+    assert np.abs(ib["color"] - (i1["color"] + i1["final_T"][None] * bg[:, None, None])).max() < 1e-6
+    assert 0.0 < i1["final_T"].min() and i1["final_T"].max() <= 1.0  # T never reaches 0: blending stops at 1e-4
+
+
+def test_oracle_image_does_not_depend_on_the_input_order_of_the_gaussians():
+    cam, cl = small_scene(P=1200, W=96, H=64, scale=0.06, seed=5)
+    P = 1200
+    rng = np.random.default_rng(1)
+    col = rng.random((P, 3), dtype=np.float32)
+    pr = cam_params(cam, P, [0.1, 0.1, 0.1])
+    a = _render_precomp(pr, cl, col)
+    perm = rng.permutation(P)
+    b = _render_precomp(pr, cl, col, order=perm)
+    # distinct depths (checked): every pixel blends the same Gaussians in the same order, so the bits agree
+    assert np.unique(a["geom"]["depths"][a["geom"]["radii"] > 0]).size == int((a["geom"]["radii"] > 0).sum())
+    assert np.array_equal(a["img"]["color"], b["img"]["color"])
+    assert np.array_equal(a["img"]["final_T"], b["img"]["final_T"]) and np.array_equal(a["img"]["n_contrib"], b["img"]["n_contrib"])
+    assert np.array_equal(a["geom"]["radii"][perm], b["geom"]["radii"])
+
+
+def test_oracle_ignores_gaussians_below_the_alpha_threshold():
+    """alpha < 1/255 never contributes (and never counts as a contributor): raising such Gaussians' opacity from
+    0 to just under the threshold leaves image and final T bit-identical; pixels are opaque-limited at alpha 0.99."""
+    cam, cl = small_scene(P=800, W=96, H=64, scale=0.07, seed=6)
+    P = 800
+    rng = np.random.default_rng(2)
+    col = rng.random((P, 3), dtype=np.float32)
+    pr = cam_params(cam, P, [0, 0, 0])
+    o = cl["opacities"].numpy().copy()
+    ghost = rng.random(P) < 0.4
+    o0, o1 = o.copy(), o.copy()
+    o0[ghost] = 0.0
+    o1[ghost] = 1.0 / 255.0 - 1e-5
+    a, b = _render_precomp(pr, cl, col, opac=o0), _render_precomp(pr, cl, col, opac=o1)
+    assert np.array_equal(a["img"]["color"], b["img"]["color"]) and np.array_equal(a["img"]["final_T"], b["img"]["final_T"])
+    # one fully opaque splat: T after it is 1 - 0.99 at its centre pixel, never 0
+    one = {k: v[:1] for k, v in cl.items()}
+    c = S.look_at_camera([2.5, 1.0, 1.2], 96, 64, fovx=0.9)
+    one["means3D"] = torch.zeros(1, 3)
+    one["scales"] = torch.full((1, 3), 0.3)
+    f = O.render_forward(cam_params(c, 1, [0, 0, 0]), one["means3D"].numpy(), np.ones((1, 1), np.float32),
+                         scales=one["scales"].numpy(), rotations=one["rotations"].numpy(),
+                         colors_precomp=np.ones((1, 3), np.float32))
+    assert abs(float(f["img"]["final_T"].min()) - 0.01) < 1e-6 and abs(float(f["img"]["color"].max()) - 0.99) < 1e-6
+
+
+def test_oracle_colour_gradient_is_the_adjoint_of_the_blend():
+    """The image is linear in the colours (weights w_i(pixel) = alpha_i T_i), so the blend backward's colour gradient
+    must be the transposed map: sum_i <dL/dc_i, c_i> = <dL/dimage, image - final_T * bg>, and the gradient of a second
+    colour set through the same geometry is the same linear functional."""
+    cam, cl = small_scene(P=1000, W=96, H=64, scale=0.06, seed=7)
+    P = 1000
+    rng = np.random.default_rng(3)
+    col = rng.random((P, 3), dtype=np.float32)
+    bg = np.array([0.3, 0.1, 0.6], np.float32)
+    pr = cam_params(cam, P, bg.tolist())
+    fwd = _render_precomp(pr, cl, col)
+    dL = rng.standard_normal((3, 64, 96)).astype(np.float32)
+    g = O.blend_backward(pr, fwd["geom"], fwd["bins"], fwd["img"], dL)
+    lhs = float((g["dL_dcolor"].astype(np.float64) * col).sum())
+    rhs = float((dL.astype(np.float64) * (fwd["img"]["color"] - fwd["img"]["final_T"][None] * bg[:, None, None])).sum())
+    assert abs(lhs - rhs) <= 2e-5 * max(abs(rhs), float(np.abs(dL).sum()) * 1e-3)
+    # the same functional applied to other colours predicts their image's inner product with dL
+    col2 = rng.random((P, 3), dtype=np.float32)
+    img2 = _render_precomp(pr, cl, col2)["img"]
+    rhs2 = float((dL.astype(np.float64) * (img2["color"] - img2["final_T"][None] * bg[:, None, None])).sum())
+    lhs2 = float((g["dL_dcolor"].astype(np.float64) * col2).sum())
+    assert abs(lhs2 - rhs2) <= 2e-5 * max(abs(rhs2), float(np.abs(dL).sum()) * 1e-3)
+    # Gaussians that reach no pixel get exactly zero
+    dead = fwd["geom"]["radii"] == 0
+    assert dead.any() and not g["dL_dcolor"][dead].any()
