@@ -301,3 +301,40 @@ def test_arith_divergence_script_small():
     assert r["visible_ours"] > 1000
     assert r["culling_decision_differs"] <= 2 and r["radius_differs"] <= r["visible_ours"] // 100
     assert r["image_max_abs_diff"] < 2e-2
+
+
+def test_full_size_colour_linearity_and_adjoint_h0():
+    """H0 shape, precomputed colours: the image is linear in the colours and affine in the background, the weights
+    (final T, contributor counts) do not depend on the colours, and the backward's colour gradient is the adjoint of
+    that linear map: sum_i <dL/dc_i, c_i> = <dL/dimage, image - final_T * bg> (the same identities the CPU oracle is held
+    to in tests/test_oracle.py)."""
+    from dmgs_b200.rasterizer import rasterize_backward, rasterize_forward
+    d, rs, P, W, H = _scene("h0")
+    gen = torch.Generator().manual_seed(3)
+    c1 = torch.rand(P, 3, generator=gen).cuda()
+    c2 = torch.rand(P, 3, generator=gen).cuda()
+    dL = torch.randn(3, H, W, generator=gen).cuda()
+    bg = rs.bg.view(3, 1, 1)
+
+    def render(col):
+        color, radii, st = rasterize_forward(rs, d["means3D"], d["opacities"], None, col.contiguous(), d["scales"],
+                                             d["rotations"], None)
+        im = st.image_arrays()
+        return color, im["final_T"].clone(), im["n_contrib"].clone(), st
+
+    i1, T1, n1, st1 = render(c1)
+    g = rasterize_backward(st1, dL, d["means3D"], None, d["scales"], d["rotations"], None, True)
+    g_col = g[3]
+    i2, T2, n2, _ = render(c2)
+    i12, _, _, _ = render(0.25 * c1 + 1.5 * c2)
+    torch.cuda.synchronize()
+    assert torch.equal(T1, T2) and torch.equal(n1, n2)
+    lin = (i12 - bg * T1) - (0.25 * (i1 - bg * T1) + 1.5 * (i2 - bg * T1))
+    assert float(lin.abs().max()) < 1e-4, float(lin.abs().max())
+    lhs = float((g_col.double() * c1.double()).sum())
+    rhs = float((dL.double() * (i1 - bg * T1).double()).sum())
+    scale = float((dL.abs().double() * (i1 - bg * T1).abs().double()).sum())
+    assert abs(lhs - rhs) <= 1e-4 * scale, (lhs, rhs, scale)
+    lhs2 = float((g_col.double() * c2.double()).sum())
+    rhs2 = float((dL.double() * (i2 - bg * T1).double()).sum())
+    assert abs(lhs2 - rhs2) <= 1e-4 * scale, (lhs2, rhs2, scale)
