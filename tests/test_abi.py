@@ -71,3 +71,32 @@ def test_no_cpu_fallback():
         FusedAdam([{"params": [torch.zeros(4)], "lr": 0.1, "name": "x"}])
     with pytest.raises(RuntimeError, match="no CPU path"):
         bind_faces(torch.zeros(3, 3), torch.zeros(1, 3, dtype=torch.int64), torch.ones(1, 3) / 3, 1.0, 1.0, None)
+
+
+def test_scheduling_knobs_are_host_only_and_leave_the_layouts_alone(so_path):
+    """dmgs_set_place_smem_kb / dmgs_set_blend_residency only steer how kernels are launched: argument ranges are
+    checked, and the caller-owned buffer sizes (which a caller may have computed before changing a knob) do not move."""
+    from dmgs_b200 import _lib
+    l = _lib.lib()
+    shapes = [(1_000_000, 7_400_000, 800, 800), (491_520, 900_000, 800, 800), (3_000_000, 4_000_000, 1245, 825),
+              (100_000, 2_000_000, 1920, 1080), (10, 40, 64, 48)]
+    try:
+        ref = [(l.dmgs_binning_bytes(*s), l.dmgs_geom_bytes(s[0]), l.dmgs_image_bytes(s[2], s[3]),
+                l.dmgs_backward_scratch_bytes(s[0])) for s in shapes]
+        for kb in (64, 100, 128, 160, 200):
+            assert l.dmgs_set_place_smem_kb(kb) == 0
+            for res in ((8, 8), (6, 6), (1, 3)):
+                assert l.dmgs_set_blend_residency(*res) == 0
+                got = [(l.dmgs_binning_bytes(*s), l.dmgs_geom_bytes(s[0]), l.dmgs_image_bytes(s[2], s[3]),
+                        l.dmgs_backward_scratch_bytes(s[0])) for s in shapes]
+                assert got == ref
+        for bad in (0, 32, 63, 201, 1024, -1):
+            assert l.dmgs_set_place_smem_kb(bad) == -7
+        for bad in ((9, 1), (1, 9), (-1, 1), (1, -1)):
+            assert l.dmgs_set_blend_residency(*bad) == -7
+        assert l.dmgs_set_blend_residency(0, 0) == 0  # 0 leaves a value unchanged
+    finally:
+        l.dmgs_set_place_smem_kb(200)
+        l.dmgs_set_blend_residency(8, 8)
+    # the scratch buffer carries the backward's square counter behind the P x 12 sums
+    assert l.dmgs_backward_scratch_bytes(1000) >= 1000 * 48 + 4
